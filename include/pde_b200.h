@@ -1,0 +1,232 @@
+/*
+ * pde_b200.h -- C ABI of the B200-native hot path of pde-engine.
+ *
+ * The reference (PimDeWitte/pde-engine) is pure Python and has NO FFI for this
+ * path: its boundary is duck-typed Python.  This header is the
+ * C-ABI a maintainer would bind with ctypes (INTEGRATION.md shows the stub);
+ * each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PDE_E_* code on failure;
+ *     pde_last_error() gives the message (thread local).  No exceptions cross
+ *     the ABI.
+ *   - "dev" pointers are device pointers on the current CUDA device, allocated
+ *     by the caller (torch tensors); "host" pointers are plain host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - opaque handles are owned by the library and freed with pde_*_free.
+ *   - one host thread per device.
+ */
+#ifndef PDE_B200_H
+#define PDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDE_B200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define PDE_OK            0
+#define PDE_E_INVALID    -1   /* bad argument */
+#define PDE_E_CUDA       -2   /* CUDA runtime error (message has the detail) */
+#define PDE_E_NOMEM      -3
+#define PDE_E_OVERFLOW   -4   /* output buffer too small / index space too large */
+#define PDE_E_NODEVICE   -5   /* no CUDA device: there is NO CPU fallback */
+
+/* ---- postfix bytecode (one byte per instruction) ------------------------ *
+ * Semantics of every opcode: expression_operations.py:11-77 as seen through
+ * sympify with the problem's locals (general_method_paper_reproduction.py:85-93,1257). */
+enum {
+    PDE_OP_END       = 0x00,
+    PDE_OP_VAR0      = 0x01,  /* rho | r */
+    PDE_OP_VAR1      = 0x02,  /* z   | x */
+    PDE_OP_PRIM0     = 0x08,  /* PRIM(p), p < 8: per-problem primitive jet table */
+    PDE_OP_ADD       = 0x10,
+    PDE_OP_SUB       = 0x11,
+    PDE_OP_MUL       = 0x12,
+    PDE_OP_DIV       = 0x13,
+    PDE_OP_NEG       = 0x18,  /* infix unary minus */
+    PDE_OP_ABS       = 0x19,  /* Abs(x) */
+    PDE_OP_SQRT      = 0x1A,  /* sqrt(x)  (EO:38-40) */
+    PDE_OP_EXP       = 0x1B,  /* exp(x)   (EO:54-56) */
+    PDE_OP_FN_NEG    = 0x20,  /* neg(x)          EO:30-32 */
+    PDE_OP_FN_INV    = 0x21,  /* inv(x)          EO:34-36 */
+    PDE_OP_FN_SQUARE = 0x22,  /* square(x)       EO:42-44 */
+    PDE_OP_FN_POW32  = 0x23,  /* pow_3_2(x)      EO:46-48 */
+    PDE_OP_FN_POWN32 = 0x24,  /* pow_neg_3_2(x)  EO:50-52 */
+    PDE_OP_FN_EXPNEG = 0x25,  /* exp_neg(x)      EO:58-60 */
+    PDE_OP_POW0      = 0x40,  /* POW(k), k < 64: x ** pow_table[k] */
+    PDE_OP_CONST0    = 0x80   /* CONST(k), k < 128: const_table[k] */
+};
+#define PDE_N_PRIM   8
+#define PDE_N_POW    64
+#define PDE_N_CONST  128
+/* reserved slots: CONST(0) = 1; POW(0) = 3/2, POW(1) = -3/2, POW(2) = 2 */
+
+/* per-expression compile flags (0 = device-evaluable) */
+#define PDE_FLAG_UNSUPPORTED 1  /* I, zoo, x**y, unknown name ... -> CPU only */
+#define PDE_FLAG_TABLE_FULL  2
+#define PDE_FLAG_TOO_LONG    4
+
+/* per-expression string predicates used by the prune rules (LBF:134-136,143-152) */
+#define PDE_ATTR_HAS_VARS    1  /* 'r' in s or 'x' in s or 'rho' in s or 'z' in s */
+#define PDE_ATTR_IS_ONE      2  /* s == '1' */
+#define PDE_ATTR_STARTS_INV  4  /* s.startswith('inv(') */
+
+/* enumerator op codes in (op, i, j) triples: the iteration order of the
+ * reference's dicts (expression_operations.py:80-106) */
+#define PDE_ENUM_N_UNARY  8   /* neg inv sqrt square pow_3_2 pow_neg_3_2 exp exp_neg */
+#define PDE_ENUM_N_BINARY 5   /* add sub mul div geom_sum (the 4 special ops emit nothing, LBF:170-195) */
+
+/* problems with a built-in residual operator */
+#define PDE_PROBLEM_FORCE_FREE 0  /* problems/force_free/validator.py:305-347, order-4 jets */
+#define PDE_PROBLEM_KERR       1  /* problems/kerr_magnetosphere/validator.py:77-91, order-2 jets */
+
+typedef struct pde_session pde_session;
+typedef struct pde_exprset pde_exprset;
+typedef struct pde_program pde_program;
+
+int         pde_abi_version(void);
+const char *pde_last_error(void);
+/* number of visible CUDA devices (0 => every compute entry point returns PDE_E_NODEVICE) */
+int         pde_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Session = the symbol table sympify works with (GM:85-93): two coordinate
+ * names, named constants with the numeric values used by the validator
+ * (KV: M_value, a_value), and the append-only constant / exponent tables the
+ * bytecode indexes.
+ * ---------------------------------------------------------------------- */
+int  pde_session_create(const char *var0, const char *var1,
+                        const char *const *const_names, const double *const_vals, int n_named,
+                        pde_session **out);
+void pde_session_free(pde_session *s);
+/* copy the current tables out (host): const_vals[PDE_N_CONST], pow_vals[PDE_N_POW] */
+int  pde_session_tables(const pde_session *s, double *const_vals, int *n_const,
+                        double *pow_vals, int *n_pow);
+/* key strings ("1", "1/3", "M", ...) of slot k, for decompilation / debugging */
+const char *pde_session_const_key(const pde_session *s, int k);
+const char *pde_session_pow_key(const pde_session *s, int k);
+
+/* ------------------------------------------------------------------------
+ * Host compiler: expression strings -> term-structured postfix bytecode.
+ * Replaces sympify(expr_str, locals) on the hot path (GM:1257) and prepares
+ * the operands of the textual splice (LBF:170-195).  Also evaluates the
+ * string predicates of the prune rules and the lexicographic rank used for
+ * the `a > b` swap (LBF:168-169).  The set is uploaded to the current device.
+ * ---------------------------------------------------------------------- */
+int  pde_compile_exprs(pde_session *s, const char *const *strs, int n, pde_exprset **out);
+void pde_exprset_free(pde_exprset *e);
+int  pde_exprset_size(const pde_exprset *e, int *n_expr, int *n_terms, int *n_pool_bytes);
+/* host copies of the compiled form:
+ *   flags[n], attrs[n], rank[n] (dense rank of the string among the set),
+ *   term_begin[n+1], term_sign[n_terms] (+1/-1), term_off[n_terms+1], pool[n_pool_bytes] */
+int  pde_exprset_export(const pde_exprset *e, uint8_t *flags, uint8_t *attrs, uint32_t *rank,
+                        uint32_t *term_begin, int8_t *term_sign, uint32_t *term_off, uint8_t *pool);
+/* "whole" programs  t1 [NEG] (tk ADD|SUB)*  into a host [n, L] array (zero padded);
+ * len[i] = 0 and flags != 0 for expressions that are not device-evaluable or longer than L */
+int  pde_exprset_programs(const pde_exprset *e, int L, uint8_t *code_host, uint8_t *len_host);
+
+/* ------------------------------------------------------------------------
+ * Stage 1: the combinatorial generator.
+ * Replaces the candidate loops of FastExpressionGenerator.stream_generate
+ * (LBF:139-195).  `e` holds E[1] ++ E[2] ++ ... ++ E[depth-1]; depth_begin has
+ * `depth` entries + 1 (depth_begin[k-1] = index of the first expression of
+ * depth k, depth_begin[depth-1] = total).
+ *
+ *   pde_enumerate_count : number of candidates the reference would append
+ *   pde_enumerate       : for each candidate, in the reference's order:
+ *       triple[c] = (op, i, j)  op 0..7 unary / 8..12 binary, i,j indices into e
+ *                               (after the add/mul swap; j = -1 for unary)
+ *       code[c, L], len[c]      spliced postfix program (len 0 = operand not
+ *                               device-compilable or program longer than L)
+ *       hash[c]                 64-bit structural hash of (len, code)
+ *   pde_dedup           : first_occurrence[c] = 1 iff no earlier candidate has
+ *                         the same program (hash match confirmed byte-wise);
+ *                         candidates with len 0 are always kept.
+ * ---------------------------------------------------------------------- */
+int  pde_enumerate_count(const pde_exprset *e, const int32_t *depth_begin, int depth, int prune,
+                         int64_t *n_candidates, void *stream);
+int  pde_enumerate(const pde_exprset *e, const int32_t *depth_begin, int depth, int prune,
+                   int64_t first, int64_t count, int L,
+                   int32_t *triple_dev, uint8_t *code_dev, uint8_t *len_dev, uint64_t *hash_dev,
+                   void *stream);
+int  pde_dedup(const uint8_t *code_dev, const uint8_t *len_dev, const uint64_t *hash_dev,
+               int64_t n, int L, uint8_t *first_occurrence_dev, int64_t *n_unique, void *stream);
+
+/* synthetic depth-d trees of SURVEY 8d (tree semantics, splitmix64 seeded per tree) */
+int  pde_synth_trees(uint64_t seed, int64_t first, int64_t count, int depth, int L,
+                     uint8_t *code_dev, uint8_t *len_dev, uint64_t *hash_dev, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Residual programs (one per problem, compiled once).
+ * Replaces the symbolic construction of det_M (FFV:305-347) / lhs (KV:77-91).
+ * `consts`: force-free none; Kerr (M, a) (KV:36-37).
+ * ---------------------------------------------------------------------- */
+int  pde_compile_residual(int problem_id, const double *consts, int n_consts, pde_program **out);
+void pde_program_free(pde_program *p);
+int  pde_program_info(const pde_program *p, int *jet_order, int *n_coef, int *n_point_cols);
+/* per-point coefficient table (host -> host): force-free [P,1] = 1/rho;
+ * Kerr [P,4] = G/(1-x^2), d_r(G/(1-x^2)), G/Delta, d_x(G/Delta)  (column major [cols][P]) */
+int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][P]*/, int P,
+                             double *table_host /*[cols][P]*/);
+
+/* ------------------------------------------------------------------------
+ * Stage 2: the batched validator.
+ * Replaces the per-candidate validate() call of emit_to_db (GM:1302-1316) and
+ * the validator worker pool (GM:1672-1824) as a *filter*: a candidate is
+ * rejected only when its residual is numerically non-zero: n_finite >= min_finite
+ * and |R| > tau * S at >= vote_frac * n_finite of the finite points (a
+ * majority vote is robust against isolated ill-conditioned points near poles);
+ * everything else survives to the CPU validator.
+ *
+ *   code[n, L], len[n]   postfix programs (len 0 = skip: survivor, n_finite 0)
+ *   pts[2][P]            collocation grid, SoA, P a multiple of 64
+ *   table[cols][P]       pde_program_point_table
+ *   prim[n_prim][n_coef][P]  jets of PRIM(p) leaves (may be NULL if unused)
+ * outputs (per candidate):
+ *   ratio_max   max |R|/S over finite points        resid_max  max |R|
+ *   scale_at    S at the arg-max of the ratio       n_finite, n_votes
+ *   ref_rs[n, n_ref, 2]  (R, S) at the first n_ref points (the reference's own
+ *                        test points, FFV:296-297 / KV:168-172); n_ref <= 4
+ *   survivor_bits[(n+31)/32]  bit c = 1 iff candidate c is NOT rejected
+ *   n_finite < 0: not evaluated (-1 empty program, -2 malformed, -3 needs more
+ *   than `spill_slots` (1..8) spilled jets) -> survivor
+ * ---------------------------------------------------------------------- */
+typedef struct pde_validate_out {
+    double   *ratio_max;     /* [n] */
+    double   *resid_max;     /* [n] */
+    double   *scale_at;      /* [n] */
+    int32_t  *n_finite;      /* [n] */
+    int32_t  *n_votes;       /* [n] */
+    double   *ref_rs;        /* [n, n_ref, 2] or NULL */
+    uint32_t *survivor_bits; /* [(n+31)/32] */
+} pde_validate_out;
+
+int  pde_validate(const pde_session *s, const pde_program *p,
+                  const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
+                  const double *pts_dev, const double *table_dev, const double *prim_dev, int P,
+                  double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
+                  const pde_validate_out *out, void *stream);
+
+/* parity / tooling entry: full per-point output for SMALL batches.
+ *   jets[n, n_coef, P] normalised Taylor coefficients of u (may be NULL)
+ *   resid[n, P], scale[n, P] (may be NULL) */
+int  pde_eval_points(const pde_session *s, const pde_program *p,
+                     const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
+                     const double *pts_dev, const double *table_dev, const double *prim_dev, int P,
+                     int spill_slots,
+                     double *jets_dev, double *resid_dev, double *scale_dev, void *stream);
+
+/* number of kernels launched by this library since load (bench "gpu_launches") */
+int64_t pde_launch_count(void);
+
+/* FP64 pipe microbenchmark: register-resident DFMA chains; returns TFLOP/s */
+int  pde_fp64_peak(int iters, double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDE_B200_H */

@@ -245,6 +245,14 @@ def whole_code(terms: Sequence[Tuple[int, bytes]]) -> bytes:
 
 
 def compile_expr(s: str, sess: Session) -> Compiled:
+    nc0, np0 = len(sess.const_keys), len(sess.pow_keys)
+    c = _compile_expr(s, sess)
+    if c.flags:  # failed compiles leave the append-only tables untouched
+        del sess.const_keys[nc0:], sess.const_vals[nc0:], sess.pow_keys[np0:], sess.pow_vals[np0:]
+    return c
+
+
+def _compile_expr(s: str, sess: Session) -> Compiled:
     try:
         ir = _to_ir(ast.parse(s.strip(), mode="eval"), sess)
         terms = []

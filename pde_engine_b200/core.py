@@ -1,0 +1,276 @@
+"""Thin Python objects over the C-ABI (include/pde_b200.h).
+
+PyTorch is used for device memory and streams only; every computation is a
+hand-written sm_100a kernel inside libpde_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+# problem ids (include/pde_b200.h)
+PROBLEM_FORCE_FREE = 0
+PROBLEM_KERR = 1
+
+N_CONST, N_POW = 128, 64
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream_ptr(stream=None) -> C.c_void_p:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def device_count() -> int:
+    return int(lib.pde_device_count())
+
+
+def launch_count() -> int:
+    return int(lib.pde_launch_count())
+
+
+class Session:
+    """Symbol / constant / exponent tables of one problem (GM:85-93)."""
+
+    def __init__(self, var_names: Tuple[str, str], named_consts: Optional[Dict[str, float]] = None):
+        named_consts = dict(named_consts or {})
+        names = (C.c_char_p * max(1, len(named_consts)))(*[k.encode() for k in named_consts])
+        vals = (C.c_double * max(1, len(named_consts)))(*[float(v) for v in named_consts.values()])
+        h = C.c_void_p()
+        check(lib.pde_session_create(var_names[0].encode(), var_names[1].encode(), names, vals, len(named_consts), C.byref(h)))
+        self._h = h
+        self.var_names = tuple(var_names)
+        self.named_consts = named_consts
+
+    @staticmethod
+    def for_problem(slug: str) -> "Session":
+        if slug in ("force_free", "forcefree", "foliation", "foliations"):
+            return Session(("rho", "z"), {})
+        if slug in ("kerr", "kerr_magnetosphere", "kerr-magnetosphere"):
+            # numeric values used by the reference's point checks: M_value=1, a_value=1/10 (PI:283)
+            return Session(("r", "x"), {"M": 1.0, "a": 0.1})
+        raise ValueError(f"Unknown problem '{slug}'")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.pde_session_free(h)
+
+    def tables(self):
+        cv = np.zeros(N_CONST)
+        pv = np.zeros(N_POW)
+        nc, npw = C.c_int(), C.c_int()
+        check(lib.pde_session_tables(self._h, cv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nc),
+                                     pv.ctypes.data_as(C.POINTER(C.c_double)), C.byref(npw)))
+        return cv, nc.value, pv, npw.value
+
+    def const_keys(self) -> List[str]:
+        n = self.tables()[1]
+        return [lib.pde_session_const_key(self._h, k).decode() for k in range(n)]
+
+    def pow_keys(self) -> List[str]:
+        n = self.tables()[3]
+        return [lib.pde_session_pow_key(self._h, k).decode() for k in range(n)]
+
+    def compile(self, strs: Sequence[str]) -> "ExprSet":
+        return ExprSet(self, strs)
+
+
+class ExprSet:
+    """Term-structured postfix bytecode of a list of expression strings."""
+
+    def __init__(self, session: Session, strs: Sequence[str]):
+        self.session = session
+        self.n = len(strs)
+        arr = (C.c_char_p * max(1, self.n))(*[s.encode() for s in strs])
+        h = C.c_void_p()
+        check(lib.pde_compile_exprs(session._h, arr, self.n, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.pde_exprset_free(h)
+
+    def sizes(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib.pde_exprset_size(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def export(self) -> Dict[str, np.ndarray]:
+        n, nt, nb = self.sizes()
+        out = {
+            "flags": np.zeros(n, np.uint8), "attrs": np.zeros(n, np.uint8), "rank": np.zeros(n, np.uint32),
+            "term_begin": np.zeros(n + 1, np.uint32), "term_sign": np.zeros(max(nt, 1), np.int8)[:nt],
+            "term_off": np.zeros(nt + 1, np.uint32), "pool": np.zeros(max(nb, 1), np.uint8)[:nb],
+        }
+        check(lib.pde_exprset_export(self._h, *[_np_ptr(out[k]) for k in
+                                                ("flags", "attrs", "rank", "term_begin", "term_sign", "term_off", "pool")]))
+        return out
+
+    def flags(self) -> np.ndarray:
+        f = np.zeros(self.n, np.uint8)
+        check(lib.pde_exprset_export(self._h, _np_ptr(f), None, None, None, None, None, None))
+        return f
+
+    def programs(self, L: int) -> Tuple[np.ndarray, np.ndarray]:
+        code = np.zeros((self.n, L), np.uint8)
+        ln = np.zeros(self.n, np.uint8)
+        check(lib.pde_exprset_programs(self._h, L, _np_ptr(code), _np_ptr(ln)))
+        return code, ln
+
+
+class ResidualProgram:
+    """A problem's PDE residual operator, compiled once (FFV:305-347 / KV:77-91)."""
+
+    def __init__(self, problem_id: int, consts: Sequence[float] = ()):
+        arr = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
+        h = C.c_void_p()
+        check(lib.pde_compile_residual(problem_id, arr, len(consts), C.byref(h)))
+        self._h = h
+        self.problem_id = problem_id
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib.pde_program_info(h, C.byref(a), C.byref(b), C.byref(c)))
+        self.order, self.n_coef, self.cols = a.value, b.value, c.value
+
+    @staticmethod
+    def for_problem(slug: str) -> "ResidualProgram":
+        if slug in ("force_free", "forcefree", "foliation", "foliations"):
+            return ResidualProgram(PROBLEM_FORCE_FREE)
+        if slug in ("kerr", "kerr_magnetosphere", "kerr-magnetosphere"):
+            return ResidualProgram(PROBLEM_KERR, (1.0, 0.1))
+        raise ValueError(f"Unknown problem '{slug}'")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.pde_program_free(h)
+
+    def point_table(self, pts: np.ndarray) -> np.ndarray:
+        """pts [2, P] float64 (SoA) -> [cols, P]"""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        assert pts.ndim == 2 and pts.shape[0] == 2
+        tab = np.zeros((self.cols, pts.shape[1]))
+        check(lib.pde_program_point_table(self._h, _np_ptr(pts), pts.shape[1], _np_ptr(tab)))
+        return tab
+
+
+# ---------------------------------------------------------------------------
+# device entry points (torch tensors as caller-allocated buffers)
+# ---------------------------------------------------------------------------
+
+def validate(session: Session, program: ResidualProgram, code, length, pts, table, prim=None, *,
+             tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, n_ref: int = 3,
+             spill_slots: int = 4, stream=None, out: Optional[dict] = None) -> dict:
+    """Stage 2 (pde_validate).  code [n, L] uint8, length [n] uint8, pts [2, P] f64,
+    table [cols, P] f64, prim [n_prim, n_coef, P] f64 or None -- all CUDA tensors."""
+    import torch
+    n, L = code.shape
+    Pn = pts.shape[1]
+    dev = code.device
+    if out is None:
+        out = {
+            "ratio_max": torch.empty(n, dtype=torch.float64, device=dev),
+            "resid_max": torch.empty(n, dtype=torch.float64, device=dev),
+            "scale_at": torch.empty(n, dtype=torch.float64, device=dev),
+            "n_finite": torch.empty(n, dtype=torch.int32, device=dev),
+            "n_votes": torch.empty(n, dtype=torch.int32, device=dev),
+            "ref_rs": torch.empty((n, n_ref, 2), dtype=torch.float64, device=dev) if n_ref else None,
+            "survivor_bits": torch.empty((n + 31) // 32, dtype=torch.int32, device=dev),
+        }
+    vo = _lib.ValidateOut(*[_dev_ptr(out[k]) for k in
+                            ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "survivor_bits")])
+    check(lib.pde_validate(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
+                           _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), Pn,
+                           float(tau), int(min_finite), float(vote_frac), int(n_ref), int(spill_slots),
+                           C.byref(vo), _stream_ptr(stream)))
+    return out
+
+
+def eval_points(session: Session, program: ResidualProgram, code, length, pts, table, prim=None, *,
+                spill_slots: int = 4, want_jets: bool = True, want_resid: bool = True, stream=None):
+    """Parity / tooling entry (pde_eval_points): full per-point jets [n, NC, P], R [n, P], S [n, P]."""
+    import torch
+    n, L = code.shape
+    Pn = pts.shape[1]
+    dev = code.device
+    jets = torch.full((n, program.n_coef, Pn), float("nan"), dtype=torch.float64, device=dev) if want_jets else None
+    resid = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
+    scale = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
+    check(lib.pde_eval_points(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
+                              _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), Pn, int(spill_slots),
+                              _dev_ptr(jets), _dev_ptr(resid), _dev_ptr(scale), _stream_ptr(stream)))
+    return jets, resid, scale
+
+
+def enumerate_count(exprs: ExprSet, depth_begin: Sequence[int], depth: int, prune: bool = True, stream=None) -> int:
+    db = (C.c_int32 * len(depth_begin))(*[int(x) for x in depth_begin])
+    n = C.c_int64()
+    check(lib.pde_enumerate_count(exprs._h, db, depth, int(prune), C.byref(n), _stream_ptr(stream)))
+    return int(n.value)
+
+
+def enumerate_candidates(exprs: ExprSet, depth_begin: Sequence[int], depth: int, prune: bool = True,
+                         first: int = 0, count: Optional[int] = None, L: int = 48, device=None, stream=None) -> dict:
+    """Stage 1 (pde_enumerate): triples, spliced programs and structural hashes of
+    candidates [first, first+count) in the reference's order."""
+    import torch
+    if count is None:
+        count = enumerate_count(exprs, depth_begin, depth, prune, stream) - first
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    out = {
+        "triple": torch.empty((count, 3), dtype=torch.int32, device=dev),
+        "code": torch.empty((count, L), dtype=torch.uint8, device=dev),
+        "len": torch.empty(count, dtype=torch.uint8, device=dev),
+        "hash": torch.empty(count, dtype=torch.int64, device=dev),
+    }
+    db = (C.c_int32 * len(depth_begin))(*[int(x) for x in depth_begin])
+    check(lib.pde_enumerate(exprs._h, db, depth, int(prune), first, count, L,
+                            _dev_ptr(out["triple"]), _dev_ptr(out["code"]), _dev_ptr(out["len"]), _dev_ptr(out["hash"]),
+                            _stream_ptr(stream)))
+    return out
+
+
+def dedup(code, length, hashes, stream=None):
+    """First-occurrence flags of exact duplicate programs (pde_dedup)."""
+    import torch
+    n, L = code.shape
+    first = torch.empty(n, dtype=torch.uint8, device=code.device)
+    nu = C.c_int64()
+    check(lib.pde_dedup(_dev_ptr(code), _dev_ptr(length), _dev_ptr(hashes), n, L, _dev_ptr(first), C.byref(nu), _stream_ptr(stream)))
+    return first, int(nu.value)
+
+
+def synth_trees(seed: int, first: int, count: int, depth: int = 5, L: int = 48, device=None, stream=None, out=None) -> dict:
+    """Synthetic depth-d trees of SURVEY 8d (pde_synth_trees)."""
+    import torch
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    if out is None:
+        out = {
+            "code": torch.empty((count, L), dtype=torch.uint8, device=dev),
+            "len": torch.empty(count, dtype=torch.uint8, device=dev),
+            "hash": torch.empty(count, dtype=torch.int64, device=dev),
+        }
+    check(lib.pde_synth_trees(C.c_uint64(seed & ((1 << 64) - 1)), first, count, depth, L,
+                              _dev_ptr(out["code"]), _dev_ptr(out["len"]), _dev_ptr(out["hash"]), _stream_ptr(stream)))
+    return out
+
+
+def fp64_peak(iters: int = 20000) -> float:
+    """Register-resident DFMA-chain microbenchmark -> TFLOP/s."""
+    t = C.c_double()
+    check(lib.pde_fp64_peak(iters, C.byref(t), _stream_ptr()))
+    return float(t.value)

@@ -1,0 +1,59 @@
+// common.h -- shared host-side definitions of libpde_b200 (error handling, handles).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/pde_b200.h"
+
+namespace pde {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(int err, const char* what);   // records message, returns PDE_E_CUDA
+void count_launch(int n = 1);
+bool have_device();
+
+#define PDE_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) return ::pde::cuda_fail((int)_e, #call);    \
+    } while (0)
+
+}  // namespace pde
+
+// ---- opaque handles ------------------------------------------------------
+struct pde_session {
+    std::string var[2];
+    std::vector<std::string> named;       // names of symbolic constants
+    std::vector<double> named_vals;
+    std::vector<std::string> const_keys;  // slot -> key
+    std::vector<double> const_vals;
+    std::vector<std::string> pow_keys;
+    std::vector<double> pow_vals;
+};
+
+struct pde_exprset {
+    int n = 0;
+    std::vector<uint8_t> flags, attrs;
+    std::vector<uint32_t> rank;
+    std::vector<uint32_t> term_begin;   // [n+1]
+    std::vector<int8_t> term_sign;      // [nt]
+    std::vector<uint32_t> term_off;     // [nt+1]
+    std::vector<uint8_t> pool;
+    // device mirrors (cudaMalloc'd by the library, on the device current at compile time)
+    int device = -1;
+    uint8_t* d_flags = nullptr;
+    uint8_t* d_attrs = nullptr;
+    uint32_t* d_rank = nullptr;
+    uint32_t* d_term_begin = nullptr;
+    int8_t* d_term_sign = nullptr;
+    uint32_t* d_term_off = nullptr;
+    uint8_t* d_pool = nullptr;
+};
+
+struct pde_program {
+    int problem = 0;
+    int order = 0;
+    int n_coef = 0;
+    int cols = 0;
+    double consts[4] = {0, 0, 0, 0};
+};

@@ -1,0 +1,346 @@
+// jet.cuh -- register-resident FP64 Taylor-mode jets, two variables, order N.
+//
+// Generalises the reference's 2nd-order forward-mode rules
+// (problems/force_free/validator.py:70-180: leaf rules 78-83, Add 102-110,
+// Mul/Leibniz 113-129, Pow 132-141, sqrt/exp 151-163) to order N.
+//
+// A jet holds NORMALISED Taylor coefficients c[idx(i,j)] = d0^i d1^j f/(i! j!),
+// idx(i,j) = n(n+1)/2 + j, n = i+j, so a product is a plain truncated
+// convolution.  Every loop below has compile-time bounds and is fully
+// unrolled: all indices are static and the jets live in registers.
+//
+// Recurrences (D = radial Euler operator, D c_g = |g| c_g):
+//   mul   c_g = sum_{b<=g} a_b b_{g-b}                         (in place, descending |g|)
+//   div   q_g = (a_g - sum_{b!=0} d_b q_{g-b}) / d_0           (in place on the numerator)
+//   sqrt  s_g = (a_g - sum_{0<b<g} s_b s_{g-b}) / (2 s_0)       (in place)
+//   exp   |g| e_g = sum_{b!=0} |b| a_b e_{g-b}
+//   pow   |g| a_0 p_g = sum_{b!=0} (k|b| - |g-b|) a_b p_{g-b}
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace pde {
+
+__host__ __device__ constexpr int jidx(int i, int j) { return (i + j) * (i + j + 1) / 2 + j; }
+
+template <int N>
+struct Jet {
+    static constexpr int NC = (N + 1) * (N + 2) / 2;
+    double c[NC];
+};
+
+template <int N>
+__device__ __forceinline__ void jet_set_const(Jet<N>& t, double v) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = 0.0;
+    t.c[0] = v;
+}
+
+template <int N>
+__device__ __forceinline__ void jet_set_var(Jet<N>& t, int k, double x) {
+    jet_set_const(t, x);
+    if (N >= 1) {
+        t.c[1] = (k == 0) ? 1.0 : 0.0;
+        t.c[2] = (k == 0) ? 0.0 : 1.0;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void jet_copy(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = u.c[g];
+}
+
+template <int N>
+__device__ __forceinline__ void jet_add(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] += u.c[g];
+}
+
+template <int N>  // t = t - u
+__device__ __forceinline__ void jet_sub(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] -= u.c[g];
+}
+
+template <int N>  // t = u - t
+__device__ __forceinline__ void jet_rsub(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = u.c[g] - t.c[g];
+}
+
+template <int N>
+__device__ __forceinline__ void jet_scale(Jet<N>& t, double s) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] *= s;
+}
+
+template <int N>
+__device__ __forceinline__ void jet_neg(Jet<N>& t) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = -t.c[g];
+}
+
+// t = t * u   (in place: descending total degree; c_g only reads t_b with b <= g)
+template <int N>
+__device__ __forceinline__ void jet_mul(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int n = N; n >= 0; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = t.c[jidx(gi, gj)] * u.c[0];
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == gi && bj == gj) continue;
+                    acc = fma(t.c[jidx(bi, bj)], u.c[jidx(gi - bi, gj - bj)], acc);
+                }
+            }
+            t.c[jidx(gi, gj)] = acc;
+        }
+    }
+}
+
+// t = t * (x_k + dx_k): multiply by a coordinate (2 non-zero coefficients)
+template <int N>
+__device__ __forceinline__ void jet_mul_var(Jet<N>& t, int k, double x) {
+#pragma unroll
+    for (int n = N; n >= 0; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = t.c[jidx(gi, gj)] * x;
+            if (k == 0) {
+                if (gi > 0) acc += t.c[jidx(gi - 1, gj)];
+            } else {
+                if (gj > 0) acc += t.c[jidx(gi, gj - 1)];
+            }
+            t.c[jidx(gi, gj)] = acc;
+        }
+    }
+}
+
+// t = t / (x_k + dx_k)
+template <int N>
+__device__ __forceinline__ void jet_div_var(Jet<N>& t, int k, double x) {
+    const double r = 1.0 / x;
+#pragma unroll
+    for (int n = 0; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = t.c[jidx(gi, gj)];
+            if (k == 0) {
+                if (gi > 0) acc -= t.c[jidx(gi - 1, gj)];
+            } else {
+                if (gj > 0) acc -= t.c[jidx(gi, gj - 1)];
+            }
+            t.c[jidx(gi, gj)] = acc * r;
+        }
+    }
+}
+
+// t = t * t
+template <int N>
+__device__ __forceinline__ void jet_square(Jet<N>& t) {
+#pragma unroll
+    for (int n = N; n >= 0; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            // pairs (b, g-b): count each unordered pair once, doubled
+            double acc = 0.0;
+            double mid = 0.0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    const int ci = gi - bi, cj = gj - bj;
+                    const int ib = jidx(bi, bj), ic = jidx(ci, cj);
+                    if (ib < ic) acc = fma(t.c[ib], t.c[ic], acc);
+                    else if (ib == ic) mid = t.c[ib] * t.c[ib];
+                }
+            }
+            t.c[jidx(gi, gj)] = fma(2.0, acc, mid);
+        }
+    }
+}
+
+// t = t / d   (in place on the numerator, ascending degree)
+template <int N>
+__device__ __forceinline__ void jet_div(Jet<N>& t, const Jet<N>& d) {
+    const double r0 = 1.0 / d.c[0];
+#pragma unroll
+    for (int n = 0; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = t.c[jidx(gi, gj)];
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    acc = fma(-d.c[jidx(bi, bj)], t.c[jidx(gi - bi, gj - bj)], acc);
+                }
+            }
+            t.c[jidx(gi, gj)] = acc * r0;
+        }
+    }
+}
+
+// t = num / t  for a scalar numerator: r_g = -r_0/num * ... ; computed into o
+template <int N>
+__device__ __forceinline__ void jet_inv(Jet<N>& o, const Jet<N>& t) {
+    const double r0 = 1.0 / t.c[0];
+    o.c[0] = r0;
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = 0.0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    acc = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], acc);
+                }
+            }
+            o.c[jidx(gi, gj)] = -r0 * acc;
+        }
+    }
+}
+
+// t = sqrt(t)  (in place, ascending degree)
+template <int N>
+__device__ __forceinline__ void jet_sqrt(Jet<N>& t) {
+    const double s0 = sqrt(t.c[0]);   // NaN for negative values: SymPy goes complex there
+    const double h = 0.5 / s0;
+    t.c[0] = s0;
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = 0.0, mid = 0.0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    const int ci = gi - bi, cj = gj - bj;
+                    if ((bi == 0 && bj == 0) || (ci == 0 && cj == 0)) continue;
+                    const int ib = jidx(bi, bj), ic = jidx(ci, cj);
+                    if (ib < ic) acc = fma(t.c[ib], t.c[ic], acc);
+                    else if (ib == ic) mid = t.c[ib] * t.c[ib];
+                }
+            }
+            t.c[jidx(gi, gj)] = (t.c[jidx(gi, gj)] - fma(2.0, acc, mid)) * h;
+        }
+    }
+}
+
+// o = exp(t); t is clobbered (pre-scaled by |b|)
+template <int N>
+__device__ __forceinline__ void jet_exp(Jet<N>& o, Jet<N>& t) {
+    o.c[0] = exp(t.c[0]);
+#pragma unroll
+    for (int n = 2; n <= N; ++n) {
+#pragma unroll
+        for (int j = 0; j <= n; ++j) t.c[jidx(n - j, j)] *= (double)n;
+    }
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc = 0.0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    acc = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], acc);
+                }
+            }
+            o.c[jidx(gi, gj)] = acc * (1.0 / (double)n);
+        }
+    }
+}
+
+// value of b0 ** k in REAL arithmetic (NaN where SymPy's principal value is complex)
+__device__ __forceinline__ double pow0(double b0, double k) {
+    const double ak = fabs(k);
+    const double ik = rint(ak);
+    if (ik == ak && ak <= 16.0) {          // integer exponent: exact products, any sign of b0
+        double r = 1.0, base = b0;
+        int e = (int)ik;
+#pragma unroll 1
+        while (e) {
+            if (e & 1) r *= base;
+            base *= base;
+            e >>= 1;
+        }
+        return k < 0 ? 1.0 / r : r;
+    }
+    const double a2 = 2.0 * ak;
+    if (rint(a2) == a2 && a2 <= 32.0) {    // half-integer: sqrt(b0)^(2k)
+        const double s = sqrt(b0);
+        double r = 1.0, base = s;
+        int e = (int)a2;
+#pragma unroll 1
+        while (e) {
+            if (e & 1) r *= base;
+            base *= base;
+            e >>= 1;
+        }
+        return k < 0 ? 1.0 / r : r;
+    }
+    return b0 >= 0.0 ? pow(b0, k) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// o = t ** k  (constant real exponent)
+template <int N>
+__device__ __forceinline__ void jet_pow(Jet<N>& o, const Jet<N>& t, double k) {
+    o.c[0] = pow0(t.c[0], k);
+    const double rb0 = 1.0 / t.c[0];
+    const double k1 = k + 1.0;
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double tot = 0.0;
+            // group by m = |b|: coefficient ((k+1) m - n)
+#pragma unroll
+            for (int m = 1; m <= n; ++m) {
+                double sm = 0.0;
+#pragma unroll
+                for (int bj = 0; bj <= m; ++bj) {
+                    const int bi = m - bj;
+                    if (bi > gi || bj > gj) continue;
+                    sm = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], sm);
+                }
+                tot = fma(k1 * (double)m - (double)n, sm, tot);
+            }
+            o.c[jidx(gi, gj)] = tot * (rb0 * (1.0 / (double)n));
+        }
+    }
+}
+
+// t = |t|   (not differentiable at 0: derivatives become NaN there)
+template <int N>
+__device__ __forceinline__ void jet_abs(Jet<N>& t) {
+    const double v = t.c[0];
+    const double s = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : __longlong_as_double(0x7ff8000000000000LL));
+#pragma unroll
+    for (int g = 1; g < Jet<N>::NC; ++g) t.c[g] *= s;
+    t.c[0] = fabs(v);
+}
+
+__host__ __device__ constexpr double factorial(int n) { return n <= 1 ? 1.0 : n * factorial(n - 1); }
+
+}  // namespace pde

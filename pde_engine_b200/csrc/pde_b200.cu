@@ -1,0 +1,283 @@
+// pde_b200.cu -- C-ABI glue: errors, sessions, residual programs, stage-2 launchers.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <cmath>
+
+#include "common.h"
+#include "validate.cuh"
+
+namespace pde {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(int err, const char* what) {
+    set_error("CUDA error %d (%s) in %s", err, cudaGetErrorString((cudaError_t)err), what);
+    return PDE_E_CUDA;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+bool have_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n > 0;
+}
+
+// ---- FP64 pipe microbenchmark: 8 independent DFMA chains per thread ----
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace pde
+
+using namespace pde;
+
+extern "C" {
+
+int pde_abi_version(void) { return PDE_B200_ABI_VERSION; }
+const char* pde_last_error(void) { return g_err; }
+int64_t pde_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pde_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------- sessions
+int pde_session_create(const char* var0, const char* var1, const char* const* const_names,
+                       const double* const_vals, int n_named, pde_session** out) {
+    if (!var0 || !var1 || !out || n_named < 0) { set_error("pde_session_create: bad argument"); return PDE_E_INVALID; }
+    pde_session* s = new pde_session();
+    s->var[0] = var0;
+    s->var[1] = var1;
+    bool has_e = false;
+    for (int i = 0; i < n_named; ++i) {
+        s->named.push_back(const_names[i]);
+        s->named_vals.push_back(const_vals[i]);
+        if (s->named.back() == "E") has_e = true;
+    }
+    if (!has_e) { s->named.push_back("E"); s->named_vals.push_back(2.718281828459045); }
+    s->const_keys = {"1"};
+    s->const_vals = {1.0};
+    s->pow_keys = {"3/2", "-3/2", "2"};
+    s->pow_vals = {1.5, -1.5, 2.0};
+    *out = s;
+    return PDE_OK;
+}
+
+void pde_session_free(pde_session* s) { delete s; }
+
+int pde_session_tables(const pde_session* s, double* const_vals, int* n_const, double* pow_vals, int* n_pow) {
+    if (!s) { set_error("null session"); return PDE_E_INVALID; }
+    if (const_vals) {
+        memset(const_vals, 0, sizeof(double) * PDE_N_CONST);
+        memcpy(const_vals, s->const_vals.data(), sizeof(double) * s->const_vals.size());
+    }
+    if (pow_vals) {
+        memset(pow_vals, 0, sizeof(double) * PDE_N_POW);
+        memcpy(pow_vals, s->pow_vals.data(), sizeof(double) * s->pow_vals.size());
+    }
+    if (n_const) *n_const = (int)s->const_vals.size();
+    if (n_pow) *n_pow = (int)s->pow_vals.size();
+    return PDE_OK;
+}
+
+const char* pde_session_const_key(const pde_session* s, int k) {
+    if (!s || k < 0 || k >= (int)s->const_keys.size()) return nullptr;
+    return s->const_keys[k].c_str();
+}
+const char* pde_session_pow_key(const pde_session* s, int k) {
+    if (!s || k < 0 || k >= (int)s->pow_keys.size()) return nullptr;
+    return s->pow_keys[k].c_str();
+}
+
+// ------------------------------------------------------- residual programs
+int pde_compile_residual(int problem_id, const double* consts, int n_consts, pde_program** out) {
+    if (!out) { set_error("null out"); return PDE_E_INVALID; }
+    pde_program* p = new pde_program();
+    p->problem = problem_id;
+    if (problem_id == PDE_PROBLEM_FORCE_FREE) {
+        p->order = 4; p->cols = 1;
+    } else if (problem_id == PDE_PROBLEM_KERR) {
+        if (n_consts < 2 || !consts) { delete p; set_error("Kerr residual needs consts (M, a)"); return PDE_E_INVALID; }
+        p->order = 2; p->cols = 4;
+        p->consts[0] = consts[0]; p->consts[1] = consts[1];
+    } else {
+        delete p;
+        set_error("unknown problem id %d", problem_id);
+        return PDE_E_INVALID;
+    }
+    p->n_coef = (p->order + 1) * (p->order + 2) / 2;
+    *out = p;
+    return PDE_OK;
+}
+
+void pde_program_free(pde_program* p) { delete p; }
+
+int pde_program_info(const pde_program* p, int* jet_order, int* n_coef, int* n_point_cols) {
+    if (!p) { set_error("null program"); return PDE_E_INVALID; }
+    if (jet_order) *jet_order = p->order;
+    if (n_coef) *n_coef = p->n_coef;
+    if (n_point_cols) *n_point_cols = p->cols;
+    return PDE_OK;
+}
+
+int pde_program_point_table(const pde_program* p, const double* pts, int P, double* tab) {
+    if (!p || !pts || !tab || P <= 0) { set_error("pde_program_point_table: bad argument"); return PDE_E_INVALID; }
+    if (p->problem == PDE_PROBLEM_FORCE_FREE) {
+        for (int i = 0; i < P; ++i) tab[i] = 1.0 / pts[i];     // w = 1/rho  (FFV:319: u_rho/rho)
+    } else {
+        // KV:69-91: Delta = r^2 - 2Mr + a^2, G = 1 - 2Mr/(r^2 + a^2 x^2)
+        const double M = p->consts[0], a = p->consts[1];
+        for (int i = 0; i < P; ++i) {
+            const double r = pts[i], x = pts[P + i];
+            const double Sg = r * r + a * a * x * x;
+            const double G = 1.0 - 2.0 * M * r / Sg;
+            const double G_r = -2.0 * M / Sg + 4.0 * M * r * r / (Sg * Sg);
+            const double G_x = 4.0 * M * r * a * a * x / (Sg * Sg);
+            const double Delta = r * r - 2.0 * M * r + a * a;
+            const double om = 1.0 - x * x;
+            tab[i] = G / om;
+            tab[P + i] = G_r / om;
+            tab[2 * (size_t)P + i] = G / Delta;
+            tab[3 * (size_t)P + i] = G_x / Delta;
+        }
+    }
+    return PDE_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------- stage 2
+static int upload_tables(const pde_session* s, cudaStream_t st) {
+    double cv[PDE_N_CONST], pv[PDE_N_POW];
+    pde_session_tables(s, cv, nullptr, pv, nullptr);
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_const, cv, sizeof(cv), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow, pv, sizeof(pv), 0, cudaMemcpyHostToDevice, st));
+    return PDE_OK;
+}
+
+template <int PROBLEM, bool DUMP>
+static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
+    constexpr int N = Residual<PROBLEM>::N;
+    const size_t smem = warp_smem_bytes<N>(vp.L, vp.ns) * kWarpsPerBlock;
+    auto kern = validate_kernel<PROBLEM, DUMP>;
+    PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, occ = 0;
+    PDE_CUDA(cudaGetDevice(&dev));
+    PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem));
+    if (occ < 1) { set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
+    long long blocks_needed = (vp.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long resident = (long long)sms * occ;    // persistent grid: a multiple of the SM count
+    int grid = (int)(blocks_needed < resident ? blocks_needed : resident);
+    if (grid < 1) grid = 1;
+    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(vp);
+    count_launch();
+    PDE_CUDA(cudaGetLastError());
+    return PDE_OK;
+}
+
+static int check_common(const pde_session* s, const pde_program* p, const void* code, const void* len,
+                        int64_t n, int L, const void* pts, const void* tab, int P, int ns) {
+    if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
+    if (!s || !p || !code || !len || !pts || !tab) { set_error("null argument"); return PDE_E_INVALID; }
+    if (n < 0 || L < 4 || L > kMaxL || (L % 4) != 0) { set_error("L must be a multiple of 4 in [4, %d]", kMaxL); return PDE_E_INVALID; }
+    if (P < 64 || (P % 64) != 0) { set_error("P must be a positive multiple of 64"); return PDE_E_INVALID; }
+    if (ns < 1 || ns > 8) { set_error("spill_slots must be in 1..8"); return PDE_E_INVALID; }
+    return PDE_OK;
+}
+
+extern "C" {
+
+int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
+                 int64_t n, int L, const double* pts, const double* tab, const double* prim, int P,
+                 double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
+                 const pde_validate_out* out, void* stream) {
+    int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
+    if (rc) return rc;
+    if (!out || !out->ratio_max || !out->resid_max || !out->scale_at || !out->n_finite || !out->n_votes || !out->survivor_bits) {
+        set_error("pde_validate: null output"); return PDE_E_INVALID;
+    }
+    if (n_ref < 0 || n_ref > 4) { set_error("n_ref must be in 0..4"); return PDE_E_INVALID; }
+    if (n == 0) return PDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = upload_tables(s, st);
+    if (rc) return rc;
+    PDE_CUDA(cudaMemsetAsync(out->survivor_bits, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
+    ValidateParams vp{};
+    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.P = P;
+    vp.ns = spill_slots; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
+    vp.ratio_max = out->ratio_max; vp.resid_max = out->resid_max; vp.scale_at = out->scale_at;
+    vp.n_finite = out->n_finite; vp.n_votes = out->n_votes; vp.ref_rs = out->ref_rs; vp.survivor_bits = out->survivor_bits;
+    if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, false>(vp, st);
+    return launch_validate<PDE_PROBLEM_KERR, false>(vp, st);
+}
+
+int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
+                    int64_t n, int L, const double* pts, const double* tab, const double* prim, int P,
+                    int spill_slots, double* jets, double* resid, double* scale, void* stream) {
+    int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
+    if (rc) return rc;
+    if (n == 0) return PDE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = upload_tables(s, st);
+    if (rc) return rc;
+    ValidateParams vp{};
+    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.P = P;
+    vp.ns = spill_slots; vp.jets = jets; vp.resid = resid; vp.scale = scale;
+    if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true>(vp, st);
+    return launch_validate<PDE_PROBLEM_KERR, true>(vp, st);
+}
+
+int pde_fp64_peak(int iters, double* tflops, void* stream) {
+    if (!have_device()) { set_error("no CUDA device"); return PDE_E_NODEVICE; }
+    if (!tflops || iters < 1) { set_error("bad argument"); return PDE_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    PDE_CUDA(cudaGetDevice(&dev));
+    PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256;
+    double* buf = nullptr;
+    PDE_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PDE_CUDA(cudaEventCreate(&e0));
+    PDE_CUDA(cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, iters / 4 + 1, 1.0000001, 1e-9);  // warm-up
+    PDE_CUDA(cudaEventRecord(e0, st));
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(buf, iters, 1.0000001, 1e-9);
+    PDE_CUDA(cudaEventRecord(e1, st));
+    count_launch(2);
+    PDE_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PDE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return PDE_OK;
+}
+
+}  // extern "C"
