@@ -1,0 +1,202 @@
+"""GpuBatchValidator -- the batched FP64 jet filter in front of a problem's
+CPU validator.
+
+Replaces the per-candidate ``validator.validate(u)`` call of ``emit_to_db``
+(general_method_paper_reproduction.py:1302-1316) and the validator worker pool
+(GM:1672-1824).  It keeps the validator protocol of problems/__init__.py:52
+(``validate(u, check_regularity=True, fast_point_only=False, **kw) -> (bool, str)``,
+optional ``describe()`` / ``last_evidence()``) so it can be assigned to
+``discovery.validator`` unchanged.
+
+Soundness: the reference accepts a candidate only when its residual is
+*identically* zero (FFV:405-427, KV:283-294).  The device rejects a candidate
+only when the float64 residual is numerically non-zero relative to its
+round-off scale S at a majority of the finite collocation points; every other
+candidate (including anything the device cannot evaluate: complex values,
+unsupported tokens, too few finite points) is handed to the wrapped CPU
+validator, whose verdict is final.  A GPU reject therefore never flips a
+reference-valid row.
+"""
+from __future__ import annotations
+
+import json
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import core
+from .grids import canonical_slug, collocation_grid
+
+
+class BatchVerdict:
+    """Host copy of one pde_validate call."""
+
+    def __init__(self, strs: Sequence[str], flags: np.ndarray, out: Dict[str, np.ndarray]):
+        self.strs = list(strs)
+        self.flags = flags
+        self.ratio_max = out["ratio_max"]
+        self.resid_max = out["resid_max"]
+        self.scale_at = out["scale_at"]
+        self.n_finite = out["n_finite"]
+        self.n_votes = out["n_votes"]
+        self.ref_rs = out["ref_rs"]
+        bits = out["survivor_bits"].view(np.uint32)
+        n = len(self.strs)
+        self.survivor = ((bits[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+
+    @property
+    def rejected(self) -> np.ndarray:
+        return ~self.survivor
+
+    def evidence(self, i: int) -> dict:
+        return {
+            "gpu_filter": "pde_engine_b200.pde_validate",
+            "n_finite": int(self.n_finite[i]), "n_votes": int(self.n_votes[i]),
+            "ratio_max": float(self.ratio_max[i]), "resid_max": float(self.resid_max[i]),
+            "scale_at_max": float(self.scale_at[i]),
+            "ref_points_R_S": None if self.ref_rs is None else [[float(v) for v in row] for row in self.ref_rs[i]],
+        }
+
+
+class GpuBatchValidator:
+    def __init__(self, cpu_validator: Any = None, problem: str = "force_free", P: int = 4096,
+                 tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, L: int = 128,
+                 spill_slots: int = 4, sympify_locals: Optional[dict] = None, device=None):
+        import torch
+        self.cpu_validator = cpu_validator
+        self.problem = canonical_slug(problem)
+        self.session = core.Session.for_problem(self.problem)
+        self.program = core.ResidualProgram.for_problem(self.problem)
+        self.P, self.tau, self.min_finite, self.vote_frac = P, tau, min_finite, vote_frac
+        self.L, self.spill_slots = L, spill_slots
+        self.sympify_locals = sympify_locals
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        pts = collocation_grid(self.problem, P)
+        self.pts_host = pts
+        self.pts = torch.from_numpy(pts).to(self.device)
+        self.table = torch.from_numpy(self.program.point_table(pts)).to(self.device)
+        self._cache: Dict[str, Tuple[bool, dict, Optional[float]]] = {}
+        self._last_evidence: dict = {}
+        self.stats = {"gpu_evaluated": 0, "gpu_rejected": 0, "cpu_confirmed": 0, "not_compilable": 0}
+        # forwarded attributes the engine reads (GM:2071-2074)
+        for name in ("monopole_target", "require_monopole_extension"):
+            if hasattr(cpu_validator, name):
+                setattr(self, name, getattr(cpu_validator, name))
+
+    # ---- batch path --------------------------------------------------------
+    def prefilter(self, expr_strs: Sequence[str]) -> BatchVerdict:
+        """GPU filter for a batch of expression strings (normalised uniques)."""
+        import torch
+        exprs = self.session.compile(list(expr_strs))
+        code, ln = exprs.programs(self.L)
+        flags = exprs.flags()
+        code_t = torch.from_numpy(code).to(self.device, non_blocking=True)
+        len_t = torch.from_numpy(ln).to(self.device, non_blocking=True)
+        out = core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
+                            tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac,
+                            n_ref=3, spill_slots=self.spill_slots)
+        host = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+        bv = BatchVerdict(expr_strs, flags, host)
+        self.stats["gpu_evaluated"] += len(bv.strs)
+        self.stats["gpu_rejected"] += int(bv.rejected.sum())
+        self.stats["not_compilable"] += int((ln == 0).sum())
+        return bv
+
+    def prefetch(self, depth: int, expr_strs: Sequence[str]) -> None:
+        """pre_batch_hook for GpuExpressionGenerator: filter a whole on_batch chunk at
+        once and remember the verdicts under the key ``validate`` will see, i.e.
+        ``str(sympify(s, locals))`` (GM:1257)."""
+        import sympy as sp
+        bv = self.prefilter(expr_strs)
+        for i, s in enumerate(bv.strs):
+            key = s
+            if self.sympify_locals is not None:
+                try:
+                    key = str(sp.sympify(s, locals=self.sympify_locals))
+                except Exception:
+                    key = s
+            r0 = None if bv.ref_rs is None else float(bv.ref_rs[i][0][0])
+            self._cache[key] = (bool(bv.survivor[i]), bv.evidence(i), r0)
+
+    def _reject_reason(self, r0: Optional[float], ev: dict) -> str:
+        if self.problem == "force_free":
+            # mirrors FFV:395 "Invalid (point check ≈ {abs(det_val):.2e})"
+            if r0 is not None and np.isfinite(r0) and r0 != 0.0:
+                return f"Invalid (point check ≈ {abs(r0):.2e})"
+            return f"Invalid (GPU residual filter: |R|/S up to {ev['ratio_max']:.2e} at {ev['n_votes']}/{ev['n_finite']} points)"
+        # mirrors KV:269
+        return (f"PDE residual != 0 (fast point check) | residual: gpu max|R|={ev['resid_max']:.3e}, "
+                f"|R|/S up to {ev['ratio_max']:.2e} at {ev['n_votes']}/{ev['n_finite']} points")
+
+    # ---- the validator protocol (PI:52) -----------------------------------
+    def validate(self, u: Any, check_regularity: bool = True, fast_point_only: bool = False, **kw) -> Tuple[bool, str]:
+        key = str(u)
+        hit = self._cache.get(key)
+        if hit is None:
+            bv = self.prefilter([key])
+            r0 = None if bv.ref_rs is None else float(bv.ref_rs[0][0][0])
+            hit = (bool(bv.survivor[0]), bv.evidence(0), r0)
+            self._cache[key] = hit
+        survivor, ev, r0 = hit
+        self._last_evidence = ev
+        if not survivor:
+            return False, self._reject_reason(r0, ev)
+        if self.cpu_validator is None:
+            return True, "GPU residual filter passed (no CPU validator attached)"
+        self.stats["cpu_confirmed"] += 1
+        try:
+            res = self.cpu_validator.validate(u, check_regularity=check_regularity, fast_point_only=fast_point_only, **kw)
+        except TypeError:   # basic validators take only the two protocol kwargs (GM:1310-1316)
+            res = self.cpu_validator.validate(u, check_regularity=check_regularity, fast_point_only=fast_point_only)
+        cpu_ev = {}
+        if hasattr(self.cpu_validator, "last_evidence"):
+            try:
+                cpu_ev = self.cpu_validator.last_evidence() or {}
+            except Exception:
+                cpu_ev = {}
+        self._last_evidence = {**cpu_ev, "gpu": ev}
+        return res
+
+    def validate_strings(self, expr_strs: Sequence[str], sympify_locals: Optional[dict] = None, **kw) -> List[Tuple[Optional[bool], str]]:
+        """Batch form of the emit_to_db inner loop (GM:1289-1339): GPU filter for the
+        whole list, CPU validator for the survivors."""
+        import sympy as sp
+        locs = sympify_locals if sympify_locals is not None else (self.sympify_locals or {})
+        bv = self.prefilter(expr_strs)
+        out: List[Tuple[Optional[bool], str]] = []
+        for i, s in enumerate(bv.strs):
+            ev = bv.evidence(i)
+            if not bv.survivor[i]:
+                r0 = None if bv.ref_rs is None else float(bv.ref_rs[i][0][0])
+                out.append((False, self._reject_reason(r0, ev)))
+                continue
+            if self.cpu_validator is None:
+                out.append((True, "GPU residual filter passed (no CPU validator attached)"))
+                continue
+            try:
+                u = sp.sympify(s, locals=locs)
+                self._cache[str(u)] = (True, ev, None)
+                out.append(self.validate(u, **kw))
+            except Exception as e:  # GM:1336-1339
+                out.append((None, f"Validator Error: {e}"))
+        return out
+
+    def describe(self) -> Dict[str, str]:
+        base = {}
+        if hasattr(self.cpu_validator, "describe"):
+            try:
+                base = self.cpu_validator.describe() or {}
+            except Exception:
+                base = {}
+        return {
+            "method_name": base.get("method_name", f"{self.__class__.__module__}.{self.__class__.__name__}.validate"),
+            "math_definition": base.get("math_definition",
+                                        "det[[L_T A, L_T B],[L_T^2 A, L_T^2 B]] = 0" if self.problem == "force_free"
+                                        else "d_r[(G/(1-x^2)) d_r u] + d_x[(G/Delta) d_x u] = 0"),
+        }
+
+    def last_evidence(self) -> dict:
+        return self._last_evidence
+
+    def _lhs(self, u):   # GM:2190-2193
+        return self.cpu_validator._lhs(u)

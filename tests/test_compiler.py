@@ -1,0 +1,71 @@
+"""Host compiler (C++) vs the oracle parser (Python ast): byte-for-byte (CPU)."""
+import numpy as np
+import pytest
+
+from conftest import uniques_by_depth
+from oracle import enumerate as oe
+from oracle import parser as op
+
+EDGE = ["I*rho", "zoo", "rho**z", "2**(1/2)*rho", "-(rho+z)", "- -rho", "+rho", "((rho))", "1/3 - 1/3*rho",
+        "rho**-2", "2**-1*z", "foo(rho)", "rho +", "(rho", "rho)", "1.5*rho", "Abs(z)", "exp(-2*z)", "-1",
+        "-rho**2*z", "E*rho", "10**30*rho", "3**40", "", "rho//z", "rho**2**2", "-rho**-2", "1/0*rho", "0**-1",
+        "rho*(-1 + 1/z)", "(rho**2*(rho - z) - z**3)/(rho - z)", "rho - -z + 1", "exp_neg(pow_3_2(rho/z))"]
+
+
+def _compare(problem, strs):
+    import pde_engine_b200 as pb
+    sess = pb.Session.for_problem(problem)
+    osess = op.Session.for_problem(problem)
+    es = sess.compile(strs)
+    ex = es.export()
+    for i, s in enumerate(strs):
+        c = op.compile_expr(s, osess)
+        assert int(ex["flags"][i]) == c.flags, s
+        if c.flags:
+            continue
+        tb, te = ex["term_begin"][i], ex["term_begin"][i + 1]
+        terms = [(int(ex["term_sign"][t]), bytes(ex["pool"][ex["term_off"][t]:ex["term_off"][t + 1]])) for t in range(tb, te)]
+        assert terms == c.terms, s
+    cv, nc, pv, npw = sess.tables()
+    assert sess.const_keys() == osess.const_keys and sess.pow_keys() == osess.pow_keys
+    assert np.array_equal(cv[:nc], np.array(osess.const_vals)) and np.array_equal(pv[:npw], np.array(osess.pow_vals))
+    return es, ex
+
+
+def test_compiler_force_free(enum_ff):
+    E = uniques_by_depth(enum_ff)
+    strs = E[1] + E[2] + E[3] + E[4][::37] + enum_ff["depths"]["2"]["candidates"] + enum_ff["depths"]["3"]["candidates"][::5] + EDGE
+    es, ex = _compare("force_free", strs)
+    # string predicates + lexicographic rank (LBF:134-136,143-152,168-169)
+    for i, s in enumerate(strs):
+        a = (1 if oe.has_vars(s) else 0) | (2 if s == "1" else 0) | (4 if s.startswith("inv(") else 0)
+        assert a == ex["attrs"][i], s
+    rk = {s: i for i, s in enumerate(sorted(set(strs)))}
+    assert all(rk[s] == ex["rank"][i] for i, s in enumerate(strs))
+    # whole programs
+    osess = op.Session.for_problem("force_free")
+    code, ln = es.programs(64)
+    for i, s in enumerate(strs[:600]):
+        c = op.compile_expr(s, osess)
+        if c.flags or len(c.whole()) > 64:
+            assert ln[i] == 0
+        else:
+            w = c.whole()
+            assert ln[i] == len(w) and bytes(code[i, :len(w)]) == w and not code[i, len(w):].any()
+
+
+def test_compiler_kerr(enum_kerr):
+    E = uniques_by_depth(enum_kerr)
+    strs = E[1] + E[2] + E[3][::9] + enum_kerr["depths"]["2"]["candidates"] + EDGE
+    _compare("kerr_magnetosphere", strs)
+
+
+def test_table_overflow_is_flagged():
+    import pde_engine_b200 as pb
+    sess = pb.Session.for_problem("force_free")
+    strs = [f"{k}*rho" for k in range(2, 200)]
+    es = sess.compile(strs)
+    fl = es.flags()
+    assert fl[:120].sum() == 0 and (fl[130:] == 2).all()        # PDE_FLAG_TABLE_FULL
+    osess = op.Session.for_problem("force_free")
+    assert [op.compile_expr(s, osess).flags for s in strs] == list(fl)

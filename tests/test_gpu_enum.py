@@ -1,0 +1,144 @@
+"""Stage 1 on the GPU vs the oracle: candidate order, spliced programs, hashes,
+first-occurrence dedup, and the full stream_generate protocol (bit-exact)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import uniques_by_depth
+from oracle import bytecode as bc
+from oracle import enumerate as oe
+from oracle import parser as op
+from oracle.normalizer import OracleNormalizer
+
+pytestmark = pytest.mark.gpu
+
+
+def _enumerate(problem, E, depth, L=128, prune=True):
+    import torch
+    import pde_engine_b200 as pb
+    sess = pb.Session.for_problem(problem)
+    flat, db = [], [0]
+    for k in range(1, depth):
+        flat += E[k]
+        db.append(len(flat))
+    es = sess.compile(flat)
+    n = pb.enumerate_count(es, db, depth, prune)
+    dev = pb.enumerate_candidates(es, db, depth, prune, 0, n, L)
+    first, nu = pb.dedup(dev["code"], dev["len"], dev["hash"])
+    torch.cuda.synchronize()
+    return flat, n, {k: v.cpu().numpy() for k, v in dev.items()}, first.cpu().numpy(), nu
+
+
+@pytest.mark.parametrize("problem,depth", [("force_free", 2), ("force_free", 3), ("kerr_magnetosphere", 2), ("kerr_magnetosphere", 3)])
+def test_candidates_bit_exact(problem, depth, cuda_device, enum_ff, enum_kerr):
+    g = enum_ff if problem == "force_free" else enum_kerr
+    E = uniques_by_depth(g)
+    flat, n, dev, first, nu = _enumerate(problem, E, depth)
+    cands, triples = oe.candidates_for_depth(E, depth, with_triples=True)
+    assert n == len(cands) == g["depths"][str(depth)]["n_candidates"]
+    assert np.array_equal(dev["triple"], np.array(triples, dtype=np.int32))
+    # rendered strings == the reference's candidate list
+    from pde_engine_b200.generator import candidate_string
+    got = [candidate_string(int(o), flat[a], flat[b] if b >= 0 else None) for o, a, b in dev["triple"]]
+    assert got == g["depths"][str(depth)]["candidates"]
+    # spliced programs + hashes == oracle splice of the oracle-compiled operands
+    osess = op.Session.for_problem(problem)
+    comp = [op.compile_expr(s, osess) for s in flat]
+    seen = {}
+    for c, (o, a, b) in enumerate(triples):
+        code = op.splice(o, comp[a], comp[b] if b >= 0 else None)
+        if code is None or len(code) > 128:
+            assert dev["len"][c] == 0
+            assert first[c] == 1
+            continue
+        assert dev["len"][c] == len(code), cands[c]
+        assert bytes(dev["code"][c, :len(code)]) == code, cands[c]
+        assert not dev["code"][c, len(code):].any()
+        assert int(dev["hash"][c]) & bc.MASK64 == bc.structural_hash(code)
+        assert bool(first[c]) == (code not in seen), cands[c]
+        seen.setdefault(code, c)
+    assert nu == int(first.sum())
+
+
+def test_depth4_candidates_checksum(cuda_device, enum_ff):
+    """Full-size: the 258 285 depth-4 force-free candidates, in order (sha256 of the
+    reference's list), and the dedup invariants at that size."""
+    from pde_engine_b200.generator import candidate_string
+    E = uniques_by_depth(enum_ff)
+    flat, n, dev, first, nu = _enumerate("force_free", E, 4)
+    rec = enum_ff["depths"]["4"]
+    assert n == rec["n_candidates"] == 258285
+    strs = [candidate_string(int(o), flat[a], flat[b] if b >= 0 else None) for o, a, b in dev["triple"]]
+    assert hashlib.sha256("\n".join(strs).encode()).hexdigest() == rec["candidates_sha256"]
+    # every dropped candidate has an earlier identical program
+    rows = {}
+    for c in range(n):
+        ln = int(dev["len"][c])
+        if ln == 0:
+            assert first[c]
+            continue
+        key = bytes(dev["code"][c, :ln])
+        assert bool(first[c]) == (key not in rows)
+        rows.setdefault(key, c)
+    # exact string duplicates are a subset of what the device drops (~19 %)
+    assert nu <= len(set(strs))
+    assert nu == int(first.sum())
+
+
+def test_windowed_enumeration_equals_full(cuda_device, enum_ff):
+    """Sharding contract: any [first, first+count) window equals the slice of the full run."""
+    import torch
+    import pde_engine_b200 as pb
+    E = uniques_by_depth(enum_ff)
+    flat, n, dev, _, _ = _enumerate("force_free", E, 3, L=48)
+    sess = pb.Session.for_problem("force_free")
+    es = sess.compile(flat)
+    db = [0, len(E[1]), len(flat)]
+    for first, count in ((0, 1), (1000, 2345), (n - 7, 7), (n // 2, n - n // 2)):
+        w = pb.enumerate_candidates(es, db, 3, True, first, count, 48)
+        torch.cuda.synchronize()
+        for k in ("triple", "code", "len", "hash"):
+            assert np.array_equal(w[k].cpu().numpy(), dev[k][first:first + count]), (k, first, count)
+
+
+def test_prune_off_counts(cuda_device, enum_ff):
+    E = uniques_by_depth(enum_ff)
+    flat, n, dev, _, _ = _enumerate("force_free", E, 2, prune=False)
+    cands = oe.candidates_for_depth(E, 2, prune=False)
+    assert n == len(cands) == 5 * 8 + 5 * 5 * 5
+
+
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_stream_generate_drop_in(problem, cuda_device, enum_ff, enum_kerr):
+    """GpuExpressionGenerator.stream_generate reproduces the reference's on_batch
+    stream (depth <= 3) with the oracle normaliser (SymPy on the CPU, memo warmed from
+    the golden candidate->normalised pairs so the test is fast; misses are computed)."""
+    from pde_engine_b200.generator import GpuExpressionGenerator, UNARY_NAMES, BINARY_NAMES, DEAD_BINARY_NAMES
+    g = enum_ff if problem == "force_free" else enum_kerr
+    norm = OracleNormalizer()
+    for d in ("2", "3"):
+        norm.preload(dict(zip(g["depths"][d]["candidates"], g["depths"][d]["normalized"])))
+    calls = []
+    gen = GpuExpressionGenerator(norm, problem)
+
+    class _Prim:   # stream_generate only calls str(p) on the primitives (LBF:127)
+        def __init__(self, s):
+            self.s = s
+
+        def __str__(self):
+            return self.s
+
+    prims = [_Prim(s) for s in g["primitives"]]
+    unary = {k: None for k in UNARY_NAMES}
+    binary = {k: None for k in BINARY_NAMES + DEAD_BINARY_NAMES}
+    gen.stream_generate(prims, unary, binary, max_depth=3, batch_size=2000,
+                        on_batch=lambda d, xs: calls.append((d, list(xs))), prune=True)
+    for d in (1, 2, 3):
+        rec = g["depths"][str(d)]
+        chunks = [xs for dd, xs in calls if dd == d]
+        assert [len(c) for c in chunks] == rec["batch_sizes"]
+        assert [s for c in chunks for s in c] == rec["uniques"]
+    assert gen.stats[3]["exact_duplicates_dropped_on_device"] > 0
+    with pytest.raises(ValueError):
+        gen.stream_generate(prims, {"neg": None}, binary, max_depth=2)

@@ -1,0 +1,81 @@
+"""Synthetic depth-5 workload: generator parity, PRIM leaves, flop table."""
+import numpy as np
+import pytest
+
+from oracle import bytecode as bc
+from oracle import jets as J
+from oracle import parser as op
+from oracle import residuals as Rz
+from oracle import synth as osyn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_synth_trees_bit_exact(cuda_device):
+    import torch
+    import pde_engine_b200 as pb
+    n = 4096
+    for depth in (1, 2, 5):
+        dev = pb.synth_trees(osyn.SEED_TREES, 100, n, depth, 48)
+        torch.cuda.synchronize()
+        code, ln, hs = dev["code"].cpu().numpy(), dev["len"].cpu().numpy(), dev["hash"].cpu().numpy()
+        want = osyn.trees(osyn.SEED_TREES, 100, n, depth)
+        for i, w in enumerate(want):
+            assert ln[i] == len(w) and bytes(code[i, :len(w)]) == w and not code[i, len(w):].any()
+            assert int(hs[i]) & bc.MASK64 == bc.structural_hash(w)
+            assert bc.stack_depth(w) >= 1
+    assert max(len(w) for w in want) <= 17
+
+
+def test_flop_table_matches_oracle(cuda_device):
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.flops import batch_flops_per_point, op_cost_table
+    for order in (4, 2):
+        t = osyn.flop_table(order)
+        mine = op_cost_table(order)
+        for b, c in t.items():
+            assert mine[b] == c, hex(b)
+    dev = pb.synth_trees(osyn.SEED_TREES, 0, 2000, 5, 48)
+    want = osyn.trees(osyn.SEED_TREES, 0, 2000, 5)
+    tab = osyn.flop_table(4)
+    total = sum(osyn.program_flops(w, tab) for w in want) + 2000 * osyn.RESIDUAL_FLOPS["force_free"]
+    assert batch_flops_per_point(dev["code"], "force_free", 4) == total
+    # SURVEY 8d expectation: 0.65-0.75 kflop per (candidate, point)
+    assert 500 < total / 2000 < 900
+
+
+def test_synth_validate_matches_oracle(cuda_device):
+    """PRIM leaves: the primitive jet table is produced by the interpreter itself
+    (pde_eval_points on the primitives' own programs) and consumed by PRIM(p)."""
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.grids import collocation_grid
+    from pde_engine_b200.synthetic import primitive_jets
+    P, n = 64, 600
+    sess = pb.Session.for_problem("force_free")
+    prog = pb.ResidualProgram.for_problem("force_free")
+    pts = collocation_grid("force_free", P)
+    pts_t = torch.from_numpy(pts).to(cuda_device)
+    tab_t = torch.from_numpy(prog.point_table(pts)).to(cuda_device)
+    prim_t = primitive_jets(sess, prog, pts_t, tab_t)
+    dev = pb.synth_trees(osyn.SEED_TREES, 0, n, 5, 48)
+    jets, resid, scale = pb.eval_points(sess, prog, dev["code"], dev["len"], pts_t, tab_t, prim_t, spill_slots=2)
+    torch.cuda.synchronize()
+    jets, resid, scale = jets.cpu().numpy(), resid.cpu().numpy(), scale.cpu().numpy()
+    osess = op.Session.for_problem("force_free")
+    opts = np.ascontiguousarray(pts.T)
+    oprim = [J.evaluate(op.compile_expr(s, osess).whole(), opts, 4, osess.const_vals, osess.pow_vals) for s in osyn.PRIM_EXPRS]
+    np.testing.assert_allclose(prim_t.cpu().numpy()[0], oprim[0], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(prim_t.cpu().numpy()[1], oprim[1], rtol=1e-13, atol=1e-15)
+    n_cmp = 0
+    for i, w in enumerate(osyn.trees(osyn.SEED_TREES, 0, n, 5)):
+        u = J.evaluate(w, opts, 4, osess.const_vals, osess.pow_vals, oprim)
+        R, S, _ = Rz.force_free_residual(u, opts[:, 0])
+        ok = np.isfinite(u).all(axis=0) & np.isfinite(jets[i]).all(axis=0)
+        mag = np.max(np.abs(u[:, ok]), axis=0) if ok.any() else 0
+        assert np.all(np.max(np.abs(jets[i][:, ok] - u[:, ok]), axis=0) <= 1e-8 * mag + 1e-300)
+        okr = ok & np.isfinite(R) & np.isfinite(S) & np.isfinite(resid[i]) & (S > 0) & np.isfinite(scale[i])
+        assert np.all(np.abs(resid[i][okr] - R[okr]) <= 1e-9 * S[okr] + 1e-300)
+        n_cmp += int(okr.sum())
+    assert n_cmp > 0.5 * n * P

@@ -1,0 +1,222 @@
+"""Parity of the CUDA jet interpreter (through the C-ABI) against the oracle and the
+reference-derived golden vectors.  Tolerance (BASELINE.json north_star): per-point
+residuals within 1e-10 relative to the residual's scale S wherever finite; u-jets
+within 1e-10 (relative to the largest coefficient magnitude of the jet)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, uniques_by_depth
+from oracle import jets as J
+from oracle import parser as op
+from oracle import residuals as Rz
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _setup(problem, P, cuda_device):
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.grids import collocation_grid
+    sess = pb.Session.for_problem(problem)
+    prog = pb.ResidualProgram.for_problem(problem)
+    pts = collocation_grid(problem, P)
+    tab = prog.point_table(pts)
+    return pb, sess, prog, pts, torch.from_numpy(pts).to(cuda_device), torch.from_numpy(tab).to(cuda_device)
+
+
+def _oracle_eval(problem, strs, pts_soa):
+    sess = op.Session.for_problem(problem)
+    order = 4 if problem == "force_free" else 2
+    pts = np.ascontiguousarray(pts_soa.T)
+    out = []
+    for s in strs:
+        c = op.compile_expr(s, sess)
+        if c.flags:
+            out.append(None)
+            continue
+        u = J.evaluate(c.whole(), pts, order, sess.const_vals, sess.pow_vals)
+        R, S, _ = (Rz.force_free_residual(u, pts[:, 0]) if problem == "force_free" else Rz.kerr_residual(u, pts))
+        out.append((u, R, S))
+    return out
+
+
+def _compare_points(jets, resid, scale, oracle, strs):
+    n_cmp = 0
+    for i, o in enumerate(oracle):
+        if o is None:
+            continue
+        u, R, S = o
+        gj, gR, gS = jets[i], resid[i], scale[i]
+        fin_o = np.isfinite(u).all(axis=0)
+        fin_g = np.isfinite(gj).all(axis=0)
+        # same finiteness pattern (the domain policy: NaN where SymPy goes complex)
+        assert (fin_o == fin_g).mean() > 0.995, strs[i]
+        ok = fin_o & fin_g
+        if not ok.any():
+            continue
+        mag = np.max(np.abs(u[:, ok]), axis=0)
+        err = np.max(np.abs(gj[:, ok] - u[:, ok]), axis=0)
+        # value + first derivatives: cancellation free -> tight; higher orders relative to the jet magnitude
+        assert np.all(np.abs(gj[:3, ok] - u[:3, ok]) <= RTOL * np.maximum(np.abs(u[:3, ok]), 1e-3 * mag + 1e-300)), strs[i]
+        assert np.all(err <= 1e-8 * mag + 1e-300), strs[i]
+        okr = ok & np.isfinite(R) & np.isfinite(S) & np.isfinite(gR) & np.isfinite(gS) & (S > 0)
+        assert np.all(np.abs(gR[okr] - R[okr]) <= RTOL * S[okr] * 10 + 1e-300), strs[i]
+        assert np.all(np.abs(gS[okr] - S[okr]) <= 1e-9 * S[okr]), strs[i]
+        n_cmp += int(okr.sum())
+    return n_cmp
+
+
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_eval_points_matches_oracle(problem, cuda_device, enum_ff, enum_kerr):
+    import torch
+    g = enum_ff if problem == "force_free" else enum_kerr
+    E = uniques_by_depth(g)
+    strs = E[1] + E[2] + E[3][::(9 if problem == "force_free" else 40)]
+    pb, sess, prog, pts, pts_t, tab_t = _setup(problem, 64, cuda_device)
+    es = sess.compile(strs)
+    code, ln = es.programs(128)
+    jets, resid, scale = pb.eval_points(sess, prog, torch.from_numpy(code).to(cuda_device), torch.from_numpy(ln).to(cuda_device),
+                                        pts_t, tab_t, None, spill_slots=8)
+    torch.cuda.synchronize()
+    oracle = _oracle_eval(problem, strs, pts)
+    n = _compare_points(jets.cpu().numpy(), resid.cpu().numpy(), scale.cpu().numpy(), oracle, strs)
+    assert n > 0.8 * 64 * len(strs) * 0.8
+
+
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_residuals_match_reference_vectors(problem, cuda_device, resid_ff, resid_kerr):
+    """CUDA residuals vs the reference's own det_M / _lhs values (evalf(50)) at the
+    golden points -- the first 8 points of the product grid."""
+    import torch
+    g = resid_ff if problem == "force_free" else resid_kerr
+    strs = [r["s"] for r in g["records"]]
+    pb, sess, prog, pts, pts_t, tab_t = _setup(problem, 64, cuda_device)
+    np.testing.assert_array_equal(pts[:, :8].T, np.array(g["points"]))
+    es = sess.compile(strs)
+    code, ln = es.programs(128)
+    assert (ln > 0).all()
+    jets, resid, scale = pb.eval_points(sess, prog, torch.from_numpy(code).to(cuda_device), torch.from_numpy(ln).to(cuda_device),
+                                        pts_t, tab_t, None, spill_slots=8)
+    resid, scale = resid.cpu().numpy(), scale.cpu().numpy()
+    n = 0
+    for i, rec in enumerate(g["records"]):
+        for k in range(8):
+            gR = rec["R"][k]
+            if gR is None or not np.isfinite(resid[i, k]):
+                continue
+            assert abs(resid[i, k] - gR) <= RTOL * scale[i, k] * 10 + 1e-300, (rec["s"], k, resid[i, k], gR, scale[i, k])
+            n += 1
+    assert n > 3000
+
+
+def test_validate_reduction_consistent_with_points(cuda_device, enum_ff):
+    """pde_validate's per-candidate outputs == reducing pde_eval_points' per-point
+    output on the host (same kernel, dump vs reduce mode)."""
+    import torch
+    E = uniques_by_depth(enum_ff)
+    strs = E[2] + E[3][::29] + ["zoo*rho", "I*sqrt(rho)"]
+    P = 256
+    pb, sess, prog, pts, pts_t, tab_t = _setup("force_free", P, cuda_device)
+    es = sess.compile(strs)
+    code, ln = es.programs(128)
+    code_t, len_t = torch.from_numpy(code).to(cuda_device), torch.from_numpy(ln).to(cuda_device)
+    tau = 1e-10
+    out = pb.validate(sess, prog, code_t, len_t, pts_t, tab_t, None, tau=tau, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=8)
+    _, resid, scale = pb.eval_points(sess, prog, code_t, len_t, pts_t, tab_t, None, spill_slots=8, want_jets=False)
+    torch.cuda.synchronize()
+    resid, scale = resid.cpu().numpy(), scale.cpu().numpy()
+    o = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    bits = o["survivor_bits"].view(np.uint32)
+    for i in range(len(strs)):
+        surv = (bits[i >> 5] >> (i & 31)) & 1
+        if ln[i] == 0:
+            assert o["n_finite"][i] == -1 and surv == 1
+            continue
+        fin = np.isfinite(resid[i]) & np.isfinite(scale[i]) & (scale[i] > 0)
+        assert o["n_finite"][i] == fin.sum()
+        votes = (np.abs(resid[i][fin]) > tau * scale[i][fin]).sum()
+        assert o["n_votes"][i] == votes
+        if fin.any():
+            ratio = np.abs(resid[i][fin]) / scale[i][fin]
+            assert o["ratio_max"][i] == ratio.max()
+            assert o["resid_max"][i] == np.abs(resid[i][fin]).max()
+        reject = fin.sum() >= 8 and votes > 0 and votes >= 0.5 * fin.sum()
+        assert surv == (0 if reject else 1)
+        for k in range(3):
+            a, b = o["ref_rs"][i, k], (resid[i, k], scale[i, k])
+            assert (a[0] == b[0] or (np.isnan(a[0]) and np.isnan(b[0]))) and (a[1] == b[1] or (np.isnan(a[1]) and np.isnan(b[1])))
+
+
+def test_filter_keeps_every_reference_valid_row(cuda_device):
+    """Golden verdicts: rows 1-85 of the reference's committed run DB (58 valid, 27
+    invalid) + its validator cache + the 6 known solutions of the sequential report.
+    The GPU filter must keep every reference-valid row (is_valid identity is
+    mandatory) and should reject the reference-invalid ones."""
+    from pde_engine_b200.validator import GpuBatchValidator
+    fx = load_golden("ref_fixtures.json")
+    rows = [r for r in fx["ff_run_db"] if r["id"] <= 85 and r["reason"] != "constant-only (skipped)"]
+    strs = [r["expression"] for r in rows]
+    want = [bool(r["is_valid"]) for r in rows]
+    for s, v, reason in fx["ff_validator_cache"]:
+        if not reason.startswith("Error"):
+            strs.append(s)
+            want.append(bool(v))
+    for r in fx["ff_sequential_report_valid"]:
+        strs.append(r["expression"])
+        want.append(True)
+    gv = GpuBatchValidator(None, "force_free", P=4096)
+    bv = gv.prefilter(strs)
+    want = np.array(want)
+    assert bv.survivor[want].all(), [s for s, w, k in zip(strs, want, bv.survivor) if w and not k]
+    # the filter is useful: the reference-invalid rows are (almost all) rejected on device
+    assert bv.rejected[~want].mean() > 0.9, [s for s, w, k in zip(strs, want, bv.survivor) if (not w) and k]
+    # valid rows have residuals at round-off level relative to the scale
+    ok = want & (bv.n_finite > 0)
+    assert np.median(bv.ratio_max[ok]) < 1e-12
+
+
+def test_kerr_primitives_rejected(cuda_device):
+    """The committed Kerr run DB rejects all 9 primitives except constants with
+    'PDE residual != 0 (fast point check)' (KV:265-271); so does the device."""
+    from pde_engine_b200.validator import GpuBatchValidator
+    fx = load_golden("ref_fixtures.json")
+    rows = fx["kerr_run_db"]
+    gv = GpuBatchValidator(None, "kerr_magnetosphere", P=4096)
+    strs = [r["expression"] for r in rows]
+    bv = gv.prefilter(strs)
+    for r, surv, nf in zip(rows, bv.survivor, bv.n_finite):
+        if r["reason"] and r["reason"].startswith("PDE residual != 0"):
+            assert not surv, r["expression"]
+        if r["is_valid"]:
+            assert surv
+
+
+def test_full_size_properties(cuda_device, enum_ff):
+    """BASELINE-size property checks (P = 4096, all 143 461 depth-4 uniques):
+    linearity of the residual scale (u -> c*u leaves |R|/S invariant), idempotence
+    (same input, same bits), and every known solution survives."""
+    import torch
+    E = uniques_by_depth(enum_ff)
+    strs = E[4]
+    pb, sess, prog, pts, pts_t, tab_t = _setup("force_free", 4096, cuda_device)
+    es = sess.compile(strs)
+    code, ln = es.programs(128)
+    code_t, len_t = torch.from_numpy(code).to(cuda_device), torch.from_numpy(ln).to(cuda_device)
+    a = pb.validate(sess, prog, code_t, len_t, pts_t, tab_t, None, spill_slots=4)
+    b = pb.validate(sess, prog, code_t, len_t, pts_t, tab_t, None, spill_slots=4)
+    torch.cuda.synchronize()
+    for k in ("ratio_max", "resid_max", "n_finite", "n_votes", "survivor_bits"):
+        x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+        assert np.array_equal(x, y, equal_nan=(x.dtype.kind == "f")), k
+    nf = a["n_finite"].cpu().numpy()
+    assert (nf >= -3).all() and (nf <= 4096).all()
+    frac_evaluated = (nf >= 0).mean()
+    assert frac_evaluated > 0.99
+    # Bent solution variants found at depth 4 survive
+    bits = a["survivor_bits"].cpu().numpy().view(np.uint32)
+    for s in ("square(rho*exp(-z))", "rho**2/pow_3_2(rho**2 + z**2)", "-z/sqrt(rho**2 + z**2) + 1"):
+        if s in strs:
+            i = strs.index(s)
+            assert (bits[i >> 5] >> (i & 31)) & 1, s
