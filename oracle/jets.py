@@ -202,8 +202,9 @@ def absj(b):
 def derivatives(j: np.ndarray, order: int) -> np.ndarray:
     """Normalised Taylor coefficients -> partial derivatives (multiply by i! j!)."""
     out = np.empty_like(j)
-    for g, (i, jj) in enumerate(multi_indices(order)):
-        out[g] = j[g] * (math.factorial(i) * math.factorial(jj))
+    with np.errstate(all="ignore"):
+        for g, (i, jj) in enumerate(multi_indices(order)):
+            out[g] = j[g] * (math.factorial(i) * math.factorial(jj))
     return out
 
 

@@ -341,6 +341,8 @@ __device__ __forceinline__ void jet_abs(Jet<N>& t) {
     t.c[0] = fabs(v);
 }
 
-__host__ __device__ constexpr double factorial(int n) { return n <= 1 ? 1.0 : n * factorial(n - 1); }
+__host__ __device__ __forceinline__ constexpr double factorial(int n) {
+    return n <= 1 ? 1.0 : n == 2 ? 2.0 : n == 3 ? 6.0 : n == 4 ? 24.0 : n == 5 ? 120.0 : 720.0;
+}
 
 }  // namespace pde

@@ -173,7 +173,10 @@ int pde_program_point_table(const pde_program* p, const double* pts, int P, doub
 static int upload_tables(const pde_session* s, cudaStream_t st) {
     double cv[PDE_N_CONST], pv[PDE_N_POW];
     pde_session_tables(s, cv, nullptr, pv, nullptr);
+    double rv[PDE_N_CONST];
+    for (int i = 0; i < PDE_N_CONST; ++i) rv[i] = 1.0 / cv[i];
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_const, cv, sizeof(cv), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconst, rv, sizeof(rv), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow, pv, sizeof(pv), 0, cudaMemcpyHostToDevice, st));
     return PDE_OK;
 }

@@ -27,13 +27,23 @@ constexpr int kMaxL = 256;
 
 // per-launch tables (warp-uniform reads -> constant cache)
 __constant__ double c_const[PDE_N_CONST];
+__constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
 __constant__ double c_pow[PDE_N_POW];
 
+// Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel (operands are
+// brought into the operand jet U by separate micro-ops) so the interpreter's code
+// stays inside the 32 KB instruction cache: an earlier version that inlined the
+// bodies per call site ran at a 75 % i-cache hit rate (profiles/r1_v1_*).
 enum UKind : uint8_t {
-    U_END = 0, U_SPILL, U_LOADT,
-    U_NEG, U_ABS, U_SQRT, U_EXP, U_INV, U_SQUARE, U_EXPNEG, U_POW,
-    U_ADD_S, U_SUB_S, U_MUL_S, U_DIV_S,
-    U_ADD_L, U_SUB_L, U_RSUB_L, U_MUL_L, U_DIV_L, U_RDIV_L
+    U_END = 0,
+    U_SPILL,                          // S[sp++] = T
+    U_MOVTU,                          // T = U
+    U_SETU_C, U_SETU_V0, U_SETU_V1,   // U = const / coordinate jet (one shared body)
+    U_LOADU_P, U_LOADU_S,             // U = primitive jet table / S[--sp]
+    U_ADD, U_SUB, U_RSUB, U_MUL, U_DIV, U_RDIV,   // T = T op U;  RSUB: U - T, RDIV: U / T
+    U_ADDC, U_SUBC, U_MULC,           // sparse leaf fast paths (arg = const slot; MULC bit7 = reciprocal)
+    U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
+    U_NEG, U_ABS, U_SQRT, U_EXP, U_SQUARE, U_POW     // EXP, POW, RDIV leave the result in U (MOVTU follows)
 };
 
 struct ValidateParams {
@@ -76,12 +86,40 @@ __device__ __forceinline__ bool op_is_unary(unsigned b) {
 constexpr uint8_t V_JET_T = 0x03;  // virtual-stack markers (unused opcode values)
 constexpr uint8_t V_JET_S = 0x04;
 
+__host__ __device__ constexpr int kUcodeMax(int L) { return 3 * L + 4; }
+
 // Postfix bytecode -> micro-ops.  Returns 0 ok, 1 malformed, 2 spill overflow.
 // Invariant: the top-most jet of the virtual stack is always T; older jets are
 // spilled in stack order, leaves never occupy a jet.
-__device__ inline int translate(const uint8_t* code, int len, uint16_t* uc, uint8_t* vst, int ns_max) {
+__device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc, uint8_t* vst, int ns_max) {
     int sp = 0, nu = 0, ns = 0, tpos = -1;
     auto emit = [&](unsigned kind, unsigned arg) { uc[nu++] = (uint16_t)((kind << 8) | arg); };
+    auto set_u = [&](unsigned leaf) {   // U = jet of a leaf
+        if (leaf >= PDE_OP_CONST0) emit(U_SETU_C, leaf - PDE_OP_CONST0);
+        else if (leaf == PDE_OP_VAR0) emit(U_SETU_V0, 0);
+        else if (leaf == PDE_OP_VAR1) emit(U_SETU_V1, 0);
+        else emit(U_LOADU_P, leaf - PDE_OP_PRIM0);
+    };
+    auto spill_t = [&]() -> bool {
+        if (tpos < 0) return true;
+        if (ns >= ns_max) return false;
+        emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
+        return true;
+    };
+    auto emit_inv = [&]() { emit(U_SETU_C, 0); emit(U_RDIV, 0); emit(U_MOVTU, 0); };   // 1 / T  (CONST(0) = 1)
+    // T = T op leaf (leaf on the right)
+    auto bin_leaf_right = [&](unsigned o, unsigned leaf) {
+        if (leaf >= PDE_OP_CONST0) {
+            const unsigned k = leaf - PDE_OP_CONST0;
+            emit(o == 0 ? U_ADDC : o == 1 ? U_SUBC : U_MULC, o == 3 ? (k | 0x80u) : k);
+        } else if (leaf == PDE_OP_VAR0 || leaf == PDE_OP_VAR1) {
+            const unsigned v = leaf - PDE_OP_VAR0;
+            emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + v, 0);
+        } else {
+            set_u(leaf);
+            emit(U_ADD + o, 0);
+        }
+    };
     for (int pc = 0; pc < len; ++pc) {
         const unsigned b = code[pc];
         if (op_is_leaf(b)) {
@@ -91,49 +129,48 @@ __device__ inline int translate(const uint8_t* code, int len, uint16_t* uc, uint
             const unsigned top = vst[sp - 1];
             if (top != V_JET_T) {
                 if (top == V_JET_S) return 1;
-                if (tpos >= 0) {
-                    if (ns >= ns_max) return 2;
-                    emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
-                }
-                emit(U_LOADT, top);
+                if (!spill_t()) return 2;
+                set_u(top); emit(U_MOVTU, 0);
                 vst[sp - 1] = V_JET_T; tpos = sp - 1;
             }
-            unsigned kind, arg = 0;
             switch (b) {
-                case PDE_OP_NEG: case PDE_OP_FN_NEG: kind = U_NEG; break;
-                case PDE_OP_ABS: kind = U_ABS; break;
-                case PDE_OP_SQRT: kind = U_SQRT; break;
-                case PDE_OP_EXP: kind = U_EXP; break;
-                case PDE_OP_FN_INV: kind = U_INV; break;
-                case PDE_OP_FN_SQUARE: kind = U_SQUARE; break;
-                case PDE_OP_FN_POW32: kind = U_POW; arg = 0; break;
-                case PDE_OP_FN_POWN32: kind = U_POW; arg = 1; break;
-                case PDE_OP_FN_EXPNEG: kind = U_EXPNEG; break;
+                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0); break;
+                case PDE_OP_ABS: emit(U_ABS, 0); break;
+                case PDE_OP_SQRT: emit(U_SQRT, 0); break;
+                case PDE_OP_EXP: emit(U_EXP, 0); emit(U_MOVTU, 0); break;
+                case PDE_OP_FN_INV: emit_inv(); break;
+                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0); break;
+                case PDE_OP_FN_POW32: emit(U_POW, 0); emit(U_MOVTU, 0); break;
+                case PDE_OP_FN_POWN32: emit(U_POW, 1); emit(U_MOVTU, 0); break;
+                case PDE_OP_FN_EXPNEG: emit(U_NEG, 0); emit(U_EXP, 0); emit(U_MOVTU, 0); break;
                 default: {
-                    arg = b - PDE_OP_POW0;
-                    const double k = c_pow[arg];
-                    kind = (k == 2.0) ? U_SQUARE : (k == 0.5) ? U_SQRT : (k == -1.0) ? U_INV : U_POW;
+                    const unsigned slot = b - PDE_OP_POW0;
+                    const double k = c_pow[slot];
+                    if (k == 2.0) emit(U_SQUARE, 0);
+                    else if (k == 0.5) emit(U_SQRT, 0);
+                    else if (k == -1.0) emit_inv();
+                    else { emit(U_POW, slot); emit(U_MOVTU, 0); }
                 }
             }
-            emit(kind, arg);
         } else if (op_is_binary(b)) {
             if (sp < 2) return 1;
             const unsigned bb = vst[sp - 1], aa = vst[sp - 2];
             sp -= 2;
             const unsigned o = b - PDE_OP_ADD;  // 0 add 1 sub 2 mul 3 div
             if (aa == V_JET_S && bb == V_JET_T) {
-                emit(U_ADD_S + o, 0); --ns;
+                emit(U_LOADU_S, 0); --ns;
+                emit(o == 0 ? U_ADD : o == 1 ? U_RSUB : o == 2 ? U_MUL : U_RDIV, 0);     // U op T
+                if (o == 3) emit(U_MOVTU, 0);
             } else if (aa == V_JET_T && bb != V_JET_S) {
-                emit(o == 0 ? U_ADD_L : o == 1 ? U_SUB_L : o == 2 ? U_MUL_L : U_DIV_L, bb);
+                bin_leaf_right(o, bb);
             } else if (bb == V_JET_T && aa != V_JET_S) {
-                emit(o == 0 ? U_ADD_L : o == 1 ? U_RSUB_L : o == 2 ? U_MUL_L : U_RDIV_L, aa);
+                if (o == 0 || o == 2) bin_leaf_right(o, aa);                  // commutative
+                else if (o == 1) { emit(U_NEG, 0); bin_leaf_right(0, aa); }   // leaf - T = -T + leaf
+                else { set_u(aa); emit(U_RDIV, 0); emit(U_MOVTU, 0); }      // leaf / T
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
-                if (tpos >= 0) {
-                    if (ns >= ns_max) return 2;
-                    emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
-                }
-                emit(U_LOADT, aa);
-                emit(o == 0 ? U_ADD_L : o == 1 ? U_SUB_L : o == 2 ? U_MUL_L : U_DIV_L, bb);
+                if (!spill_t()) return 2;
+                set_u(aa); emit(U_MOVTU, 0);
+                bin_leaf_right(o, bb);
             } else {
                 return 1;
             }
@@ -143,7 +180,7 @@ __device__ inline int translate(const uint8_t* code, int len, uint16_t* uc, uint
         }
     }
     if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) emit(U_LOADT, vst[0]);
+    if (vst[0] != V_JET_T) { set_u(vst[0]); emit(U_MOVTU, 0); }
     emit(U_END, 0);
     return 0;
 }
@@ -156,21 +193,6 @@ struct PointCtx {
     const double* prim;
 };
 
-template <int N>
-__device__ __forceinline__ void load_leaf(Jet<N>& u, unsigned leaf, const PointCtx<N>& cx) {
-    if (leaf >= PDE_OP_CONST0) {
-        jet_set_const(u, c_const[leaf - PDE_OP_CONST0]);
-    } else if (leaf == PDE_OP_VAR0) {
-        jet_set_var(u, 0, cx.x0);
-    } else if (leaf == PDE_OP_VAR1) {
-        jet_set_var(u, 1, cx.x1);
-    } else {
-        const double* src = cx.prim + (size_t)(leaf - PDE_OP_PRIM0) * Jet<N>::NC * cx.P + cx.pt;
-#pragma unroll
-        for (int g = 0; g < Jet<N>::NC; ++g) u.c[g] = __ldg(src + (size_t)g * cx.P);
-    }
-}
-
 // Interpret the micro-ops for one point: result in T.
 template <int N>
 __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, double* __restrict__ spill,
@@ -179,10 +201,11 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
     Jet<N> U;
     int sp = 0;  // spill depth
     int pc = 0;
+    unsigned ins = uc[0];
 #pragma unroll 1
     for (;;) {
-        const unsigned ins = uc[pc++];
         const unsigned kind = ins >> 8, arg = ins & 0xff;
+        ins = uc[++pc];            // prefetch the next micro-op behind this one's body
         switch (kind) {
             case U_END: return;
             case U_SPILL: {
@@ -191,61 +214,48 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
                 for (int g = 0; g < NC; ++g) dst[g * 32] = T.c[g];
                 ++sp;
             } break;
-            case U_LOADT: load_leaf(T, arg, cx); break;
-            case U_NEG: jet_neg(T); break;
-            case U_ABS: jet_abs(T); break;
-            case U_SQRT: jet_sqrt(T); break;
-            case U_EXPNEG: jet_neg(T);  // fallthrough
-            case U_EXP: jet_exp(U, T); jet_copy(T, U); break;
-            case U_INV: jet_inv(U, T); jet_copy(T, U); break;
-            case U_SQUARE: jet_square(T); break;
-            case U_POW: jet_pow(U, T, c_pow[arg]); jet_copy(T, U); break;
-            case U_ADD_S: case U_SUB_S: case U_MUL_S: case U_DIV_S: {
+            case U_SETU_C: case U_SETU_V0: case U_SETU_V1: {
+                const double v = kind == U_SETU_C ? c_const[arg] : kind == U_SETU_V0 ? cx.x0 : cx.x1;
+                jet_set_const(U, v);
+                U.c[1] = kind == U_SETU_V0 ? 1.0 : 0.0;
+                U.c[2] = kind == U_SETU_V1 ? 1.0 : 0.0;
+            } break;
+            case U_LOADU_P: {
+                const double* src = cx.prim + (size_t)arg * NC * cx.P + cx.pt;
+#pragma unroll
+                for (int g = 0; g < NC; ++g) U.c[g] = __ldg(src + (size_t)g * cx.P);
+            } break;
+            case U_LOADU_S: {
                 --sp;
                 const double* src = spill + (size_t)sp * NC * 32;
 #pragma unroll
                 for (int g = 0; g < NC; ++g) U.c[g] = src[g * 32];
-                if (kind == U_ADD_S) jet_add(T, U);
-                else if (kind == U_SUB_S) jet_rsub(T, U);          // S - T
-                else if (kind == U_MUL_S) jet_mul(T, U);
-                else { jet_div(U, T); jet_copy(T, U); }            // S / T
             } break;
-            case U_ADD_L:
-                if (arg >= PDE_OP_CONST0) T.c[0] += c_const[arg - PDE_OP_CONST0];
-                else if (arg == PDE_OP_VAR0) { T.c[0] += cx.x0; T.c[1] += 1.0; }
-                else if (arg == PDE_OP_VAR1) { T.c[0] += cx.x1; T.c[2] += 1.0; }
-                else { load_leaf(U, arg, cx); jet_add(T, U); }
-                break;
-            case U_SUB_L:
-                if (arg >= PDE_OP_CONST0) T.c[0] -= c_const[arg - PDE_OP_CONST0];
-                else if (arg == PDE_OP_VAR0) { T.c[0] -= cx.x0; T.c[1] -= 1.0; }
-                else if (arg == PDE_OP_VAR1) { T.c[0] -= cx.x1; T.c[2] -= 1.0; }
-                else { load_leaf(U, arg, cx); jet_sub(T, U); }
-                break;
-            case U_RSUB_L:
-                jet_neg(T);
-                if (arg >= PDE_OP_CONST0) T.c[0] += c_const[arg - PDE_OP_CONST0];
-                else if (arg == PDE_OP_VAR0) { T.c[0] += cx.x0; T.c[1] += 1.0; }
-                else if (arg == PDE_OP_VAR1) { T.c[0] += cx.x1; T.c[2] += 1.0; }
-                else { load_leaf(U, arg, cx); jet_add(T, U); }
-                break;
-            case U_MUL_L:
-                if (arg >= PDE_OP_CONST0) jet_scale(T, c_const[arg - PDE_OP_CONST0]);
-                else if (arg == PDE_OP_VAR0) jet_mul_var(T, 0, cx.x0);
-                else if (arg == PDE_OP_VAR1) jet_mul_var(T, 1, cx.x1);
-                else { load_leaf(U, arg, cx); jet_mul(T, U); }
-                break;
-            case U_DIV_L:
-                if (arg >= PDE_OP_CONST0) jet_scale(T, 1.0 / c_const[arg - PDE_OP_CONST0]);
-                else if (arg == PDE_OP_VAR0) jet_div_var(T, 0, cx.x0);
-                else if (arg == PDE_OP_VAR1) jet_div_var(T, 1, cx.x1);
-                else { load_leaf(U, arg, cx); jet_div(T, U); }
-                break;
-            case U_RDIV_L:
-                if (arg >= PDE_OP_CONST0) { jet_inv(U, T); jet_scale(U, c_const[arg - PDE_OP_CONST0]); }
-                else { load_leaf(U, arg, cx); jet_div(U, T); }
-                jet_copy(T, U);
-                break;
+            case U_ADD: jet_add(T, U); break;
+            case U_SUB: jet_sub(T, U); break;
+            case U_RSUB: jet_rsub(T, U); break;
+            case U_MUL: jet_mul(T, U); break;
+            case U_DIV: jet_div(T, U); break;
+            case U_ADDC: T.c[0] += c_const[arg]; break;
+            case U_SUBC: T.c[0] -= c_const[arg]; break;
+            case U_MULC: jet_scale(T, (arg & 0x80u) ? c_rconst[arg & 0x7fu] : c_const[arg]); break;
+            case U_ADDV0: T.c[0] += cx.x0; T.c[1] += 1.0; break;
+            case U_ADDV1: T.c[0] += cx.x1; T.c[2] += 1.0; break;
+            case U_SUBV0: T.c[0] -= cx.x0; T.c[1] -= 1.0; break;
+            case U_SUBV1: T.c[0] -= cx.x1; T.c[2] -= 1.0; break;
+            case U_MULV0: jet_mul_var(T, 0, cx.x0); break;
+            case U_MULV1: jet_mul_var(T, 1, cx.x1); break;
+            case U_DIVV0: jet_div_var(T, 0, cx.x0); break;
+            case U_DIVV1: jet_div_var(T, 1, cx.x1); break;
+            case U_NEG: jet_neg(T); break;
+            case U_ABS: jet_abs(T); break;
+            case U_SQRT: jet_sqrt(T); break;
+            case U_SQUARE: jet_square(T); break;
+            // out-of-place bodies leave their result in U; the translator appends MOVTU
+            case U_RDIV: jet_div(U, T); break;
+            case U_EXP: jet_exp(U, T); break;
+            case U_POW: jet_pow(U, T, c_pow[arg]); break;
+            case U_MOVTU: jet_copy(T, U); break;
             default: return;
         }
     }
@@ -291,12 +301,12 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
 
 template <int N>
 __host__ __device__ constexpr size_t warp_smem_bytes(int L, int ns) {
-    // code[L] | vstack[L] | ucode[2L+2] u16 | spill[ns][NC][32] f64   (16-byte aligned pieces)
-    return (size_t)((L + 15) / 16 * 16) * 2 + (size_t)((2 * L + 2) * 2 + 15) / 16 * 16 + (size_t)ns * Jet<N>::NC * 32 * 8;
+    // code[L] | vstack[L] | ucode[3L+4] u16 | spill[ns][NC][32] f64   (16-byte aligned pieces)
+    return (size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 2 + 15) / 16 * 16 + (size_t)ns * Jet<N>::NC * 32 * 8;
 }
 
 template <int PROBLEM, bool DUMP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PROBLEM == PDE_PROBLEM_FORCE_FREE ? 4 : 5)
 validate_kernel(const ValidateParams p) {
     using Res = Residual<PROBLEM>;
     constexpr int N = Res::N;
@@ -309,7 +319,7 @@ validate_kernel(const ValidateParams p) {
     uint8_t* s_code = base;
     uint8_t* s_vst = base + Lp;
     uint16_t* s_uc = reinterpret_cast<uint16_t*>(base + 2 * Lp);
-    double* s_spill = reinterpret_cast<double*>(base + 2 * Lp + ((2 * p.L + 2) * 2 + 15) / 16 * 16) + lane;
+    double* s_spill = reinterpret_cast<double*>(base + 2 * Lp + (kUcodeMax(p.L) * 2 + 15) / 16 * 16) + lane;
 
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long cand = (long long)blockIdx.x * kWarpsPerBlock + warp; cand < p.n; cand += nwarps) {
