@@ -117,7 +117,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
             emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + v, 0);
         } else {
             set_u(leaf);
-            emit(U_ADD + o, 0);
+            emit(o == 0 ? U_ADD : o == 1 ? U_SUB : o == 2 ? U_MUL : U_DIV, 0);
         }
     };
     for (int pc = 0; pc < len; ++pc) {
