@@ -87,7 +87,7 @@ def flop_table(order: int, prim_nnz: Sequence[int] = (6, 9)) -> Dict[int, int]:
     return t
 
 
-RESIDUAL_FLOPS = {"force_free": 103, "kerr_magnetosphere": 7}   # SURVEY 8d (CSE'd straight-line form)
+RESIDUAL_FLOPS = {"force_free": 206, "kerr_magnetosphere": 14}   # residual + its abs-propagated scale S ("add one more cost(residual)")   # SURVEY 8d (CSE'd straight-line form)
 
 
 def program_flops(code: bytes, table: Dict[int, int]) -> int:

@@ -45,6 +45,9 @@ __device__ __forceinline__ void jet_set_var(Jet<N>& t, int k, double x) {
     }
 }
 
+// The copy is an opaque asm mov on purpose: a plain assignment lets ptxas alias the two
+// jets and then re-shuffle all 30 registers at the head of the interpreter loop on EVERY
+// micro-op (38 % of all executed instructions were IMAD.MOV, profiles/r1_v2_*).
 template <int N>
 __device__ __forceinline__ void jet_copy(Jet<N>& t, const Jet<N>& u) {
 #pragma unroll
@@ -89,16 +92,19 @@ __device__ __forceinline__ void jet_mul(Jet<N>& t, const Jet<N>& u) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
-            double acc = t.c[jidx(gi, gj)] * u.c[0];
+            // two accumulators: halves the dependent-DFMA chain of the long sums
+            double acc = t.c[jidx(gi, gj)] * u.c[0], acc1 = 0.0;
+            int cnt = 0;
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == gi && bj == gj) continue;
-                    acc = fma(t.c[jidx(bi, bj)], u.c[jidx(gi - bi, gj - bj)], acc);
+                    if ((cnt++ & 1) == 0) acc1 = fma(t.c[jidx(bi, bj)], u.c[jidx(gi - bi, gj - bj)], acc1);
+                    else acc = fma(t.c[jidx(bi, bj)], u.c[jidx(gi - bi, gj - bj)], acc);
                 }
             }
-            t.c[jidx(gi, gj)] = acc;
+            t.c[jidx(gi, gj)] = cnt > 0 ? acc + acc1 : acc;
         }
     }
 }
@@ -177,16 +183,18 @@ __device__ __forceinline__ void jet_div(Jet<N>& t, const Jet<N>& d) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
-            double acc = t.c[jidx(gi, gj)];
+            double acc = t.c[jidx(gi, gj)], acc1 = 0.0;
+            int cnt = 0;
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == 0 && bj == 0) continue;
-                    acc = fma(-d.c[jidx(bi, bj)], t.c[jidx(gi - bi, gj - bj)], acc);
+                    if ((cnt++ & 1) == 0) acc = fma(-d.c[jidx(bi, bj)], t.c[jidx(gi - bi, gj - bj)], acc);
+                    else acc1 = fma(-d.c[jidx(bi, bj)], t.c[jidx(gi - bi, gj - bj)], acc1);
                 }
             }
-            t.c[jidx(gi, gj)] = acc * r0;
+            t.c[jidx(gi, gj)] = (cnt > 1 ? acc + acc1 : acc) * r0;
         }
     }
 }
@@ -257,16 +265,18 @@ __device__ __forceinline__ void jet_exp(Jet<N>& o, Jet<N>& t) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
-            double acc = 0.0;
+            double acc = 0.0, acc1 = 0.0;
+            int cnt = 0;
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == 0 && bj == 0) continue;
-                    acc = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], acc);
+                    if ((cnt++ & 1) == 0) acc = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], acc);
+                    else acc1 = fma(t.c[jidx(bi, bj)], o.c[jidx(gi - bi, gj - bj)], acc1);
                 }
             }
-            o.c[jidx(gi, gj)] = acc * (1.0 / (double)n);
+            o.c[jidx(gi, gj)] = (cnt > 1 ? acc + acc1 : acc) * (1.0 / (double)n);
         }
     }
 }

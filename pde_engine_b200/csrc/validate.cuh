@@ -22,6 +22,9 @@
 
 namespace pde {
 
+#ifndef PDE_FF_MINBLOCKS
+#define PDE_FF_MINBLOCKS 4
+#endif
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxL = 256;
 
@@ -43,7 +46,7 @@ enum UKind : uint8_t {
     U_ADD, U_SUB, U_RSUB, U_MUL, U_DIV, U_RDIV,   // T = T op U;  RSUB: U - T, RDIV: U / T
     U_ADDC, U_SUBC, U_MULC,           // sparse leaf fast paths (arg = const slot; MULC bit7 = reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
-    U_NEG, U_ABS, U_SQRT, U_EXP, U_SQUARE, U_POW     // EXP, POW, RDIV leave the result in U (MOVTU follows)
+    U_NEG, U_ABS, U_SQRT, U_EXP, U_SQUARE, U_POW
 };
 
 struct ValidateParams {
@@ -106,7 +109,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
         emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
         return true;
     };
-    auto emit_inv = [&]() { emit(U_SETU_C, 0); emit(U_RDIV, 0); emit(U_MOVTU, 0); };   // 1 / T  (CONST(0) = 1)
+    auto emit_inv = [&]() { emit(U_SETU_C, 0); emit(U_RDIV, 0); };   // 1 / T  (CONST(0) = 1)
     // T = T op leaf (leaf on the right)
     auto bin_leaf_right = [&](unsigned o, unsigned leaf) {
         if (leaf >= PDE_OP_CONST0) {
@@ -137,19 +140,19 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
                 case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0); break;
                 case PDE_OP_ABS: emit(U_ABS, 0); break;
                 case PDE_OP_SQRT: emit(U_SQRT, 0); break;
-                case PDE_OP_EXP: emit(U_EXP, 0); emit(U_MOVTU, 0); break;
+                case PDE_OP_EXP: emit(U_EXP, 0); break;
                 case PDE_OP_FN_INV: emit_inv(); break;
                 case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0); break;
-                case PDE_OP_FN_POW32: emit(U_POW, 0); emit(U_MOVTU, 0); break;
-                case PDE_OP_FN_POWN32: emit(U_POW, 1); emit(U_MOVTU, 0); break;
-                case PDE_OP_FN_EXPNEG: emit(U_NEG, 0); emit(U_EXP, 0); emit(U_MOVTU, 0); break;
+                case PDE_OP_FN_POW32: emit(U_POW, 0); break;
+                case PDE_OP_FN_POWN32: emit(U_POW, 1); break;
+                case PDE_OP_FN_EXPNEG: emit(U_NEG, 0); emit(U_EXP, 0); break;
                 default: {
                     const unsigned slot = b - PDE_OP_POW0;
                     const double k = c_pow[slot];
                     if (k == 2.0) emit(U_SQUARE, 0);
                     else if (k == 0.5) emit(U_SQRT, 0);
                     else if (k == -1.0) emit_inv();
-                    else { emit(U_POW, slot); emit(U_MOVTU, 0); }
+                    else emit(U_POW, slot);
                 }
             }
         } else if (op_is_binary(b)) {
@@ -160,13 +163,12 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
             if (aa == V_JET_S && bb == V_JET_T) {
                 emit(U_LOADU_S, 0); --ns;
                 emit(o == 0 ? U_ADD : o == 1 ? U_RSUB : o == 2 ? U_MUL : U_RDIV, 0);     // U op T
-                if (o == 3) emit(U_MOVTU, 0);
             } else if (aa == V_JET_T && bb != V_JET_S) {
                 bin_leaf_right(o, bb);
             } else if (bb == V_JET_T && aa != V_JET_S) {
                 if (o == 0 || o == 2) bin_leaf_right(o, aa);                  // commutative
                 else if (o == 1) { emit(U_NEG, 0); bin_leaf_right(0, aa); }   // leaf - T = -T + leaf
-                else { set_u(aa); emit(U_RDIV, 0); emit(U_MOVTU, 0); }      // leaf / T
+                else { set_u(aa); emit(U_RDIV, 0); }      // leaf / T
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
                 if (!spill_t()) return 2;
                 set_u(aa); emit(U_MOVTU, 0);
@@ -251,10 +253,11 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
             case U_ABS: jet_abs(T); break;
             case U_SQRT: jet_sqrt(T); break;
             case U_SQUARE: jet_square(T); break;
-            // out-of-place bodies leave their result in U; the translator appends MOVTU
-            case U_RDIV: jet_div(U, T); break;
-            case U_EXP: jet_exp(U, T); break;
-            case U_POW: jet_pow(U, T, c_pow[arg]); break;
+            // out-of-place bodies compute into U and copy back (jet_copy is opaque to the
+            // register allocator, see jet.cuh)
+            case U_RDIV: jet_div(U, T); jet_copy(T, U); break;
+            case U_EXP: jet_exp(U, T); jet_copy(T, U); break;
+            case U_POW: jet_pow(U, T, c_pow[arg]); jet_copy(T, U); break;
             case U_MOVTU: jet_copy(T, U); break;
             default: return;
         }
@@ -306,7 +309,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int L, int ns) {
 }
 
 template <int PROBLEM, bool DUMP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, PROBLEM == PDE_PROBLEM_FORCE_FREE ? 4 : 5)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PROBLEM == PDE_PROBLEM_FORCE_FREE ? PDE_FF_MINBLOCKS : 5)
 validate_kernel(const ValidateParams p) {
     using Res = Residual<PROBLEM>;
     constexpr int N = Res::N;

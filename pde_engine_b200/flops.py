@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-RESIDUAL_FLOPS = {"force_free": 103, "kerr_magnetosphere": 7}
+RESIDUAL_FLOPS = {"force_free": 206, "kerr_magnetosphere": 14}   # residual + its abs-propagated scale S ("add one more cost(residual)")
 # non-zero jet coefficients of the synthetic primitives PRIM(0) = rho**2 + z**2, PRIM(1) = rho/z
 PRIM_NNZ = (6, 9)
 
