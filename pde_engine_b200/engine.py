@@ -1,0 +1,159 @@
+"""Glue between the GPU hot path and the reference's engine.
+
+Two ways in:
+
+* ``install(discovery)`` -- the drop-in: takes the reference's
+  ``GeneralFoliationDiscovery`` instance (GM:62-132) and replaces its two
+  injection points, ``fast_generator`` (GM:107) and ``validator`` (GM:73-75),
+  with ``GpuExpressionGenerator`` / ``GpuBatchValidator``.  Everything else of
+  the reference (CLI, run database, writer/monitor processes, reports) keeps
+  running unchanged; the generator filters each ``on_batch`` chunk on the device
+  right before ``emit_to_db`` (GM:1251) sees it, so the per-row
+  ``validator.validate`` calls are cache hits that only reach the CPU validator
+  for survivors.  CUDA must be initialised inside the generator process
+  (GM:1243 rebuilds the discovery object there), so call ``install`` in that
+  process.
+
+* ``run_discovery(...)`` -- a self-contained driver with the semantics of
+  ``_parallel_generator_worker.emit_to_db`` (GM:1251-1411, inline validation)
+  and the reference's run-DB schema (GM:655-683), used by the tests and the
+  depth-4 wall-time measurement where the reference tree is not available.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import sqlite3
+import time
+from typing import Any, Callable, Dict, List, Optional
+
+from .generator import GpuExpressionGenerator
+from .validator import GpuBatchValidator
+
+
+def install(discovery: Any, P: int = 4096, **gpu_kwargs) -> Any:
+    """Swap the two hot-path objects of a reference ``GeneralFoliationDiscovery``."""
+    slug = discovery.problem.slug
+    gv = GpuBatchValidator(discovery.validator, slug, P=P, sympify_locals=dict(discovery._sympify_locals), **gpu_kwargs)
+    discovery.validator = gv
+    discovery.problem.validator = gv
+    discovery.fast_generator = GpuExpressionGenerator(discovery.normalizer, slug, pre_batch_hook=gv.prefetch)
+    return discovery
+
+
+SCHEMA = """
+CREATE TABLE IF NOT EXISTS {table} (
+    id INTEGER PRIMARY KEY AUTOINCREMENT,
+    expression TEXT NOT NULL,
+    normalized TEXT NOT NULL UNIQUE,
+    signature INTEGER,
+    depth INTEGER NOT NULL,
+    validation_status TEXT DEFAULT 'pending',
+    is_valid BOOLEAN,
+    validation_reason TEXT,
+    validator_method TEXT,
+    validator_math TEXT,
+    is_paper_solution BOOLEAN DEFAULT 0,
+    paper_solution_name TEXT,
+    created_at TIMESTAMP DEFAULT CURRENT_TIMESTAMP,
+    validated_at TIMESTAMP,
+    validator_evidence TEXT
+)"""   # GM:655-683
+
+
+def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Optional[str] = None,
+                  run_id: str = "gpu_run", db_normalize: Optional[Callable[[str], str]] = None,
+                  is_degenerate: Optional[Callable[[Any], bool]] = None, batch_size: int = 2000,
+                  match_known: bool = True) -> Dict[str, Any]:
+    """Enumerate to ``max_depth`` and validate every unique (GM:1251-1411 semantics).
+
+    spec          ProblemSpec whose ``validator`` is a GpuBatchValidator
+    normalizer    the CPU canonicaliser (``normalize_batch``)
+    db_normalize  the DB-normalisation ``str(simplify(expand(.)))`` of GM:1267-1278 (CPU,
+                  out of scope; returns None for rows the reference drops as degenerate);
+                  None = use the expression string (no DB dedup)
+    is_degenerate ``_has_degenerate_denominator`` of GM:134-199 (CPU, out of scope)
+    Returns {'rows': [...], 'stats': {...}}; rows carry the run-DB columns.
+    """
+    import sympy as sp
+    gv: GpuBatchValidator = spec.validator
+    locs = spec.sympify_locals()
+    gen = GpuExpressionGenerator(normalizer, spec.slug, pre_batch_hook=gv.prefetch)
+    rows: List[dict] = []
+    seen_norm = set()
+    t_start = time.time()
+    conn = cur = None
+    table = f"expressions_{run_id.replace('-', '_')}"
+    if db_path:
+        conn = sqlite3.connect(db_path)
+        cur = conn.cursor()
+        cur.execute(SCHEMA.format(table=table))
+    desc = gv.describe()
+    coord = list(spec.symbols.values())
+    known = {}
+    if match_known:
+        for s, name in spec.known_solutions.items():
+            try:
+                known[sp.sympify(s, locals=locs)] = name
+            except Exception:
+                pass
+
+    def emit(depth: int, expr_list: List[str]) -> None:
+        for expr_str in expr_list:
+            try:
+                u = sp.sympify(expr_str, locals=locs)                      # GM:1257
+            except Exception:
+                u = None
+            if u is not None and is_degenerate is not None and is_degenerate(u):
+                continue                                                   # GM:1261
+            normalized = db_normalize(expr_str) if db_normalize else expr_str     # GM:1267-1278
+            if normalized is None:                                         # degenerate without locals, GM:1270-1276
+                continue
+            if normalized in seen_norm:                                    # UNIQUE(normalized), GM:1407
+                continue
+            seen_norm.add(normalized)
+            sig = int(hashlib.sha256(normalized.encode()).hexdigest()[:8], 16)   # GM:1281
+            try:
+                if u is None:
+                    u = sp.sympify(expr_str, locals=locs)
+                if not any(u.has(v) for v in coord):
+                    is_valid, reason = False, "constant-only (skipped)"   # GM:1293-1294
+                else:
+                    is_valid, reason = gv.validate(u, check_regularity=False, fast_point_only=False,
+                                                   lean_first=True, defer_heavy_checks=True, enforce_anchor=False)
+                evidence = gv.last_evidence()
+            except Exception as e:                                         # GM:1336-1339
+                is_valid, reason, evidence = None, f"Validator Error: {e}", {}
+            paper = None
+            if is_valid and known:                                         # GM:1785-1798 (the worker path's matching)
+                for k_expr, name in known.items():
+                    try:
+                        if sp.simplify(u - k_expr) == 0:
+                            paper = name
+                            break
+                    except Exception:
+                        pass
+            row = dict(id=len(rows) + 1, expression=expr_str, normalized=normalized, signature=sig, depth=depth,
+                       validation_status="completed" if is_valid is not None else "error", is_valid=is_valid,
+                       validation_reason=reason, validator_method=desc.get("method_name"),
+                       validator_math=desc.get("math_definition"), is_paper_solution=int(paper is not None),
+                       paper_solution_name=paper, validator_evidence=json.dumps(evidence, default=str))
+            rows.append(row)
+            if cur is not None:
+                cur.execute(f"INSERT INTO {table} (expression, normalized, signature, depth, validation_status, is_valid,"
+                            " validation_reason, validator_method, validator_math, is_paper_solution, paper_solution_name,"
+                            " validator_evidence, validated_at) VALUES (?,?,?,?,?,?,?,?,?,?,?,?,CURRENT_TIMESTAMP)",
+                            (row["expression"], row["normalized"], row["signature"], row["depth"], row["validation_status"],
+                             row["is_valid"], row["validation_reason"], row["validator_method"], row["validator_math"],
+                             row["is_paper_solution"], row["paper_solution_name"], row["validator_evidence"]))
+        if conn is not None:
+            conn.commit()
+
+    gen.stream_generate(primitives=spec.primitives, unary_ops=spec.unary_ops, binary_ops=spec.all_binary_ops,
+                        max_depth=max_depth, batch_size=batch_size, on_batch=emit, prune=True)
+    if conn is not None:
+        conn.close()
+    stats = dict(gv.stats)
+    stats.update(rows=len(rows), valid=sum(1 for r in rows if r["is_valid"]), wall_s=time.time() - t_start,
+                 enumeration=gen.stats)
+    return {"rows": rows, "stats": stats, "table": table}
