@@ -351,6 +351,226 @@ __device__ __forceinline__ void jet_abs(Jet<N>& t) {
     t.c[0] = fabs(v);
 }
 
+
+// ---------------------------------------------------------------------------------
+// NP-point versions of the long bodies: the point index h is the INNERMOST loop, so the
+// NP independent dependency chains are interleaved in program order (NP-way ILP for
+// the in-order issue of one warp; DFMA dependent latency is 8.2 cycles, the pipe takes
+// one warp-DFMA every 2 cycles -- tools/microbench/dfma_latency.cu).
+// ---------------------------------------------------------------------------------
+#define PDE_H for (int h = 0; h < NP; ++h)
+
+template <int N, int NP>
+__device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP]) {
+#pragma unroll
+    for (int n = N; n >= 0; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], acc1[NP];
+#pragma unroll
+            PDE_H { acc[h] = t[h].c[jidx(gi, gj)] * u[h].c[0]; acc1[h] = 0.0; }
+            int cnt = 0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == gi && bj == gj) continue;
+                    if ((cnt++ & 1) == 0) {
+#pragma unroll
+                        PDE_H acc1[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc1[h]);
+                    } else {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc[h]);
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H t[h].c[jidx(gi, gj)] = cnt > 0 ? acc[h] + acc1[h] : acc[h];
+        }
+    }
+}
+
+// t = t / d (in place on the numerator)
+template <int N, int NP>
+__device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP]) {
+    double r0[NP];
+#pragma unroll
+    PDE_H r0[h] = 1.0 / d[h].c[0];
+#pragma unroll
+    for (int n = 0; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], acc1[NP];
+#pragma unroll
+            PDE_H { acc[h] = t[h].c[jidx(gi, gj)]; acc1[h] = 0.0; }
+            int cnt = 0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    if ((cnt++ & 1) == 0) {
+#pragma unroll
+                        PDE_H acc[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc[h]);
+                    } else {
+#pragma unroll
+                        PDE_H acc1[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc1[h]);
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H t[h].c[jidx(gi, gj)] = (cnt > 1 ? acc[h] + acc1[h] : acc[h]) * r0[h];
+        }
+    }
+}
+
+template <int N, int NP>
+__device__ __forceinline__ void jetv_square(Jet<N> (&t)[NP]) {
+#pragma unroll
+    for (int n = N; n >= 0; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], mid[NP];
+#pragma unroll
+            PDE_H { acc[h] = 0.0; mid[h] = 0.0; }
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    const int ib = jidx(bi, bj), ic = jidx(gi - bi, gj - bj);
+                    if (ib < ic) {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[ib], t[h].c[ic], acc[h]);
+                    } else if (ib == ic) {
+#pragma unroll
+                        PDE_H mid[h] = t[h].c[ib] * t[h].c[ib];
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H t[h].c[jidx(gi, gj)] = fma(2.0, acc[h], mid[h]);
+        }
+    }
+}
+
+template <int N, int NP>
+__device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
+    double hh[NP];
+#pragma unroll
+    PDE_H { const double s0 = sqrt(t[h].c[0]); hh[h] = 0.5 / s0; t[h].c[0] = s0; }
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], mid[NP];
+#pragma unroll
+            PDE_H { acc[h] = 0.0; mid[h] = 0.0; }
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    const int ci = gi - bi, cj = gj - bj;
+                    if ((bi == 0 && bj == 0) || (ci == 0 && cj == 0)) continue;
+                    const int ib = jidx(bi, bj), ic = jidx(ci, cj);
+                    if (ib < ic) {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[ib], t[h].c[ic], acc[h]);
+                    } else if (ib == ic) {
+#pragma unroll
+                        PDE_H mid[h] = t[h].c[ib] * t[h].c[ib];
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H t[h].c[jidx(gi, gj)] = (t[h].c[jidx(gi, gj)] - fma(2.0, acc[h], mid[h])) * hh[h];
+        }
+    }
+}
+
+// o = exp(t); t is clobbered
+template <int N, int NP>
+__device__ __forceinline__ void jetv_exp(Jet<N> (&o)[NP], Jet<N> (&t)[NP]) {
+#pragma unroll
+    PDE_H o[h].c[0] = exp(t[h].c[0]);
+#pragma unroll
+    for (int n = 2; n <= N; ++n) {
+#pragma unroll
+        for (int j = 0; j <= n; ++j) {
+#pragma unroll
+            PDE_H t[h].c[jidx(n - j, j)] *= (double)n;
+        }
+    }
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], acc1[NP];
+#pragma unroll
+            PDE_H { acc[h] = 0.0; acc1[h] = 0.0; }
+            int cnt = 0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    if ((cnt++ & 1) == 0) {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[jidx(bi, bj)], o[h].c[jidx(gi - bi, gj - bj)], acc[h]);
+                    } else {
+#pragma unroll
+                        PDE_H acc1[h] = fma(t[h].c[jidx(bi, bj)], o[h].c[jidx(gi - bi, gj - bj)], acc1[h]);
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H o[h].c[jidx(gi, gj)] = (cnt > 1 ? acc[h] + acc1[h] : acc[h]) * (1.0 / (double)n);
+        }
+    }
+}
+
+// o = t ** k
+template <int N, int NP>
+__device__ __forceinline__ void jetv_pow(Jet<N> (&o)[NP], const Jet<N> (&t)[NP], double k) {
+    double rb0[NP];
+#pragma unroll
+    PDE_H { o[h].c[0] = pow0(t[h].c[0], k); rb0[h] = 1.0 / t[h].c[0]; }
+    const double k1 = k + 1.0;
+#pragma unroll
+    for (int n = 1; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double tot[NP];
+#pragma unroll
+            PDE_H tot[h] = 0.0;
+#pragma unroll
+            for (int m = 1; m <= n; ++m) {
+                double sm[NP];
+#pragma unroll
+                PDE_H sm[h] = 0.0;
+#pragma unroll
+                for (int bj = 0; bj <= m; ++bj) {
+                    const int bi = m - bj;
+                    if (bi > gi || bj > gj) continue;
+#pragma unroll
+                    PDE_H sm[h] = fma(t[h].c[jidx(bi, bj)], o[h].c[jidx(gi - bi, gj - bj)], sm[h]);
+                }
+                const double cm = k1 * (double)m - (double)n;
+#pragma unroll
+                PDE_H tot[h] = fma(cm, sm[h], tot[h]);
+            }
+#pragma unroll
+            PDE_H o[h].c[jidx(gi, gj)] = tot[h] * (rb0[h] * (1.0 / (double)n));
+        }
+    }
+}
+#undef PDE_H
+
 __host__ __device__ __forceinline__ constexpr double factorial(int n) {
     return n <= 1 ? 1.0 : n == 2 ? 2.0 : n == 3 ? 6.0 : n == 4 ? 24.0 : n == 5 ? 120.0 : 720.0;
 }

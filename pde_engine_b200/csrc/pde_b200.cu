@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 #include <cmath>
 
@@ -181,25 +182,50 @@ static int upload_tables(const pde_session* s, cudaStream_t st) {
     return PDE_OK;
 }
 
-template <int PROBLEM, bool DUMP>
-static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
+template <int PROBLEM, bool DUMP, int W, int NP, int MINB>
+static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* fits) {
     constexpr int N = Residual<PROBLEM>::N;
-    const size_t smem = warp_smem_bytes<N>(vp.L, vp.ns) * kWarpsPerBlock;
-    auto kern = validate_kernel<PROBLEM, DUMP>;
-    PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, occ = 0;
+    const size_t smem = cta_smem_bytes<N, NP>(vp.L, vp.ns, W);
+    auto kern = validate_kernel<PROBLEM, DUMP, W, NP, MINB>;
+    int dev = 0, sms = 0, occ = 0, max_smem = 0;
     PDE_CUDA(cudaGetDevice(&dev));
     PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem));
-    if (occ < 1) { set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
-    long long blocks_needed = (vp.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    long long resident = (long long)sms * occ;    // persistent grid: a multiple of the SM count
-    int grid = (int)(blocks_needed < resident ? blocks_needed : resident);
+    PDE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)max_smem) { if (fits) { *fits = false; return PDE_OK; } set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
+    PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
+    if (occ < 1) { if (fits) { *fits = false; return PDE_OK; } set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
+    if (fits) *fits = true;
+    const long long rounds = (vp.n + W - 1) / W;
+    const long long resident = (long long)sms * occ;    // persistent grid: a multiple of the SM count
+    int grid = (int)(rounds < resident ? rounds : resident);
     if (grid < 1) grid = 1;
-    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(vp);
+    kern<<<grid, W * 32, smem, st>>>(vp);
     count_launch();
     PDE_CUDA(cudaGetLastError());
     return PDE_OK;
+}
+
+// Kernel configuration: W warps per CTA sweep a round of W candidates together.
+//   W = 16 (one 512-thread CTA per SM, 122 registers): every warp of the SM runs the same micro-op
+//          stream -> one i-cache working set per SM; needs >= 16 stripes per candidate to keep the warps busy;
+//   W = 4  (four CTAs per SM): small grids, or spill areas too large for the 16-warp CTA.
+// Two points per lane in separate registers (NP = 2) was measured SLOWER on B200 (204 registers -> 8 warps
+// per SM, or 168 with spills; i-cache hit rate 75-93 %), see DESIGN.md 4.1.  PDE_B200_VARIANT=4 forces W = 4.
+static int g_variant = -1;
+template <int PROBLEM, bool DUMP>
+static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
+    if (g_variant < 0) { const char* e = getenv("PDE_B200_VARIANT"); g_variant = e ? atoi(e) : 0; }
+    if constexpr (DUMP) {
+        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4>(vp, st, nullptr);
+    } else {
+        if (g_variant != 4 && vp.P >= 1024) {
+            bool fits = false;
+            int rc = launch_validate_cfg<PROBLEM, DUMP, 16, 1, 1>(vp, st, &fits);
+            if (rc || fits) return rc;
+        }
+        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4>(vp, st, nullptr);
+    }
 }
 
 static int check_common(const pde_session* s, const pde_program* p, const void* code, const void* len,

@@ -22,10 +22,6 @@
 
 namespace pde {
 
-#ifndef PDE_FF_MINBLOCKS
-#define PDE_FF_MINBLOCKS 4
-#endif
-constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxL = 256;
 
 // per-launch tables (warp-uniform reads -> constant cache)
@@ -42,6 +38,7 @@ enum UKind : uint8_t {
     U_SPILL,                          // S[sp++] = T
     U_MOVTU,                          // T = U
     U_SETU_C, U_SETU_V0, U_SETU_V1,   // U = const / coordinate jet (one shared body)
+    U_SETT_C, U_SETT_V0, U_SETT_V1, U_LOADT_P,   // T = leaf (first leaf of a sub-tree)
     U_LOADU_P, U_LOADU_S,             // U = primitive jet table / S[--sp]
     U_ADD, U_SUB, U_RSUB, U_MUL, U_DIV, U_RDIV,   // T = T op U;  RSUB: U - T, RDIV: U / T
     U_ADDC, U_SUBC, U_MULC,           // sparse leaf fast paths (arg = const slot; MULC bit7 = reciprocal)
@@ -103,6 +100,12 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
         else if (leaf == PDE_OP_VAR1) emit(U_SETU_V1, 0);
         else emit(U_LOADU_P, leaf - PDE_OP_PRIM0);
     };
+    auto set_t = [&](unsigned leaf) {   // T = jet of a leaf
+        if (leaf >= PDE_OP_CONST0) emit(U_SETT_C, leaf - PDE_OP_CONST0);
+        else if (leaf == PDE_OP_VAR0) emit(U_SETT_V0, 0);
+        else if (leaf == PDE_OP_VAR1) emit(U_SETT_V1, 0);
+        else emit(U_LOADT_P, leaf - PDE_OP_PRIM0);
+    };
     auto spill_t = [&]() -> bool {
         if (tpos < 0) return true;
         if (ns >= ns_max) return false;
@@ -133,7 +136,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
             if (top != V_JET_T) {
                 if (top == V_JET_S) return 1;
                 if (!spill_t()) return 2;
-                set_u(top); emit(U_MOVTU, 0);
+                set_t(top);
                 vst[sp - 1] = V_JET_T; tpos = sp - 1;
             }
             switch (b) {
@@ -171,7 +174,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
                 else { set_u(aa); emit(U_RDIV, 0); }      // leaf / T
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
                 if (!spill_t()) return 2;
-                set_u(aa); emit(U_MOVTU, 0);
+                set_t(aa);
                 bin_leaf_right(o, bb);
             } else {
                 return 1;
@@ -182,7 +185,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
         }
     }
     if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) { set_u(vst[0]); emit(U_MOVTU, 0); }
+    if (vst[0] != V_JET_T) set_t(vst[0]);
     emit(U_END, 0);
     return 0;
 }
@@ -195,15 +198,19 @@ struct PointCtx {
     const double* prim;
 };
 
-// Interpret the micro-ops for one point: result in T.
-template <int N>
-__device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, double* __restrict__ spill,
-                                            const PointCtx<N>& cx, Jet<N>& T) {
+// Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
+// The NP jets are independent, which gives the scheduler NP-way instruction-level
+// parallelism inside every body and amortises the dispatch over NP points.
+// Spill layout: [(slot * NC + coef) * NP + point][thread]  (conflict free).
+template <int N, int NP>
+__device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, double* __restrict__ spill, int stride,
+                                            const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
     constexpr int NC = Jet<N>::NC;
-    Jet<N> U;
+    Jet<N> U[NP];
     int sp = 0;  // spill depth
     int pc = 0;
     unsigned ins = uc[0];
+#define PDE_EACH for (int h = 0; h < NP; ++h)
 #pragma unroll 1
     for (;;) {
         const unsigned kind = ins >> 8, arg = ins & 0xff;
@@ -211,57 +218,151 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
         switch (kind) {
             case U_END: return;
             case U_SPILL: {
-                double* dst = spill + (size_t)sp * NC * 32;
+                double* dst = spill + (size_t)sp * NC * NP * stride;
 #pragma unroll
-                for (int g = 0; g < NC; ++g) dst[g * 32] = T.c[g];
+                PDE_EACH {
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) dst[(g * NP + h) * stride] = T[h].c[g];
+                }
                 ++sp;
             } break;
             case U_SETU_C: case U_SETU_V0: case U_SETU_V1: {
-                const double v = kind == U_SETU_C ? c_const[arg] : kind == U_SETU_V0 ? cx.x0 : cx.x1;
-                jet_set_const(U, v);
-                U.c[1] = kind == U_SETU_V0 ? 1.0 : 0.0;
-                U.c[2] = kind == U_SETU_V1 ? 1.0 : 0.0;
+#pragma unroll
+                PDE_EACH {
+                    const double v = kind == U_SETU_C ? c_const[arg] : kind == U_SETU_V0 ? cx[h].x0 : cx[h].x1;
+                    jet_set_const(U[h], v);
+                    U[h].c[1] = kind == U_SETU_V0 ? 1.0 : 0.0;
+                    U[h].c[2] = kind == U_SETU_V1 ? 1.0 : 0.0;
+                }
             } break;
             case U_LOADU_P: {
-                const double* src = cx.prim + (size_t)arg * NC * cx.P + cx.pt;
 #pragma unroll
-                for (int g = 0; g < NC; ++g) U.c[g] = __ldg(src + (size_t)g * cx.P);
+                PDE_EACH {
+                    const double* src = cx[h].prim + (size_t)arg * NC * cx[h].P + cx[h].pt;
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(src + (size_t)g * cx[h].P);
+                }
+            } break;
+            case U_SETT_C: case U_SETT_V0: case U_SETT_V1: {
+#pragma unroll
+                PDE_EACH {
+                    const double v = kind == U_SETT_C ? c_const[arg] : kind == U_SETT_V0 ? cx[h].x0 : cx[h].x1;
+                    jet_set_const(T[h], v);
+                    T[h].c[1] = kind == U_SETT_V0 ? 1.0 : 0.0;
+                    T[h].c[2] = kind == U_SETT_V1 ? 1.0 : 0.0;
+                }
+            } break;
+            case U_LOADT_P: {
+#pragma unroll
+                PDE_EACH {
+                    const double* src = cx[h].prim + (size_t)arg * NC * cx[h].P + cx[h].pt;
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(src + (size_t)g * cx[h].P);
+                }
             } break;
             case U_LOADU_S: {
                 --sp;
-                const double* src = spill + (size_t)sp * NC * 32;
+                const double* src = spill + (size_t)sp * NC * NP * stride;
 #pragma unroll
-                for (int g = 0; g < NC; ++g) U.c[g] = src[g * 32];
+                PDE_EACH {
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) U[h].c[g] = src[(g * NP + h) * stride];
+                }
             } break;
-            case U_ADD: jet_add(T, U); break;
-            case U_SUB: jet_sub(T, U); break;
-            case U_RSUB: jet_rsub(T, U); break;
-            case U_MUL: jet_mul(T, U); break;
-            case U_DIV: jet_div(T, U); break;
-            case U_ADDC: T.c[0] += c_const[arg]; break;
-            case U_SUBC: T.c[0] -= c_const[arg]; break;
-            case U_MULC: jet_scale(T, (arg & 0x80u) ? c_rconst[arg & 0x7fu] : c_const[arg]); break;
-            case U_ADDV0: T.c[0] += cx.x0; T.c[1] += 1.0; break;
-            case U_ADDV1: T.c[0] += cx.x1; T.c[2] += 1.0; break;
-            case U_SUBV0: T.c[0] -= cx.x0; T.c[1] -= 1.0; break;
-            case U_SUBV1: T.c[0] -= cx.x1; T.c[2] -= 1.0; break;
-            case U_MULV0: jet_mul_var(T, 0, cx.x0); break;
-            case U_MULV1: jet_mul_var(T, 1, cx.x1); break;
-            case U_DIVV0: jet_div_var(T, 0, cx.x0); break;
-            case U_DIVV1: jet_div_var(T, 1, cx.x1); break;
-            case U_NEG: jet_neg(T); break;
-            case U_ABS: jet_abs(T); break;
-            case U_SQRT: jet_sqrt(T); break;
-            case U_SQUARE: jet_square(T); break;
+            case U_ADD:
+#pragma unroll
+                PDE_EACH jet_add(T[h], U[h]);
+                break;
+            case U_SUB:
+#pragma unroll
+                PDE_EACH jet_sub(T[h], U[h]);
+                break;
+            case U_RSUB:
+#pragma unroll
+                PDE_EACH jet_rsub(T[h], U[h]);
+                break;
+            case U_MUL: jetv_mul<N, NP>(T, U); break;
+            case U_DIV: jetv_div<N, NP>(T, U); break;
+            case U_ADDC:
+#pragma unroll
+                PDE_EACH T[h].c[0] += c_const[arg];
+                break;
+            case U_SUBC:
+#pragma unroll
+                PDE_EACH T[h].c[0] -= c_const[arg];
+                break;
+            case U_MULC: {
+                const double c = (arg & 0x80u) ? c_rconst[arg & 0x7fu] : c_const[arg];
+#pragma unroll
+                PDE_EACH jet_scale(T[h], c);
+            } break;
+            case U_ADDV0:
+#pragma unroll
+                PDE_EACH { T[h].c[0] += cx[h].x0; T[h].c[1] += 1.0; }
+                break;
+            case U_ADDV1:
+#pragma unroll
+                PDE_EACH { T[h].c[0] += cx[h].x1; T[h].c[2] += 1.0; }
+                break;
+            case U_SUBV0:
+#pragma unroll
+                PDE_EACH { T[h].c[0] -= cx[h].x0; T[h].c[1] -= 1.0; }
+                break;
+            case U_SUBV1:
+#pragma unroll
+                PDE_EACH { T[h].c[0] -= cx[h].x1; T[h].c[2] -= 1.0; }
+                break;
+            case U_MULV0:
+#pragma unroll
+                PDE_EACH jet_mul_var(T[h], 0, cx[h].x0);
+                break;
+            case U_MULV1:
+#pragma unroll
+                PDE_EACH jet_mul_var(T[h], 1, cx[h].x1);
+                break;
+            case U_DIVV0:
+#pragma unroll
+                PDE_EACH jet_div_var(T[h], 0, cx[h].x0);
+                break;
+            case U_DIVV1:
+#pragma unroll
+                PDE_EACH jet_div_var(T[h], 1, cx[h].x1);
+                break;
+            case U_NEG:
+#pragma unroll
+                PDE_EACH jet_neg(T[h]);
+                break;
+            case U_ABS:
+#pragma unroll
+                PDE_EACH jet_abs(T[h]);
+                break;
+            case U_SQRT: jetv_sqrt<N, NP>(T); break;
+            case U_SQUARE: jetv_square<N, NP>(T); break;
             // out-of-place bodies compute into U and copy back (jet_copy is opaque to the
             // register allocator, see jet.cuh)
-            case U_RDIV: jet_div(U, T); jet_copy(T, U); break;
-            case U_EXP: jet_exp(U, T); jet_copy(T, U); break;
-            case U_POW: jet_pow(U, T, c_pow[arg]); jet_copy(T, U); break;
-            case U_MOVTU: jet_copy(T, U); break;
+            case U_RDIV:
+                jetv_div<N, NP>(U, T);
+#pragma unroll
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
+            case U_EXP:
+                jetv_exp<N, NP>(U, T);
+#pragma unroll
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
+            case U_POW:
+                jetv_pow<N, NP>(U, T, c_pow[arg]);
+#pragma unroll
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
+            case U_MOVTU:
+#pragma unroll
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
             default: return;
         }
     }
+#undef PDE_EACH
 }
 
 // Residual operators: R and its round-off scale S from the finished jet.
@@ -302,118 +403,175 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
     }
 };
 
-template <int N>
-__host__ __device__ constexpr size_t warp_smem_bytes(int L, int ns) {
-    // code[L] | vstack[L] | ucode[3L+4] u16 | spill[ns][NC][32] f64   (16-byte aligned pieces)
-    return (size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 2 + 15) / 16 * 16 + (size_t)ns * Jet<N>::NC * 32 * 8;
+// ---------------------------------------------------------------------------------
+// Work decomposition.  A warp OWNS a candidate: it stages + translates its bytecode and
+// each of its lanes owns collocation points (two per 64-point stripe, one LDG.128 per
+// coordinate).  W warps of a CTA run their W candidates as a round: after every warp has
+// translated its own candidate, the W warps sweep the candidates of the round TOGETHER
+// (warp w takes stripes w, w+W, ... of each candidate) so that all warps of the CTA
+// execute the same micro-op stream at the same time -- one instruction-cache working
+// set per CTA instead of one per warp (v1 ran at a 75 % i-cache hit rate) -- and the
+// per-candidate votes/maxima are combined by warp shuffles + one shared-memory row.
+// ---------------------------------------------------------------------------------
+struct WarpPartial {
+    double best_ratio, best_S, max_R;
+    int n_fin, n_vote;
+};
+
+template <int N, int NP>
+__host__ __device__ constexpr size_t cta_smem_bytes(int L, int ns, int W) {
+    // per candidate of the round: code[L] | vstack[L] | ucode[3L+4] u16 ; then partials[W][W] ; then
+    // spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
+    return ((size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 2 + 15) / 16 * 16) * W +
+           (size_t)W * W * sizeof(WarpPartial) + 16 * W +
+           (size_t)ns * Jet<N>::NC * NP * 32 * W * 8;
 }
 
-template <int PROBLEM, bool DUMP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, PROBLEM == PDE_PROBLEM_FORCE_FREE ? PDE_FF_MINBLOCKS : 5)
+template <int PROBLEM, bool DUMP, int W, int NP, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB)
 validate_kernel(const ValidateParams p) {
     using Res = Residual<PROBLEM>;
     constexpr int N = Res::N;
     constexpr int NC = Jet<N>::NC;
+    constexpr int TPB = W * 32;
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t wbytes = warp_smem_bytes<N>(p.L, p.ns);
-    unsigned char* base = smem + wbytes * warp;
     const int Lp = (p.L + 15) / 16 * 16;
-    uint8_t* s_code = base;
-    uint8_t* s_vst = base + Lp;
-    uint16_t* s_uc = reinterpret_cast<uint16_t*>(base + 2 * Lp);
-    double* s_spill = reinterpret_cast<double*>(base + 2 * Lp + (kUcodeMax(p.L) * 2 + 15) / 16 * 16) + lane;
+    const int ucb = (kUcodeMax(p.L) * 2 + 15) / 16 * 16;
+    const size_t per_cand = (size_t)Lp * 2 + ucb;
+    unsigned char* my = smem + per_cand * warp;
+    uint8_t* s_code = my;
+    uint8_t* s_vst = my + Lp;
+    uint16_t* s_uc_mine = reinterpret_cast<uint16_t*>(my + 2 * Lp);
+    WarpPartial* s_part = reinterpret_cast<WarpPartial*>(smem + per_cand * W);
+    int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial));
+    double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
 
-    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long cand = (long long)blockIdx.x * kWarpsPerBlock + warp; cand < p.n; cand += nwarps) {
-        const int len = p.len[cand];
-        // ---- stage bytecode (coalesced 4-byte loads) ----
+    const long long n_rounds = (p.n + W - 1) / W;
+    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+        const long long cand0 = round * W;
+        // ---- phase 1: every warp stages + translates its own candidate ----
         {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code + (size_t)cand * p.L);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(s_code);
-            for (int i = lane; i * 4 < len; i += 32) dst[i] = __ldg(src + i);
-        }
-        __syncwarp();
-        int status = 0;
-        if (lane == 0) status = (len == 0) ? -1 : translate(s_code, len, s_uc, s_vst, p.ns);
-        status = __shfl_sync(0xffffffffu, status, 0);
-        if (status != 0) {
-            if (!DUMP && lane == 0) {
-                p.ratio_max[cand] = 0.0; p.resid_max[cand] = 0.0; p.scale_at[cand] = 0.0;
-                p.n_finite[cand] = (status < 0) ? -1 : -1 - status;   // -1 empty, -2 malformed, -3 spill overflow
-                p.n_votes[cand] = 0;
-                if (p.ref_rs) for (int k = 0; k < 2 * p.n_ref; ++k) p.ref_rs[(size_t)cand * 2 * p.n_ref + k] = __longlong_as_double(0x7ff8000000000000LL);
-                atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
+            const long long cand = cand0 + warp;
+            int status = -1;
+            if (cand < p.n) {
+                const int len = p.len[cand];
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code + (size_t)cand * p.L);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_code);
+                for (int i = lane; i * 4 < len; i += 32) dst[i] = __ldg(src + i);
+                __syncwarp();
+                if (lane == 0) {
+                    status = (len == 0) ? -1 : translate(s_code, len, s_uc_mine, s_vst, p.ns);
+                    s_status[warp] = status;
+                }
+            } else if (lane == 0) {
+                s_status[warp] = -9;   // no candidate in this slot
             }
-            __syncwarp();
-            continue;
         }
-        int n_fin = 0, n_vote = 0;
-        double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
+        __syncthreads();
+        // ---- phase 2: the W warps sweep the round's candidates together ----
+        for (int c = 0; c < W; ++c) {
+            const long long cand = cand0 + c;
+            const int status = s_status[c];
+            if (status != 0) continue;
+            const uint16_t* uc = reinterpret_cast<const uint16_t*>(smem + per_cand * c + 2 * Lp);
+            int n_fin = 0, n_vote = 0;
+            double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
 #pragma unroll 1
-        for (int stripe = 0; stripe < p.P; stripe += 64) {
-            // one 128-bit load per coordinate: two consecutive points per lane
-            const double2 xa = __ldg(reinterpret_cast<const double2*>(p.pts + stripe) + lane);
-            const double2 xb = __ldg(reinterpret_cast<const double2*>(p.pts + p.P + stripe) + lane);
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                PointCtx<N> cx;
-                cx.x0 = h ? xa.y : xa.x;
-                cx.x1 = h ? xb.y : xb.x;
-                cx.pt = stripe + 2 * lane + h;
-                cx.P = p.P;
-                cx.prim = p.prim;
-                Jet<N> T;
-                run_program<N>(s_uc, s_spill, cx, T);
-                double R, S;
-                Res::eval(T, p.tab, p.P, cx.pt, R, S);
-                if (DUMP) {
-                    if (p.jets) {
-#pragma unroll
-                        for (int g = 0; g < NC; ++g) p.jets[((size_t)cand * NC + g) * p.P + cx.pt] = T.c[g];
-                    }
-                    if (p.resid) p.resid[(size_t)cand * p.P + cx.pt] = R;
-                    if (p.scale) p.scale[(size_t)cand * p.P + cx.pt] = S;
+            for (int stripe = warp * 32 * NP; stripe < p.P; stripe += TPB * NP) {
+                PointCtx<N> cx[NP];
+                if (NP == 2) {
+                    // one 128-bit load per coordinate: two consecutive points per lane
+                    const double2 xa = __ldg(reinterpret_cast<const double2*>(p.pts + stripe) + lane);
+                    const double2 xb = __ldg(reinterpret_cast<const double2*>(p.pts + p.P + stripe) + lane);
+                    cx[0].x0 = xa.x; cx[0].x1 = xb.x; cx[NP - 1].x0 = xa.y; cx[NP - 1].x1 = xb.y;
                 } else {
-                    const double aR = fabs(R);
-                    const bool fin = (aR <= 1.79769313486231570e308) && (S <= 1.79769313486231570e308) && (S > 0.0);
-                    if (fin) {
-                        ++n_fin;
-                        const double ratio = aR / S;
-                        n_vote += (aR > p.tau * S) ? 1 : 0;
-                        if (ratio > best_ratio) { best_ratio = ratio; best_S = S; }
-                        max_R = fmax(max_R, aR);
-                    }
-                    if (p.ref_rs && cx.pt < p.n_ref) {
-                        p.ref_rs[((size_t)cand * p.n_ref + cx.pt) * 2 + 0] = R;
-                        p.ref_rs[((size_t)cand * p.n_ref + cx.pt) * 2 + 1] = S;
+                    cx[0].x0 = __ldg(p.pts + stripe + lane);
+                    cx[0].x1 = __ldg(p.pts + p.P + stripe + lane);
+                }
+#pragma unroll
+                for (int h = 0; h < NP; ++h) { cx[h].pt = stripe + NP * lane + h; cx[h].P = p.P; cx[h].prim = p.prim; }
+                Jet<N> T[NP];
+                run_program<N, NP>(uc, s_spill, TPB, cx, T);
+#pragma unroll
+                for (int h = 0; h < NP; ++h) {
+                    double R, S;
+                    Res::eval(T[h], p.tab, p.P, cx[h].pt, R, S);
+                    if (DUMP) {
+                        if (p.jets) {
+#pragma unroll
+                            for (int g = 0; g < NC; ++g) p.jets[((size_t)cand * NC + g) * p.P + cx[h].pt] = T[h].c[g];
+                        }
+                        if (p.resid) p.resid[(size_t)cand * p.P + cx[h].pt] = R;
+                        if (p.scale) p.scale[(size_t)cand * p.P + cx[h].pt] = S;
+                    } else {
+                        const double aR = fabs(R);
+                        const bool fin = (aR <= 1.79769313486231570e308) && (S <= 1.79769313486231570e308) && (S > 0.0);
+                        if (fin) {
+                            ++n_fin;
+                            const double ratio = aR / S;
+                            n_vote += (aR > p.tau * S) ? 1 : 0;
+                            if (ratio > best_ratio) { best_ratio = ratio; best_S = S; }
+                            max_R = fmax(max_R, aR);
+                        }
+                        if (p.ref_rs && cx[h].pt < p.n_ref) {
+                            p.ref_rs[((size_t)cand * p.n_ref + cx[h].pt) * 2 + 0] = R;
+                            p.ref_rs[((size_t)cand * p.n_ref + cx[h].pt) * 2 + 1] = S;
+                        }
                     }
                 }
             }
-        }
-        if (!DUMP) {
-            // ---- warp-shuffle reduction over the lanes ----
+            if (!DUMP) {
+                // ---- warp-shuffle reduction over the lanes, one row per (candidate, warp) ----
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                n_fin += __shfl_xor_sync(0xffffffffu, n_fin, off);
-                n_vote += __shfl_xor_sync(0xffffffffu, n_vote, off);
-                const double r2 = __shfl_xor_sync(0xffffffffu, best_ratio, off);
-                const double s2 = __shfl_xor_sync(0xffffffffu, best_S, off);
-                const double m2 = __shfl_xor_sync(0xffffffffu, max_R, off);
-                if (r2 > best_ratio) { best_ratio = r2; best_S = s2; }
-                max_R = fmax(max_R, m2);
-            }
-            if (lane == 0) {
-                p.ratio_max[cand] = best_ratio;
-                p.resid_max[cand] = max_R;
-                p.scale_at[cand] = best_S;
-                p.n_finite[cand] = n_fin;
-                p.n_votes[cand] = n_vote;
-                const bool reject = (n_fin >= p.min_finite) && (n_vote > 0) && ((double)n_vote >= p.vote_frac * (double)n_fin);
-                if (!reject) atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
+                for (int off = 16; off > 0; off >>= 1) {
+                    n_fin += __shfl_xor_sync(0xffffffffu, n_fin, off);
+                    n_vote += __shfl_xor_sync(0xffffffffu, n_vote, off);
+                    const double r2 = __shfl_xor_sync(0xffffffffu, best_ratio, off);
+                    const double s2 = __shfl_xor_sync(0xffffffffu, best_S, off);
+                    const double m2 = __shfl_xor_sync(0xffffffffu, max_R, off);
+                    if (r2 > best_ratio) { best_ratio = r2; best_S = s2; }
+                    max_R = fmax(max_R, m2);
+                }
+                if (lane == 0) {
+                    WarpPartial wp;
+                    wp.best_ratio = best_ratio; wp.best_S = best_S; wp.max_R = max_R; wp.n_fin = n_fin; wp.n_vote = n_vote;
+                    s_part[c * W + warp] = wp;
+                }
             }
         }
-        __syncwarp();
+        __syncthreads();
+        // ---- phase 3: one thread per candidate of the round writes the row ----
+        if (!DUMP && threadIdx.x < W) {
+            const int c = threadIdx.x;
+            const long long cand = cand0 + c;
+            const int status = s_status[c];
+            if (cand < p.n) {
+                if (status != 0) {
+                    p.ratio_max[cand] = 0.0; p.resid_max[cand] = 0.0; p.scale_at[cand] = 0.0;
+                    p.n_finite[cand] = (status < 0) ? -1 : -1 - status;   // -1 empty, -2 malformed, -3 spill overflow
+                    p.n_votes[cand] = 0;
+                    if (p.ref_rs) for (int k = 0; k < 2 * p.n_ref; ++k) p.ref_rs[(size_t)cand * 2 * p.n_ref + k] = __longlong_as_double(0x7ff8000000000000LL);
+                    atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
+                } else {
+                    WarpPartial t = s_part[c * W];
+                    for (int w = 1; w < W; ++w) {
+                        const WarpPartial o = s_part[c * W + w];
+                        t.n_fin += o.n_fin; t.n_vote += o.n_vote;
+                        if (o.best_ratio > t.best_ratio) { t.best_ratio = o.best_ratio; t.best_S = o.best_S; }
+                        t.max_R = fmax(t.max_R, o.max_R);
+                    }
+                    p.ratio_max[cand] = t.best_ratio;
+                    p.resid_max[cand] = t.max_R;
+                    p.scale_at[cand] = t.best_S;
+                    p.n_finite[cand] = t.n_fin;
+                    p.n_votes[cand] = t.n_vote;
+                    const bool reject = (t.n_fin >= p.min_finite) && (t.n_vote > 0) && ((double)t.n_vote >= p.vote_frac * (double)t.n_fin);
+                    if (!reject) atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
