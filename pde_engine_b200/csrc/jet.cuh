@@ -23,6 +23,35 @@ namespace pde {
 
 __host__ __device__ constexpr int jidx(int i, int j) { return (i + j) * (i + j + 1) / 2 + j; }
 
+// Branch-free reciprocal / reciprocal square root: MUFU seed (about 2^-23) + two Newton steps.
+// The IEEE-exact library sequences carry a slow-path CALL/branch per use; here 0, inf and
+// subnormal inputs simply come out non-finite (NaN instead of inf), which the validator
+// treats identically (the point is not counted).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+// y = 1/sqrt(x); sqrt(x) = x * y refined once more by the caller
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double x, double& half_rsqrt) {
+    const double y = fast_rsqrt(x);
+    double s = x * y;
+    half_rsqrt = 0.5 * y;
+    s = fma(fma(-s, s, x), half_rsqrt, s);
+    return s;
+}
+
 template <int N>
 struct Jet {
     static constexpr int NC = (N + 1) * (N + 2) / 2;
@@ -131,7 +160,7 @@ __device__ __forceinline__ void jet_mul_var(Jet<N>& t, int k, double x) {
 // t = t / (x_k + dx_k)
 template <int N>
 __device__ __forceinline__ void jet_div_var(Jet<N>& t, int k, double x) {
-    const double r = 1.0 / x;
+    const double r = fast_rcp(x);
 #pragma unroll
     for (int n = 0; n <= N; ++n) {
 #pragma unroll
@@ -294,11 +323,12 @@ __device__ __forceinline__ double pow0(double b0, double k) {
             base *= base;
             e >>= 1;
         }
-        return k < 0 ? 1.0 / r : r;
+        return k < 0 ? fast_rcp(r) : r;
     }
     const double a2 = 2.0 * ak;
     if (rint(a2) == a2 && a2 <= 32.0) {    // half-integer: sqrt(b0)^(2k)
-        const double s = sqrt(b0);
+        double unused_h;
+        const double s = fast_sqrt(b0, unused_h);
         double r = 1.0, base = s;
         int e = (int)a2;
 #pragma unroll 1
@@ -307,7 +337,7 @@ __device__ __forceinline__ double pow0(double b0, double k) {
             base *= base;
             e >>= 1;
         }
-        return k < 0 ? 1.0 / r : r;
+        return k < 0 ? fast_rcp(r) : r;
     }
     return b0 >= 0.0 ? pow(b0, k) : __longlong_as_double(0x7ff8000000000000LL);
 }
@@ -396,7 +426,7 @@ template <int N, int NP>
 __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP]) {
     double r0[NP];
 #pragma unroll
-    PDE_H r0[h] = 1.0 / d[h].c[0];
+    PDE_H r0[h] = fast_rcp(d[h].c[0]);
 #pragma unroll
     for (int n = 0; n <= N; ++n) {
 #pragma unroll
@@ -460,7 +490,7 @@ template <int N, int NP>
 __device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
     double hh[NP];
 #pragma unroll
-    PDE_H { const double s0 = sqrt(t[h].c[0]); hh[h] = 0.5 / s0; t[h].c[0] = s0; }
+    PDE_H { const double s0 = fast_sqrt(t[h].c[0], hh[h]); t[h].c[0] = s0; }
 #pragma unroll
     for (int n = 1; n <= N; ++n) {
 #pragma unroll
@@ -493,15 +523,16 @@ __device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
 
 // o = exp(t); t is clobbered
 template <int N, int NP>
-__device__ __forceinline__ void jetv_exp(Jet<N> (&o)[NP], Jet<N> (&t)[NP]) {
+__device__ __forceinline__ void jetv_exp(Jet<N> (&o)[NP], Jet<N> (&t)[NP], bool negate) {
+    const double sg = negate ? -1.0 : 1.0;      // exp(-t): the sign rides on the pre-scaling
 #pragma unroll
-    PDE_H o[h].c[0] = exp(t[h].c[0]);
+    PDE_H o[h].c[0] = exp(sg * t[h].c[0]);
 #pragma unroll
-    for (int n = 2; n <= N; ++n) {
+    for (int n = 1; n <= N; ++n) {
 #pragma unroll
         for (int j = 0; j <= n; ++j) {
 #pragma unroll
-            PDE_H t[h].c[jidx(n - j, j)] *= (double)n;
+            PDE_H t[h].c[jidx(n - j, j)] *= sg * (double)n;
         }
     }
 #pragma unroll
@@ -538,7 +569,7 @@ template <int N, int NP>
 __device__ __forceinline__ void jetv_pow(Jet<N> (&o)[NP], const Jet<N> (&t)[NP], double k) {
     double rb0[NP];
 #pragma unroll
-    PDE_H { o[h].c[0] = pow0(t[h].c[0], k); rb0[h] = 1.0 / t[h].c[0]; }
+    PDE_H { o[h].c[0] = pow0(t[h].c[0], k); rb0[h] = fast_rcp(t[h].c[0]); }
     const double k1 = k + 1.0;
 #pragma unroll
     for (int n = 1; n <= N; ++n) {

@@ -29,22 +29,25 @@ __constant__ double c_const[PDE_N_CONST];
 __constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
 __constant__ double c_pow[PDE_N_POW];
 
-// Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel (operands are
-// brought into the operand jet U by separate micro-ops) so the interpreter's code
-// stays inside the 32 KB instruction cache: an earlier version that inlined the
+// Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel so the interpreter's
+// code stays inside the 32 KB instruction cache: an earlier version that inlined the
 // bodies per call site ran at a 75 % i-cache hit rate (profiles/r1_v1_*).
+// Word layout (u32): bits 0-7 kind | 8-15 arg | 16-24 operand source for the U jet
+// (0 = none, SRC_SPILL = pop the spill stack, otherwise the leaf opcode byte).  The
+// operand fetch is one shared block in front of the dispatch, so a binary node with any
+// operand kind costs ONE dispatch (the dispatch tree was 23 % of all stall samples).
 enum UKind : uint8_t {
     U_END = 0,
     U_SPILL,                          // S[sp++] = T
-    U_MOVTU,                          // T = U
-    U_SETU_C, U_SETU_V0, U_SETU_V1,   // U = const / coordinate jet (one shared body)
-    U_SETT_C, U_SETT_V0, U_SETT_V1, U_LOADT_P,   // T = leaf (first leaf of a sub-tree)
-    U_LOADU_P, U_LOADU_S,             // U = primitive jet table / S[--sp]
+    U_SETT,                           // T = U            (leaf materialisation: src = leaf)
     U_ADD, U_SUB, U_RSUB, U_MUL, U_DIV, U_RDIV,   // T = T op U;  RSUB: U - T, RDIV: U / T
     U_ADDC, U_SUBC, U_MULC,           // sparse leaf fast paths (arg = const slot; MULC bit7 = reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
-    U_NEG, U_ABS, U_SQRT, U_EXP, U_SQUARE, U_POW
+    U_NEG, U_ABS, U_SQRT, U_SQUARE,
+    U_EXP,                            // arg = 1: exp(-T)
+    U_POW                             // arg = exponent slot
 };
+constexpr unsigned SRC_SPILL = 0x100;
 
 struct ValidateParams {
     const uint8_t* code;
@@ -86,44 +89,30 @@ __device__ __forceinline__ bool op_is_unary(unsigned b) {
 constexpr uint8_t V_JET_T = 0x03;  // virtual-stack markers (unused opcode values)
 constexpr uint8_t V_JET_S = 0x04;
 
-__host__ __device__ constexpr int kUcodeMax(int L) { return 3 * L + 4; }
+__host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 4; }
 
 // Postfix bytecode -> micro-ops.  Returns 0 ok, 1 malformed, 2 spill overflow.
 // Invariant: the top-most jet of the virtual stack is always T; older jets are
 // spilled in stack order, leaves never occupy a jet.
-__device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc, uint8_t* vst, int ns_max) {
+__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* vst, int ns_max) {
     int sp = 0, nu = 0, ns = 0, tpos = -1;
-    auto emit = [&](unsigned kind, unsigned arg) { uc[nu++] = (uint16_t)((kind << 8) | arg); };
-    auto set_u = [&](unsigned leaf) {   // U = jet of a leaf
-        if (leaf >= PDE_OP_CONST0) emit(U_SETU_C, leaf - PDE_OP_CONST0);
-        else if (leaf == PDE_OP_VAR0) emit(U_SETU_V0, 0);
-        else if (leaf == PDE_OP_VAR1) emit(U_SETU_V1, 0);
-        else emit(U_LOADU_P, leaf - PDE_OP_PRIM0);
-    };
-    auto set_t = [&](unsigned leaf) {   // T = jet of a leaf
-        if (leaf >= PDE_OP_CONST0) emit(U_SETT_C, leaf - PDE_OP_CONST0);
-        else if (leaf == PDE_OP_VAR0) emit(U_SETT_V0, 0);
-        else if (leaf == PDE_OP_VAR1) emit(U_SETT_V1, 0);
-        else emit(U_LOADT_P, leaf - PDE_OP_PRIM0);
-    };
+    auto emit = [&](unsigned kind, unsigned arg, unsigned src) { uc[nu++] = kind | (arg << 8) | (src << 16); };
     auto spill_t = [&]() -> bool {
         if (tpos < 0) return true;
         if (ns >= ns_max) return false;
-        emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
+        emit(U_SPILL, 0, 0); vst[tpos] = V_JET_S; ++ns;
         return true;
     };
-    auto emit_inv = [&]() { emit(U_SETU_C, 0); emit(U_RDIV, 0); };   // 1 / T  (CONST(0) = 1)
     // T = T op leaf (leaf on the right)
     auto bin_leaf_right = [&](unsigned o, unsigned leaf) {
         if (leaf >= PDE_OP_CONST0) {
             const unsigned k = leaf - PDE_OP_CONST0;
-            emit(o == 0 ? U_ADDC : o == 1 ? U_SUBC : U_MULC, o == 3 ? (k | 0x80u) : k);
+            emit(o == 0 ? U_ADDC : o == 1 ? U_SUBC : U_MULC, o == 3 ? (k | 0x80u) : k, 0);
         } else if (leaf == PDE_OP_VAR0 || leaf == PDE_OP_VAR1) {
             const unsigned v = leaf - PDE_OP_VAR0;
-            emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + v, 0);
+            emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + v, 0, 0);
         } else {
-            set_u(leaf);
-            emit(o == 0 ? U_ADD : o == 1 ? U_SUB : o == 2 ? U_MUL : U_DIV, 0);
+            emit(o == 0 ? U_ADD : o == 1 ? U_SUB : o == 2 ? U_MUL : U_DIV, 0, leaf);     // PRIM operand
         }
     };
     for (int pc = 0; pc < len; ++pc) {
@@ -136,26 +125,26 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
             if (top != V_JET_T) {
                 if (top == V_JET_S) return 1;
                 if (!spill_t()) return 2;
-                set_t(top);
+                emit(U_SETT, 0, top);
                 vst[sp - 1] = V_JET_T; tpos = sp - 1;
             }
             switch (b) {
-                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0); break;
-                case PDE_OP_ABS: emit(U_ABS, 0); break;
-                case PDE_OP_SQRT: emit(U_SQRT, 0); break;
-                case PDE_OP_EXP: emit(U_EXP, 0); break;
-                case PDE_OP_FN_INV: emit_inv(); break;
-                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0); break;
-                case PDE_OP_FN_POW32: emit(U_POW, 0); break;
-                case PDE_OP_FN_POWN32: emit(U_POW, 1); break;
-                case PDE_OP_FN_EXPNEG: emit(U_NEG, 0); emit(U_EXP, 0); break;
+                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0, 0); break;
+                case PDE_OP_ABS: emit(U_ABS, 0, 0); break;
+                case PDE_OP_SQRT: emit(U_SQRT, 0, 0); break;
+                case PDE_OP_EXP: emit(U_EXP, 0, 0); break;
+                case PDE_OP_FN_INV: emit(U_RDIV, 0, PDE_OP_CONST0); break;         // 1 / T  (CONST(0) = 1)
+                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0, 0); break;
+                case PDE_OP_FN_POW32: emit(U_POW, 0, 0); break;
+                case PDE_OP_FN_POWN32: emit(U_POW, 1, 0); break;
+                case PDE_OP_FN_EXPNEG: emit(U_EXP, 1, 0); break;
                 default: {
                     const unsigned slot = b - PDE_OP_POW0;
                     const double k = c_pow[slot];
-                    if (k == 2.0) emit(U_SQUARE, 0);
-                    else if (k == 0.5) emit(U_SQRT, 0);
-                    else if (k == -1.0) emit_inv();
-                    else emit(U_POW, slot);
+                    if (k == 2.0) emit(U_SQUARE, 0, 0);
+                    else if (k == 0.5) emit(U_SQRT, 0, 0);
+                    else if (k == -1.0) emit(U_RDIV, 0, PDE_OP_CONST0);
+                    else emit(U_POW, slot, 0);
                 }
             }
         } else if (op_is_binary(b)) {
@@ -164,17 +153,17 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
             sp -= 2;
             const unsigned o = b - PDE_OP_ADD;  // 0 add 1 sub 2 mul 3 div
             if (aa == V_JET_S && bb == V_JET_T) {
-                emit(U_LOADU_S, 0); --ns;
-                emit(o == 0 ? U_ADD : o == 1 ? U_RSUB : o == 2 ? U_MUL : U_RDIV, 0);     // U op T
+                emit(o == 0 ? U_ADD : o == 1 ? U_RSUB : o == 2 ? U_MUL : U_RDIV, 0, SRC_SPILL);   // S op T
+                --ns;
             } else if (aa == V_JET_T && bb != V_JET_S) {
                 bin_leaf_right(o, bb);
             } else if (bb == V_JET_T && aa != V_JET_S) {
-                if (o == 0 || o == 2) bin_leaf_right(o, aa);                  // commutative
-                else if (o == 1) { emit(U_NEG, 0); bin_leaf_right(0, aa); }   // leaf - T = -T + leaf
-                else { set_u(aa); emit(U_RDIV, 0); }      // leaf / T
+                if (o == 0 || o == 2) bin_leaf_right(o, aa);                        // commutative
+                else if (o == 1) { emit(U_NEG, 0, 0); bin_leaf_right(0, aa); }      // leaf - T = -T + leaf
+                else emit(U_RDIV, 0, aa);                                           // leaf / T
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
                 if (!spill_t()) return 2;
-                set_t(aa);
+                emit(U_SETT, 0, aa);
                 bin_leaf_right(o, bb);
             } else {
                 return 1;
@@ -185,8 +174,8 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint16_t* uc
         }
     }
     if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) set_t(vst[0]);
-    emit(U_END, 0);
+    if (vst[0] != V_JET_T) emit(U_SETT, 0, vst[0]);
+    emit(U_END, 0, 0);
     return 0;
 }
 
@@ -199,11 +188,9 @@ struct PointCtx {
 };
 
 // Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
-// The NP jets are independent, which gives the scheduler NP-way instruction-level
-// parallelism inside every body and amortises the dispatch over NP points.
 // Spill layout: [(slot * NC + coef) * NP + point][thread]  (conflict free).
 template <int N, int NP>
-__device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, double* __restrict__ spill, int stride,
+__device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, double* __restrict__ spill, int stride,
                                             const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
     constexpr int NC = Jet<N>::NC;
     Jet<N> U[NP];
@@ -213,10 +200,36 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
 #define PDE_EACH for (int h = 0; h < NP; ++h)
 #pragma unroll 1
     for (;;) {
-        const unsigned kind = ins >> 8, arg = ins & 0xff;
+        const unsigned kind = ins & 0xffu, arg = (ins >> 8) & 0xffu, src = ins >> 16;
+        if (kind == U_END) return;
         ins = uc[++pc];            // prefetch the next micro-op behind this one's body
+        if (src != 0) {            // shared operand fetch: U = spilled jet | primitive table | const | coordinate
+            if (src == SRC_SPILL) {
+                --sp;
+                const double* from = spill + (size_t)sp * NC * NP * stride;
+#pragma unroll
+                PDE_EACH {
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) U[h].c[g] = from[(g * NP + h) * stride];
+                }
+            } else if (src >= PDE_OP_PRIM0 && src < PDE_OP_PRIM0 + PDE_N_PRIM) {
+#pragma unroll
+                PDE_EACH {
+                    const double* from = cx[h].prim + (size_t)(src - PDE_OP_PRIM0) * NC * cx[h].P + cx[h].pt;
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(from + (size_t)g * cx[h].P);
+                }
+            } else {
+#pragma unroll
+                PDE_EACH {
+                    const double v = src >= PDE_OP_CONST0 ? c_const[src - PDE_OP_CONST0] : src == PDE_OP_VAR0 ? cx[h].x0 : cx[h].x1;
+                    jet_set_const(U[h], v);
+                    U[h].c[1] = src == PDE_OP_VAR0 ? 1.0 : 0.0;
+                    U[h].c[2] = src == PDE_OP_VAR1 ? 1.0 : 0.0;
+                }
+            }
+        }
         switch (kind) {
-            case U_END: return;
             case U_SPILL: {
                 double* dst = spill + (size_t)sp * NC * NP * stride;
 #pragma unroll
@@ -226,49 +239,10 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
                 }
                 ++sp;
             } break;
-            case U_SETU_C: case U_SETU_V0: case U_SETU_V1: {
+            case U_SETT:
 #pragma unroll
-                PDE_EACH {
-                    const double v = kind == U_SETU_C ? c_const[arg] : kind == U_SETU_V0 ? cx[h].x0 : cx[h].x1;
-                    jet_set_const(U[h], v);
-                    U[h].c[1] = kind == U_SETU_V0 ? 1.0 : 0.0;
-                    U[h].c[2] = kind == U_SETU_V1 ? 1.0 : 0.0;
-                }
-            } break;
-            case U_LOADU_P: {
-#pragma unroll
-                PDE_EACH {
-                    const double* src = cx[h].prim + (size_t)arg * NC * cx[h].P + cx[h].pt;
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(src + (size_t)g * cx[h].P);
-                }
-            } break;
-            case U_SETT_C: case U_SETT_V0: case U_SETT_V1: {
-#pragma unroll
-                PDE_EACH {
-                    const double v = kind == U_SETT_C ? c_const[arg] : kind == U_SETT_V0 ? cx[h].x0 : cx[h].x1;
-                    jet_set_const(T[h], v);
-                    T[h].c[1] = kind == U_SETT_V0 ? 1.0 : 0.0;
-                    T[h].c[2] = kind == U_SETT_V1 ? 1.0 : 0.0;
-                }
-            } break;
-            case U_LOADT_P: {
-#pragma unroll
-                PDE_EACH {
-                    const double* src = cx[h].prim + (size_t)arg * NC * cx[h].P + cx[h].pt;
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(src + (size_t)g * cx[h].P);
-                }
-            } break;
-            case U_LOADU_S: {
-                --sp;
-                const double* src = spill + (size_t)sp * NC * NP * stride;
-#pragma unroll
-                PDE_EACH {
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) U[h].c[g] = src[(g * NP + h) * stride];
-                }
-            } break;
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
             case U_ADD:
 #pragma unroll
                 PDE_EACH jet_add(T[h], U[h]);
@@ -346,16 +320,12 @@ __device__ __forceinline__ void run_program(const uint16_t* __restrict__ uc, dou
                 PDE_EACH jet_copy(T[h], U[h]);
                 break;
             case U_EXP:
-                jetv_exp<N, NP>(U, T);
+                jetv_exp<N, NP>(U, T, arg != 0);
 #pragma unroll
                 PDE_EACH jet_copy(T[h], U[h]);
                 break;
             case U_POW:
                 jetv_pow<N, NP>(U, T, c_pow[arg]);
-#pragma unroll
-                PDE_EACH jet_copy(T[h], U[h]);
-                break;
-            case U_MOVTU:
 #pragma unroll
                 PDE_EACH jet_copy(T[h], U[h]);
                 break;
@@ -372,14 +342,15 @@ template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
     static constexpr int N = 4;
     static constexpr int COLS = 1;
     // FFV:305-347; entries expanded by tools/gen_residual.py
-    __device__ static __forceinline__ void eval(const Jet<4>& u, const double* tab, int P, int pt, double& R, double& S) {
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[1]) { c[0] = __ldg(tab + pt); }
+    __device__ static __forceinline__ void eval(const Jet<4>& u, const double (&c)[1], double& R, double& S) {
         double d[15];
 #pragma unroll
         for (int n = 0; n <= 4; ++n) {
 #pragma unroll
             for (int j = 0; j <= n; ++j) d[jidx(n - j, j)] = u.c[jidx(n - j, j)] * (factorial(n - j) * factorial(j));
         }
-        const double w = __ldg(tab + pt);   // 1/rho
+        const double w = c[0];   // 1/rho
         double p[4], a[4];
         ff_residual_entries(d, w, p, a);
         R = p[0] * p[3] - p[1] * p[2];       // det M, FFV:347
@@ -391,9 +362,12 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
     static constexpr int N = 2;
     static constexpr int COLS = 4;
     // KV:77-91 expanded: R = c1_r u_r + c1 u_rr + c2_x u_x + c2 u_xx
-    __device__ static __forceinline__ void eval(const Jet<2>& u, const double* tab, int P, int pt, double& R, double& S) {
-        const double c1 = __ldg(tab + pt), c1r = __ldg(tab + P + pt);
-        const double c2 = __ldg(tab + 2 * (size_t)P + pt), c2x = __ldg(tab + 3 * (size_t)P + pt);
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[4]) {
+        c[0] = __ldg(tab + pt); c[1] = __ldg(tab + P + pt);
+        c[2] = __ldg(tab + 2 * (size_t)P + pt); c[3] = __ldg(tab + 3 * (size_t)P + pt);
+    }
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&c)[4], double& R, double& S) {
+        const double c1 = c[0], c1r = c[1], c2 = c[2], c2x = c[3];
         const double t0 = c1r * u.c[1];
         const double t1 = c1 * (2.0 * u.c[3]);
         const double t2 = c2x * u.c[2];
@@ -420,9 +394,9 @@ struct WarpPartial {
 
 template <int N, int NP>
 __host__ __device__ constexpr size_t cta_smem_bytes(int L, int ns, int W) {
-    // per candidate of the round: code[L] | vstack[L] | ucode[3L+4] u16 ; then partials[W][W] ; then
+    // per candidate of the round: code[L] | vstack[L] | ucode[2L+4] u32 ; then partials[W][W] ; then
     // spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
-    return ((size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 2 + 15) / 16 * 16) * W +
+    return ((size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 4 + 15) / 16 * 16) * W +
            (size_t)W * W * sizeof(WarpPartial) + 16 * W +
            (size_t)ns * Jet<N>::NC * NP * 32 * W * 8;
 }
@@ -437,12 +411,12 @@ validate_kernel(const ValidateParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lp = (p.L + 15) / 16 * 16;
-    const int ucb = (kUcodeMax(p.L) * 2 + 15) / 16 * 16;
+    const int ucb = (kUcodeMax(p.L) * 4 + 15) / 16 * 16;
     const size_t per_cand = (size_t)Lp * 2 + ucb;
     unsigned char* my = smem + per_cand * warp;
     uint8_t* s_code = my;
     uint8_t* s_vst = my + Lp;
-    uint16_t* s_uc_mine = reinterpret_cast<uint16_t*>(my + 2 * Lp);
+    uint32_t* s_uc_mine = reinterpret_cast<uint32_t*>(my + 2 * Lp);
     WarpPartial* s_part = reinterpret_cast<WarpPartial*>(smem + per_cand * W);
     int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial));
     double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
@@ -474,7 +448,7 @@ validate_kernel(const ValidateParams p) {
             const long long cand = cand0 + c;
             const int status = s_status[c];
             if (status != 0) continue;
-            const uint16_t* uc = reinterpret_cast<const uint16_t*>(smem + per_cand * c + 2 * Lp);
+            const uint32_t* uc = reinterpret_cast<const uint32_t*>(smem + per_cand * c + 2 * Lp);
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
 #pragma unroll 1
@@ -489,14 +463,18 @@ validate_kernel(const ValidateParams p) {
                     cx[0].x0 = __ldg(p.pts + stripe + lane);
                     cx[0].x1 = __ldg(p.pts + p.P + stripe + lane);
                 }
+                double coef[NP][Res::COLS];
 #pragma unroll
-                for (int h = 0; h < NP; ++h) { cx[h].pt = stripe + NP * lane + h; cx[h].P = p.P; cx[h].prim = p.prim; }
+                for (int h = 0; h < NP; ++h) {
+                    cx[h].pt = stripe + NP * lane + h; cx[h].P = p.P; cx[h].prim = p.prim;
+                    Res::fetch(p.tab, p.P, cx[h].pt, coef[h]);      // issued early: latency hides behind the program
+                }
                 Jet<N> T[NP];
                 run_program<N, NP>(uc, s_spill, TPB, cx, T);
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
                     double R, S;
-                    Res::eval(T[h], p.tab, p.P, cx[h].pt, R, S);
+                    Res::eval(T[h], coef[h], R, S);
                     if (DUMP) {
                         if (p.jets) {
 #pragma unroll
@@ -509,7 +487,7 @@ validate_kernel(const ValidateParams p) {
                         const bool fin = (aR <= 1.79769313486231570e308) && (S <= 1.79769313486231570e308) && (S > 0.0);
                         if (fin) {
                             ++n_fin;
-                            const double ratio = aR / S;
+                            const double ratio = aR * fast_rcp(S);
                             n_vote += (aR > p.tau * S) ? 1 : 0;
                             if (ratio > best_ratio) { best_ratio = ratio; best_S = S; }
                             max_R = fmax(max_R, aR);

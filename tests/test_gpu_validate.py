@@ -144,7 +144,7 @@ def test_validate_reduction_consistent_with_points(cuda_device, enum_ff):
         assert o["n_votes"][i] == votes
         if fin.any():
             ratio = np.abs(resid[i][fin]) / scale[i][fin]
-            assert o["ratio_max"][i] == ratio.max()
+            assert abs(o["ratio_max"][i] - ratio.max()) <= 1e-12 * ratio.max()    # device uses a Newton reciprocal
             assert o["resid_max"][i] == np.abs(resid[i][fin]).max()
         reject = fin.sum() >= 8 and votes > 0 and votes >= 0.5 * fin.sum()
         assert surv == (0 if reject else 1)
