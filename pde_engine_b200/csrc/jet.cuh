@@ -80,7 +80,7 @@ __device__ __forceinline__ void jet_set_var(Jet<N>& t, int k, double x) {
 template <int N>
 __device__ __forceinline__ void jet_copy(Jet<N>& t, const Jet<N>& u) {
 #pragma unroll
-    for (int g = 0; g < Jet<N>::NC; ++g) asm volatile("mov.f64 %0, %1;" : "=d"(t.c[g]) : "d"(u.c[g]));
+    for (int g = 0; g < Jet<N>::NC; ++g) asm("mov.f64 %0, %1;" : "=d"(t.c[g]) : "d"(u.c[g]));
 }
 
 template <int N>

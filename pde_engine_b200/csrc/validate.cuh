@@ -203,6 +203,25 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
         const unsigned kind = ins & 0xffu, arg = (ins >> 8) & 0xffu, src = ins >> 16;
         if (kind == U_END) return;
         ins = uc[++pc];            // prefetch the next micro-op behind this one's body
+        if (kind == U_SETT) {      // first leaf of a sub-tree: T = leaf, no detour through U
+            if (src >= PDE_OP_PRIM0 && src < PDE_OP_PRIM0 + PDE_N_PRIM) {
+#pragma unroll
+                PDE_EACH {
+                    const double* from = cx[h].prim + (size_t)(src - PDE_OP_PRIM0) * NC * cx[h].P + cx[h].pt;
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(from + (size_t)g * cx[h].P);
+                }
+            } else {
+#pragma unroll
+                PDE_EACH {
+                    const double v = src >= PDE_OP_CONST0 ? c_const[src - PDE_OP_CONST0] : src == PDE_OP_VAR0 ? cx[h].x0 : cx[h].x1;
+                    jet_set_const(T[h], v);
+                    T[h].c[1] = src == PDE_OP_VAR0 ? 1.0 : 0.0;
+                    T[h].c[2] = src == PDE_OP_VAR1 ? 1.0 : 0.0;
+                }
+            }
+            continue;
+        }
         if (src != 0) {            // shared operand fetch: U = spilled jet | primitive table | const | coordinate
             if (src == SRC_SPILL) {
                 --sp;
@@ -239,10 +258,6 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                 }
                 ++sp;
             } break;
-            case U_SETT:
-#pragma unroll
-                PDE_EACH jet_copy(T[h], U[h]);
-                break;
             case U_ADD:
 #pragma unroll
                 PDE_EACH jet_add(T[h], U[h]);
