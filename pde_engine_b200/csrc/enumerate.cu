@@ -77,13 +77,14 @@ __device__ __forceinline__ Slot decode_slot(const EnumParams& p, long long s) {
     }
     int d1 = 1;
     while (d1 < d - 1 && s >= p.seg_begin[d1 + 1]) ++d1;
-    const long long t = s - p.seg_begin[d1];
+    const unsigned t = (unsigned)(s - p.seg_begin[d1]);      // every segment is < 2^32 slots (checked on the host)
     const int d2 = d - d1;
-    const int n2 = p.depth_begin[d2] - p.depth_begin[d2 - 1];
-    const long long pair = t / 5;
-    const int bop = (int)(t - pair * 5);
-    int a = p.depth_begin[d1 - 1] + (int)(pair / n2);
-    int b = p.depth_begin[d2 - 1] + (int)(pair % n2);
+    const unsigned n2 = (unsigned)(p.depth_begin[d2] - p.depth_begin[d2 - 1]);
+    const unsigned pair = t / 5u;
+    const int bop = (int)(t - pair * 5u);
+    const unsigned i1 = pair / n2;
+    int a = p.depth_begin[d1 - 1] + (int)i1;
+    int b = p.depth_begin[d2 - 1] + (int)(pair - i1 * n2);
     const unsigned ata = p.attrs[a], atb = p.attrs[b];
     if (p.prune && !((ata | atb) & PDE_ATTR_HAS_VARS)) r.keep = false;
     const uint32_t ra = p.rank[a], rb = p.rank[b];
@@ -163,12 +164,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 __device__ __forceinline__ unsigned long long hash_row(const uint8_t* row, int len) {
     unsigned long long h = 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)len * 0xD6E8FEB86659FD93ULL);
     const int nw = (len + 7) >> 3;
-    for (int w = 0; w < nw; ++w) {
-        unsigned long long v = 0;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) v = (v << 8) | row[w * 8 + k];
-        h = mix64(h ^ v);
-    }
+    const unsigned long long* w64 = reinterpret_cast<const unsigned long long*>(row);   // rows are 16-byte aligned
+    for (int w = 0; w < nw; ++w) h = mix64(h ^ w64[w]);                                  // little endian
     return h;
 }
 
@@ -249,13 +246,19 @@ enum_emit_kernel(const EnumParams p, const long long* block_off, long long first
     const int local = block_exclusive_scan(sl.keep ? 1 : 0, s_warp, total);
     const long long base = block_off[blockIdx.x];
     if (total == 0 || base + total <= first || base >= first + count) return;
+    {   // zero the block's tile with 16-byte stores (padding + unused rows)
+        uint4* z = reinterpret_cast<uint4*>(s_rows);
+        const int nz = total * L / 16;
+        for (int i = threadIdx.x; i < nz; i += kEnumThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
     if (sl.keep) {
         uint8_t* row = s_rows + (size_t)local * L;
         RowWriter w{row, L < 255 ? L : 255, 0, true};
         if (p.flags[sl.a] || (sl.b >= 0 && p.flags[sl.b])) w.ok = false;
         else splice(w, p, sl);
         int n = w.ok ? w.n : 0;
-        for (int i = (w.ok ? n : 0); i < L; ++i) row[i] = 0;
+        if (!w.ok) for (int i = 0; i < L && i < w.n; ++i) row[i] = 0;      // overflowed rows are emitted empty
         const long long c = base + local;
         if (c >= first && c < first + count) {
             const long long o = c - first;
@@ -361,7 +364,16 @@ __global__ void __launch_bounds__(256) synth_kernel(unsigned long long seed, lon
     uint8_t* dst = code + (size_t)t * L;
     for (int i = 0; i < L; ++i) { const uint8_t v = i < n ? row[i] : 0; dst[i] = v; if (i >= n && i < kMaxRow) row[i] = 0; }
     len_out[t] = (uint8_t)n;
-    hash_out[t] = hash_row(row, n);
+    {   // same hash as hash_row, byte-assembled (the local row is not 8-byte aligned)
+        unsigned long long h = 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)n * 0xD6E8FEB86659FD93ULL);
+        const int nw = (n + 7) >> 3;
+        for (int w = 0; w < nw; ++w) {
+            unsigned long long v = 0;
+            for (int k = 7; k >= 0; --k) v = (v << 8) | row[w * 8 + k];
+            h = mix64(h ^ v);
+        }
+        hash_out[t] = h;
+    }
 }
 
 static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int depth, int prune, EnumParams& p) {
@@ -382,6 +394,7 @@ static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int dep
         p.seg_begin[d1] = s;
         const int d2 = depth - d1;
         const long long n1 = depth_begin[d1] - depth_begin[d1 - 1], n2 = depth_begin[d2] - depth_begin[d2 - 1];
+        if (n1 * n2 * 5 >= 0xffffffffLL) { set_error("candidate index space too large"); return PDE_E_OVERFLOW; }
         s += n1 * n2 * 5;
     }
     p.seg_begin[depth] = s;

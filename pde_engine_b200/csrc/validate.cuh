@@ -89,7 +89,7 @@ __device__ __forceinline__ bool op_is_unary(unsigned b) {
 constexpr uint8_t V_JET_T = 0x03;  // virtual-stack markers (unused opcode values)
 constexpr uint8_t V_JET_S = 0x04;
 
-__host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 4; }
+__host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 
 // Postfix bytecode -> micro-ops.  Returns 0 ok, 1 malformed, 2 spill overflow.
 // Invariant: the top-most jet of the virtual stack is always T; older jets are
@@ -196,13 +196,15 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
     Jet<N> U[NP];
     int sp = 0;  // spill depth
     int pc = 0;
-    unsigned ins = uc[0];
+    unsigned ins = uc[0], ins_next = uc[1];
 #define PDE_EACH for (int h = 0; h < NP; ++h)
 #pragma unroll 1
     for (;;) {
         const unsigned kind = ins & 0xffu, arg = (ins >> 8) & 0xffu, src = ins >> 16;
         if (kind == U_END) return;
-        ins = uc[++pc];            // prefetch the next micro-op behind this one's body
+        ins = ins_next;
+        pc += 1;
+        ins_next = uc[pc + 1];     // two-deep prefetch: the LDS latency hides even behind one-instruction bodies
         if (kind == U_SETT) {      // first leaf of a sub-tree: T = leaf, no detour through U
             if (src >= PDE_OP_PRIM0 && src < PDE_OP_PRIM0 + PDE_N_PRIM) {
 #pragma unroll
@@ -350,6 +352,14 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
 #undef PDE_EACH
 }
 
+// A load the compiler may not sink below the interpreter loop (it otherwise moves the table
+// fetch next to its use and the residual stalls on the full L2 latency).
+__device__ __forceinline__ double ldg_early(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // Residual operators: R and its round-off scale S from the finished jet.
 template <int PROBLEM> struct Residual;
 
@@ -357,7 +367,7 @@ template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
     static constexpr int N = 4;
     static constexpr int COLS = 1;
     // FFV:305-347; entries expanded by tools/gen_residual.py
-    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[1]) { c[0] = __ldg(tab + pt); }
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[1]) { c[0] = ldg_early(tab + pt); }
     __device__ static __forceinline__ void eval(const Jet<4>& u, const double (&c)[1], double& R, double& S) {
         double d[15];
 #pragma unroll
@@ -378,8 +388,8 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
     static constexpr int COLS = 4;
     // KV:77-91 expanded: R = c1_r u_r + c1 u_rr + c2_x u_x + c2 u_xx
     __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[4]) {
-        c[0] = __ldg(tab + pt); c[1] = __ldg(tab + P + pt);
-        c[2] = __ldg(tab + 2 * (size_t)P + pt); c[3] = __ldg(tab + 3 * (size_t)P + pt);
+        c[0] = ldg_early(tab + pt); c[1] = ldg_early(tab + P + pt);
+        c[2] = ldg_early(tab + 2 * (size_t)P + pt); c[3] = ldg_early(tab + 3 * (size_t)P + pt);
     }
     __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&c)[4], double& R, double& S) {
         const double c1 = c[0], c1r = c[1], c2 = c[2], c2x = c[3];
