@@ -389,11 +389,16 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic depth-{args.depth}: {n} bytecode trees per GPU x {P} collocation points, force-free residual (order-4 jets)",
                        "trees_per_gpu": n, "points": P, "L": L, "seed": hex(SEED_TREES),
-                       "l2": f"inputs ({n * (L + 1) / 1e6:.0f} MB of bytecode per GPU) exceed the 126 MB L2; no flush needed",
+                       "l2": (f"inputs ({n * (L + 1) / 1e6:.0f} MB of bytecode per GPU, streamed once per step) exceed the 126 MB L2; no flush needed"
+                              if n * (L + 1) > 126e6 else
+                              f"inputs are {n * (L + 1) / 1e6:.0f} MB (< L2): reduced --trees run, not the headline configuration"),
                        "parallelism": f"{world} x independent candidate shards, final gather only"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak,
+                         # DRAM bytes per launch: 54.8 B per tree from the ncu --set full capture
+                         # (profiles/r1_validate_full_metrics.csv: 10.96 MB read / 0 written per 200 k trees)
+                         "traffic": 54.8 * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
                          "peak_source": "measured: pde_fp64_peak register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
                          "flops_per_candidate_point": flops_per_point / n, "kernel_ms": kernel_ms,
