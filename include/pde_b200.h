@@ -185,7 +185,10 @@ int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][
  *   code[n, L], len[n]   postfix programs (len 0 = skip: survivor, n_finite 0)
  *   pts[2][P]            collocation grid, SoA, P a multiple of 64
  *   table[cols][P]       pde_program_point_table
- *   prim[n_prim][n_coef][P]  jets of PRIM(p) leaves (may be NULL if unused)
+ *   prim[n_prim][P/32][16][32]  jets of PRIM(p) leaves in 32-point stripe blocks: coefficient g of
+ *                            point q at [p][q / 32][g][q % 32] (rows n_coef..15 are padding), so a
+ *                            warp reads a leaf with coalesced loads at immediate offsets; may be
+ *                            NULL if no program uses PRIM
  * outputs (per candidate):
  *   ratio_max   max |R|/S over finite points        resid_max  max |R|
  *   scale_at    S at the arg-max of the ratio       n_finite, n_votes

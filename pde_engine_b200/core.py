@@ -176,7 +176,7 @@ def validate(session: Session, program: ResidualProgram, code, length, pts, tabl
              tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, n_ref: int = 3,
              spill_slots: int = 4, stream=None, out: Optional[dict] = None) -> dict:
     """Stage 2 (pde_validate).  code [n, L] uint8, length [n] uint8, pts [2, P] f64,
-    table [cols, P] f64, prim [n_prim, n_coef, P] f64 or None -- all CUDA tensors."""
+    table [cols, P] f64, prim [n_prim, P/32, 16, 32] f64 (synthetic.pack_primitive_table) or None -- all CUDA tensors."""
     import torch
     n, L = code.shape
     Pn = pts.shape[1]

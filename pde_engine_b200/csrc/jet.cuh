@@ -157,10 +157,9 @@ __device__ __forceinline__ void jet_mul_var(Jet<N>& t, int k, double x) {
     }
 }
 
-// t = t / (x_k + dx_k)
+// t = t / (x_k + dx_k); r = 1 / x_k
 template <int N>
-__device__ __forceinline__ void jet_div_var(Jet<N>& t, int k, double x) {
-    const double r = fast_rcp(x);
+__device__ __forceinline__ void jet_div_var(Jet<N>& t, int k, double r) {
 #pragma unroll
     for (int n = 0; n <= N; ++n) {
 #pragma unroll
@@ -599,6 +598,73 @@ __device__ __forceinline__ void jetv_pow(Jet<N> (&o)[NP], const Jet<N> (&t)[NP],
             PDE_H o[h].c[jidx(gi, gj)] = tot[h] * (rb0[h] * (1.0 / (double)n));
         }
     }
+}
+
+// t = F(t) for a scalar function F given by its Taylor coefficients f[k] = F^(k)(t_0)/k! at the
+// jet's value: Horner on delta = t - t_0, truncated at total degree N,
+//     A <- f_N;   A <- f_k + delta * A  (k = N-1 .. 1, order N-k);   t <- f_0 + delta * A.
+// Every level is computed in place in DESCENDING degree (level m only reads levels < m of the
+// previous A), and the last level overwrites t itself (t_g reads t_b only for b <= g), so the
+// result lands in t's own registers: no out-of-place body, no copy-back.  One body serves
+// 1/x, x**k, exp(x) and exp(-x); `a` is scratch (the operand jet, dead during unary ops).
+// N = 4: 2 + 9 + 25 + 55 = 91 multiply-adds.
+// one Horner level: K > 0: a <- f_K + delta * a (order N-K, in place);  K == 0: t <- f_0 + delta * a
+template <int N, int NP, int K>
+__device__ __forceinline__ void jetv_compose_level(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
+#pragma unroll
+    for (int m = N - K; m >= 1; --m) {
+#pragma unroll
+        for (int gj = 0; gj <= m; ++gj) {
+            const int gi = m - gj;
+            const int nterms = (gi + 1) * (gj + 1) - 1;
+            const bool two = nterms > 3;      // long sums: two chains halve the dependent-DFMA depth
+            double acc[NP], acc1[NP];
+#pragma unroll
+            PDE_H { acc[h] = 0.0; acc1[h] = 0.0; }
+            int cnt = 0;
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    if (bi == 0 && bj == 0) continue;
+                    const int ib = jidx(bi, bj), ic = jidx(gi - bi, gj - bj);
+                    if (cnt == 0) {
+#pragma unroll
+                        PDE_H acc[h] = t[h].c[ib] * a[h].c[ic];
+                    } else if (two && cnt == 1) {
+#pragma unroll
+                        PDE_H acc1[h] = t[h].c[ib] * a[h].c[ic];
+                    } else if (!two || (cnt & 1) == 0) {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[ib], a[h].c[ic], acc[h]);
+                    } else {
+#pragma unroll
+                        PDE_H acc1[h] = fma(t[h].c[ib], a[h].c[ic], acc1[h]);
+                    }
+                    ++cnt;
+                }
+            }
+#pragma unroll
+            PDE_H {
+                if (two) acc[h] += acc1[h];
+                if (K > 0) a[h].c[jidx(gi, gj)] = acc[h];
+                else t[h].c[jidx(gi, gj)] = acc[h];
+            }
+        }
+    }
+#pragma unroll
+    PDE_H {
+        if (K > 0) a[h].c[0] = f[h][K];
+        else t[h].c[0] = f[h][0];
+    }
+    if constexpr (K > 0) jetv_compose_level<N, NP, K - 1>(t, a, f);
+}
+
+template <int N, int NP>
+__device__ __forceinline__ void jetv_compose(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
+#pragma unroll
+    PDE_H a[h].c[0] = f[h][N];
+    jetv_compose_level<N, NP, N - 1>(t, a, f);
 }
 #undef PDE_H
 

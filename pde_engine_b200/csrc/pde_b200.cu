@@ -179,6 +179,13 @@ static int upload_tables(const pde_session* s, cudaStream_t st) {
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_const, cv, sizeof(cv), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconst, rv, sizeof(rv), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow, pv, sizeof(pv), 0, cudaMemcpyHostToDevice, st));
+    // Taylor-ratio rows: x**k has f_{j+1}/f_j = (k - j)/(j + 1) / x_0; exp has 1/(j + 1)
+    double fr[kNRows][4];
+    for (int sl = 0; sl < kNRows; ++sl) {
+        const double k = sl < PDE_N_POW ? pv[sl] : -1.0;
+        for (int j = 0; j < 4; ++j) fr[sl][j] = sl == kRowExp ? 1.0 / (j + 1) : (k - j) / (j + 1);
+    }
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_frow, fr, sizeof(fr), 0, cudaMemcpyHostToDevice, st));
     return PDE_OK;
 }
 

@@ -28,26 +28,37 @@ constexpr int kMaxL = 256;
 __constant__ double c_const[PDE_N_CONST];
 __constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
 __constant__ double c_pow[PDE_N_POW];
+// Taylor-ratio rows of the scalar functions behind U_POW / U_INV / U_EXP: f_{j+1} = f_j * r * row[j]
+// (x**k: row[j] = (k - j)/(j + 1), r = 1/x_0;  exp: row[j] = 1/(j + 1), r = +-1)
+constexpr int kRowInv = PDE_N_POW, kRowExp = PDE_N_POW + 1, kNRows = PDE_N_POW + 2;
+__constant__ double c_frow[kNRows][4];
 
 // Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel so the interpreter's
-// code stays inside the 32 KB instruction cache: an earlier version that inlined the
-// bodies per call site ran at a 75 % i-cache hit rate (profiles/r1_v1_*).
-// Word layout (u32): bits 0-7 kind | 8-15 arg | 16-24 operand source for the U jet
-// (0 = none, SRC_SPILL = pop the spill stack, otherwise the leaf opcode byte).  The
-// operand fetch is one shared block in front of the dispatch, so a binary node with any
-// operand kind costs ONE dispatch (the dispatch tree was 23 % of all stall samples).
+// code stays inside the instruction cache: an earlier version that inlined the bodies per
+// call site ran at a 75 % i-cache hit rate (profiles/r1_v1_*).
+// Word layout (u32): bits 0-7 kind | 8-15 arg (constant slot, exponent slot or PRIM index).
+// The kinds are DENSE and the interpreter is one `switch` compiled with --jump-table-density:
+// a micro-op costs one indexed branch (LDC + BRX) instead of the 5-level compare tree of v5
+// (33 % of all warp stall samples were dispatch, profiles/README.md).  Binary bodies have one
+// entry per operand source (_S = pop the spill stack, _P = primitive table): the entry fetches
+// the operand jet U and falls into the shared body.
 enum UKind : uint8_t {
     U_END = 0,
-    U_SPILL,                          // S[sp++] = T
-    U_SETT,                           // T = U            (leaf materialisation: src = leaf)
-    U_ADD, U_SUB, U_RSUB, U_MUL, U_DIV, U_RDIV,   // T = T op U;  RSUB: U - T, RDIV: U / T
-    U_ADDC, U_SUBC, U_MULC,           // sparse leaf fast paths (arg = const slot; MULC bit7 = reciprocal)
+    U_SPILL,                                  // S[sp++] = T
+    U_SETV0, U_SETV1, U_SETC, U_SETP,         // T = leaf (first leaf of a sub-tree)
+    U_ADD_S, U_ADD_P,                         // T = T + U
+    U_SUB_P,                                  // T = T - U
+    U_RSUB_S,                                 // T = U - T
+    U_MUL_S, U_MUL_P,                         // T = T * U
+    U_DIV_P,                                  // T = T / U
+    U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
     U_NEG, U_ABS, U_SQRT, U_SQUARE,
-    U_EXP,                            // arg = 1: exp(-T)
-    U_POW                             // arg = exponent slot
+    U_INV,                                    // T = 1 / T          } one shared Horner body
+    U_EXP, U_EXPN,                            // exp(T), exp(-T)    } (jetv_compose), in place
+    U_POW,                                    // arg = exponent slot }
+    U_NKINDS
 };
-constexpr unsigned SRC_SPILL = 0x100;
 
 struct ValidateParams {
     const uint8_t* code;
@@ -56,7 +67,7 @@ struct ValidateParams {
     int L;
     const double* pts;    // [2][P]
     const double* tab;    // [cols][P]
-    const double* prim;   // [n_prim][NC][P]
+    const double* prim;   // [n_prim][P/32][16][32]: per 32-point stripe, coefficient-major, lanes contiguous
     int P;
     int ns;               // spill slots per lane
     double tau;
@@ -77,8 +88,9 @@ struct ValidateParams {
     double* scale;
 };
 
+__device__ __forceinline__ bool op_is_prim(unsigned b) { return b >= PDE_OP_PRIM0 && b < PDE_OP_PRIM0 + PDE_N_PRIM; }
 __device__ __forceinline__ bool op_is_leaf(unsigned b) {
-    return b == PDE_OP_VAR0 || b == PDE_OP_VAR1 || (b >= PDE_OP_PRIM0 && b < PDE_OP_PRIM0 + PDE_N_PRIM) || b >= PDE_OP_CONST0;
+    return b == PDE_OP_VAR0 || b == PDE_OP_VAR1 || op_is_prim(b) || b >= PDE_OP_CONST0;
 }
 __device__ __forceinline__ bool op_is_binary(unsigned b) { return b >= PDE_OP_ADD && b <= PDE_OP_DIV; }
 __device__ __forceinline__ bool op_is_unary(unsigned b) {
@@ -96,23 +108,26 @@ __host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 // spilled in stack order, leaves never occupy a jet.
 __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* vst, int ns_max) {
     int sp = 0, nu = 0, ns = 0, tpos = -1;
-    auto emit = [&](unsigned kind, unsigned arg, unsigned src) { uc[nu++] = kind | (arg << 8) | (src << 16); };
+    auto emit = [&](unsigned kind, unsigned arg) { uc[nu++] = kind | (arg << 8); };
     auto spill_t = [&]() -> bool {
         if (tpos < 0) return true;
         if (ns >= ns_max) return false;
-        emit(U_SPILL, 0, 0); vst[tpos] = V_JET_S; ++ns;
+        emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
         return true;
     };
-    // T = T op leaf (leaf on the right)
+    auto set_leaf = [&](unsigned leaf) {
+        if (leaf >= PDE_OP_CONST0) emit(U_SETC, leaf - PDE_OP_CONST0);
+        else if (op_is_prim(leaf)) emit(U_SETP, leaf - PDE_OP_PRIM0);
+        else emit(leaf == PDE_OP_VAR0 ? U_SETV0 : U_SETV1, 0);
+    };
+    // T = T op leaf (leaf on the right); o: 0 add 1 sub 2 mul 3 div
     auto bin_leaf_right = [&](unsigned o, unsigned leaf) {
         if (leaf >= PDE_OP_CONST0) {
-            const unsigned k = leaf - PDE_OP_CONST0;
-            emit(o == 0 ? U_ADDC : o == 1 ? U_SUBC : U_MULC, o == 3 ? (k | 0x80u) : k, 0);
+            emit(o == 0 ? U_ADDC : o == 1 ? U_SUBC : o == 2 ? U_MULC : U_MULRC, leaf - PDE_OP_CONST0);
         } else if (leaf == PDE_OP_VAR0 || leaf == PDE_OP_VAR1) {
-            const unsigned v = leaf - PDE_OP_VAR0;
-            emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + v, 0, 0);
+            emit((o == 0 ? U_ADDV0 : o == 1 ? U_SUBV0 : o == 2 ? U_MULV0 : U_DIVV0) + (leaf - PDE_OP_VAR0), 0);
         } else {
-            emit(o == 0 ? U_ADD : o == 1 ? U_SUB : o == 2 ? U_MUL : U_DIV, 0, leaf);     // PRIM operand
+            emit(o == 0 ? U_ADD_P : o == 1 ? U_SUB_P : o == 2 ? U_MUL_P : U_DIV_P, leaf - PDE_OP_PRIM0);
         }
     };
     for (int pc = 0; pc < len; ++pc) {
@@ -125,26 +140,26 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             if (top != V_JET_T) {
                 if (top == V_JET_S) return 1;
                 if (!spill_t()) return 2;
-                emit(U_SETT, 0, top);
+                set_leaf(top);
                 vst[sp - 1] = V_JET_T; tpos = sp - 1;
             }
             switch (b) {
-                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0, 0); break;
-                case PDE_OP_ABS: emit(U_ABS, 0, 0); break;
-                case PDE_OP_SQRT: emit(U_SQRT, 0, 0); break;
-                case PDE_OP_EXP: emit(U_EXP, 0, 0); break;
-                case PDE_OP_FN_INV: emit(U_RDIV, 0, PDE_OP_CONST0); break;         // 1 / T  (CONST(0) = 1)
-                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0, 0); break;
-                case PDE_OP_FN_POW32: emit(U_POW, 0, 0); break;
-                case PDE_OP_FN_POWN32: emit(U_POW, 1, 0); break;
-                case PDE_OP_FN_EXPNEG: emit(U_EXP, 1, 0); break;
+                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0); break;
+                case PDE_OP_ABS: emit(U_ABS, 0); break;
+                case PDE_OP_SQRT: emit(U_SQRT, 0); break;
+                case PDE_OP_EXP: emit(U_EXP, 0); break;
+                case PDE_OP_FN_INV: emit(U_INV, 0); break;
+                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0); break;
+                case PDE_OP_FN_POW32: emit(U_POW, 0); break;
+                case PDE_OP_FN_POWN32: emit(U_POW, 1); break;
+                case PDE_OP_FN_EXPNEG: emit(U_EXPN, 0); break;
                 default: {
                     const unsigned slot = b - PDE_OP_POW0;
                     const double k = c_pow[slot];
-                    if (k == 2.0) emit(U_SQUARE, 0, 0);
-                    else if (k == 0.5) emit(U_SQRT, 0, 0);
-                    else if (k == -1.0) emit(U_RDIV, 0, PDE_OP_CONST0);
-                    else emit(U_POW, slot, 0);
+                    if (k == 2.0) emit(U_SQUARE, 0);
+                    else if (k == 0.5) emit(U_SQRT, 0);
+                    else if (k == -1.0) emit(U_INV, 0);
+                    else emit(U_POW, slot);
                 }
             }
         } else if (op_is_binary(b)) {
@@ -152,18 +167,21 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             const unsigned bb = vst[sp - 1], aa = vst[sp - 2];
             sp -= 2;
             const unsigned o = b - PDE_OP_ADD;  // 0 add 1 sub 2 mul 3 div
-            if (aa == V_JET_S && bb == V_JET_T) {
-                emit(o == 0 ? U_ADD : o == 1 ? U_RSUB : o == 2 ? U_MUL : U_RDIV, 0, SRC_SPILL);   // S op T
+            if (aa == V_JET_S && bb == V_JET_T) {                                   // S op T
+                if (o == 3) { emit(U_INV, 0); emit(U_MUL_S, 0); }                   // S / T = S * (1 / T)
+                else emit(o == 0 ? U_ADD_S : o == 1 ? U_RSUB_S : U_MUL_S, 0);
                 --ns;
             } else if (aa == V_JET_T && bb != V_JET_S) {
                 bin_leaf_right(o, bb);
             } else if (bb == V_JET_T && aa != V_JET_S) {
                 if (o == 0 || o == 2) bin_leaf_right(o, aa);                        // commutative
-                else if (o == 1) { emit(U_NEG, 0, 0); bin_leaf_right(0, aa); }      // leaf - T = -T + leaf
-                else emit(U_RDIV, 0, aa);                                           // leaf / T
+                else if (o == 1) {                                                  // leaf - T
+                    if (aa >= PDE_OP_CONST0) emit(U_RSUBC, aa - PDE_OP_CONST0);
+                    else { emit(U_NEG, 0); bin_leaf_right(0, aa); }
+                } else { emit(U_INV, 0); bin_leaf_right(2, aa); }                   // leaf / T = (1 / T) * leaf
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
                 if (!spill_t()) return 2;
-                emit(U_SETT, 0, aa);
+                set_leaf(aa);
                 bin_leaf_right(o, bb);
             } else {
                 return 1;
@@ -174,83 +192,74 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
         }
     }
     if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) emit(U_SETT, 0, vst[0]);
-    emit(U_END, 0, 0);
+    if (vst[0] != V_JET_T) set_leaf(vst[0]);
+    emit(U_END, 0);
+    emit(U_END, 0);      // the interpreter prefetches two words ahead
     return 0;
 }
 
 template <int N>
 struct PointCtx {
     double x0, x1;
-    int pt;
-    int P;
-    const double* prim;
+    const double* prim;   // this point's slot in PRIM(0)'s stripe block: coefficient g at [g * 32]
 };
+
+__device__ __forceinline__ double opaque_zero() {
+    double z;
+    asm volatile("mov.f64 %0, 0d0000000000000000;" : "=d"(z));
+    return z;
+}
+template <int N>
+__device__ __forceinline__ void jet_fill(Jet<N>& t, double v) {
+#pragma unroll
+    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = v;
+}
+
+// 1/x without letting the compiler hoist it out of the interpreter loop (only DIVV needs it)
+__device__ __forceinline__ double lazy_rcp(double x) {
+    double r;
+    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 
 // Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
 // Spill layout: [(slot * NC + coef) * NP + point][thread]  (conflict free).
 template <int N, int NP>
 __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, double* __restrict__ spill, int stride,
-                                            const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
+                                            size_t prim_stride, const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
     constexpr int NC = Jet<N>::NC;
     Jet<N> U[NP];
+    double f[NP][N + 1], rr[NP];
+    int row = 0;
     int sp = 0;  // spill depth
-    int pc = 0;
     unsigned ins = uc[0], ins_next = uc[1];
+    uc += 2;
 #define PDE_EACH for (int h = 0; h < NP; ++h)
+#define PDE_FETCH_S                                                                          \
+    {                                                                                        \
+        --sp;                                                                                \
+        const double* from = spill + (size_t)sp * NC * NP * stride;                          \
+        _Pragma("unroll") PDE_EACH {                                                         \
+            _Pragma("unroll") for (int g = 0; g < NC; ++g) U[h].c[g] = from[(g * NP + h) * stride]; \
+        }                                                                                    \
+    }
+#define PDE_FETCH_P                                                                          \
+    {                                                                                        \
+        _Pragma("unroll") PDE_EACH {                                                         \
+            const double* from = cx[h].prim + (size_t)arg * prim_stride;                     \
+            _Pragma("unroll") for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(from + g * 32); \
+        }                                                                                    \
+    }
 #pragma unroll 1
     for (;;) {
-        const unsigned kind = ins & 0xffu, arg = (ins >> 8) & 0xffu, src = ins >> 16;
-        if (kind == U_END) return;
+        const unsigned kind = ins & 0xffu, arg = ins >> 8;
         ins = ins_next;
-        pc += 1;
-        ins_next = uc[pc + 1];     // two-deep prefetch: the LDS latency hides even behind one-instruction bodies
-        if (kind == U_SETT) {      // first leaf of a sub-tree: T = leaf, no detour through U
-            if (src >= PDE_OP_PRIM0 && src < PDE_OP_PRIM0 + PDE_N_PRIM) {
-#pragma unroll
-                PDE_EACH {
-                    const double* from = cx[h].prim + (size_t)(src - PDE_OP_PRIM0) * NC * cx[h].P + cx[h].pt;
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(from + (size_t)g * cx[h].P);
-                }
-            } else {
-#pragma unroll
-                PDE_EACH {
-                    const double v = src >= PDE_OP_CONST0 ? c_const[src - PDE_OP_CONST0] : src == PDE_OP_VAR0 ? cx[h].x0 : cx[h].x1;
-                    jet_set_const(T[h], v);
-                    T[h].c[1] = src == PDE_OP_VAR0 ? 1.0 : 0.0;
-                    T[h].c[2] = src == PDE_OP_VAR1 ? 1.0 : 0.0;
-                }
-            }
-            continue;
-        }
-        if (src != 0) {            // shared operand fetch: U = spilled jet | primitive table | const | coordinate
-            if (src == SRC_SPILL) {
-                --sp;
-                const double* from = spill + (size_t)sp * NC * NP * stride;
-#pragma unroll
-                PDE_EACH {
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) U[h].c[g] = from[(g * NP + h) * stride];
-                }
-            } else if (src >= PDE_OP_PRIM0 && src < PDE_OP_PRIM0 + PDE_N_PRIM) {
-#pragma unroll
-                PDE_EACH {
-                    const double* from = cx[h].prim + (size_t)(src - PDE_OP_PRIM0) * NC * cx[h].P + cx[h].pt;
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(from + (size_t)g * cx[h].P);
-                }
-            } else {
-#pragma unroll
-                PDE_EACH {
-                    const double v = src >= PDE_OP_CONST0 ? c_const[src - PDE_OP_CONST0] : src == PDE_OP_VAR0 ? cx[h].x0 : cx[h].x1;
-                    jet_set_const(U[h], v);
-                    U[h].c[1] = src == PDE_OP_VAR0 ? 1.0 : 0.0;
-                    U[h].c[2] = src == PDE_OP_VAR1 ? 1.0 : 0.0;
-                }
-            }
-        }
+        ins_next = *uc++;          // two-deep prefetch: the LDS latency hides even behind one-instruction bodies
         switch (kind) {
+            case U_END: return;
             case U_SPILL: {
                 double* dst = spill + (size_t)sp * NC * NP * stride;
 #pragma unroll
@@ -260,20 +269,54 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                 }
                 ++sp;
             } break;
-            case U_ADD:
+            // The SET bodies go through an opaque zero: a case that only assigns constants becomes an
+            // EMPTY block, the indexed branch then jumps straight to the loop header and the header's
+            // phi copies (30 register moves) land in front of the branch -- executed by EVERY micro-op.
+            case U_SETV0: {
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x0; T[h].c[1] = z + 1.0; }
+            } break;
+            case U_SETV1: {
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x1; T[h].c[2] = z + 1.0; }
+            } break;
+            case U_SETC: {
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = c_const[arg]; }
+            } break;
+            case U_SETP:
+#pragma unroll
+                PDE_EACH {
+                    const double* from = cx[h].prim + (size_t)arg * prim_stride;
+#pragma unroll
+                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(from + g * 32);
+                }
+                break;
+            case U_ADD_S: PDE_FETCH_S goto l_add;
+            case U_ADD_P: PDE_FETCH_P
+            l_add:
 #pragma unroll
                 PDE_EACH jet_add(T[h], U[h]);
                 break;
-            case U_SUB:
+            case U_SUB_P: PDE_FETCH_P
 #pragma unroll
                 PDE_EACH jet_sub(T[h], U[h]);
                 break;
-            case U_RSUB:
+            case U_RSUB_S: PDE_FETCH_S
 #pragma unroll
                 PDE_EACH jet_rsub(T[h], U[h]);
                 break;
-            case U_MUL: jetv_mul<N, NP>(T, U); break;
-            case U_DIV: jetv_div<N, NP>(T, U); break;
+            case U_MUL_S: PDE_FETCH_S goto l_mul;
+            case U_MUL_P: PDE_FETCH_P
+            l_mul:
+                jetv_mul<N, NP>(T, U);
+                break;
+            case U_DIV_P: PDE_FETCH_P
+                jetv_div<N, NP>(T, U);
+                break;
             case U_ADDC:
 #pragma unroll
                 PDE_EACH T[h].c[0] += c_const[arg];
@@ -282,11 +325,18 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
 #pragma unroll
                 PDE_EACH T[h].c[0] -= c_const[arg];
                 break;
-            case U_MULC: {
-                const double c = (arg & 0x80u) ? c_rconst[arg & 0x7fu] : c_const[arg];
+            case U_RSUBC:
 #pragma unroll
-                PDE_EACH jet_scale(T[h], c);
-            } break;
+                PDE_EACH { jet_neg(T[h]); T[h].c[0] += c_const[arg]; }
+                break;
+            case U_MULC:
+#pragma unroll
+                PDE_EACH jet_scale(T[h], c_const[arg]);
+                break;
+            case U_MULRC:
+#pragma unroll
+                PDE_EACH jet_scale(T[h], c_rconst[arg]);
+                break;
             case U_ADDV0:
 #pragma unroll
                 PDE_EACH { T[h].c[0] += cx[h].x0; T[h].c[1] += 1.0; }
@@ -313,11 +363,11 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                 break;
             case U_DIVV0:
 #pragma unroll
-                PDE_EACH jet_div_var(T[h], 0, cx[h].x0);
+                PDE_EACH jet_div_var(T[h], 0, lazy_rcp(cx[h].x0));
                 break;
             case U_DIVV1:
 #pragma unroll
-                PDE_EACH jet_div_var(T[h], 1, cx[h].x1);
+                PDE_EACH jet_div_var(T[h], 1, lazy_rcp(cx[h].x1));
                 break;
             case U_NEG:
 #pragma unroll
@@ -329,26 +379,41 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                 break;
             case U_SQRT: jetv_sqrt<N, NP>(T); break;
             case U_SQUARE: jetv_square<N, NP>(T); break;
-            // out-of-place bodies compute into U and copy back (jet_copy is opaque to the
-            // register allocator, see jet.cuh)
-            case U_RDIV:
-                jetv_div<N, NP>(U, T);
+            // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
+            // shared in-place Horner body
+            case U_INV:
 #pragma unroll
-                PDE_EACH jet_copy(T[h], U[h]);
-                break;
+                PDE_EACH { rr[h] = fast_rcp(T[h].c[0]); f[h][0] = rr[h]; }
+                row = kRowInv;
+                goto l_compose;
             case U_EXP:
-                jetv_exp<N, NP>(U, T, arg != 0);
 #pragma unroll
-                PDE_EACH jet_copy(T[h], U[h]);
-                break;
+                PDE_EACH { f[h][0] = exp(T[h].c[0]); rr[h] = 1.0; }
+                row = kRowExp;
+                goto l_compose;
+            case U_EXPN:
+#pragma unroll
+                PDE_EACH { f[h][0] = exp(-T[h].c[0]); rr[h] = -1.0; }
+                row = kRowExp;
+                goto l_compose;
             case U_POW:
-                jetv_pow<N, NP>(U, T, c_pow[arg]);
 #pragma unroll
-                PDE_EACH jet_copy(T[h], U[h]);
+                PDE_EACH { f[h][0] = pow0(T[h].c[0], c_pow[arg]); rr[h] = fast_rcp(T[h].c[0]); }
+                row = (int)arg;
+            l_compose:
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double cj = c_frow[row][j];
+#pragma unroll
+                    PDE_EACH f[h][j + 1] = f[h][j] * (rr[h] * cj);
+                }
+                jetv_compose<N, NP>(T, U, f);
                 break;
-            default: return;
+            default: __builtin_unreachable();
         }
     }
+#undef PDE_FETCH_S
+#undef PDE_FETCH_P
 #undef PDE_EACH
 }
 
@@ -476,6 +541,7 @@ validate_kernel(const ValidateParams p) {
             const uint32_t* uc = reinterpret_cast<const uint32_t*>(smem + per_cand * c + 2 * Lp);
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
+            const size_t prim_stride = (size_t)p.P * 16;
 #pragma unroll 1
             for (int stripe = warp * 32 * NP; stripe < p.P; stripe += TPB * NP) {
                 PointCtx<N> cx[NP];
@@ -489,13 +555,15 @@ validate_kernel(const ValidateParams p) {
                     cx[0].x1 = __ldg(p.pts + p.P + stripe + lane);
                 }
                 double coef[NP][Res::COLS];
+                int pt[NP];
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
-                    cx[h].pt = stripe + NP * lane + h; cx[h].P = p.P; cx[h].prim = p.prim;
-                    Res::fetch(p.tab, p.P, cx[h].pt, coef[h]);      // issued early: latency hides behind the program
+                    pt[h] = stripe + NP * lane + h;
+                    cx[h].prim = p.prim + (size_t)(pt[h] >> 5) * (16 * 32) + (pt[h] & 31);   // coalesced, immediate offsets
+                    Res::fetch(p.tab, p.P, pt[h], coef[h]);      // issued early: latency hides behind the program
                 }
                 Jet<N> T[NP];
-                run_program<N, NP>(uc, s_spill, TPB, cx, T);
+                run_program<N, NP>(uc, s_spill, TPB, prim_stride, cx, T);
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
                     double R, S;
@@ -503,10 +571,10 @@ validate_kernel(const ValidateParams p) {
                     if (DUMP) {
                         if (p.jets) {
 #pragma unroll
-                            for (int g = 0; g < NC; ++g) p.jets[((size_t)cand * NC + g) * p.P + cx[h].pt] = T[h].c[g];
+                            for (int g = 0; g < NC; ++g) p.jets[((size_t)cand * NC + g) * p.P + pt[h]] = T[h].c[g];
                         }
-                        if (p.resid) p.resid[(size_t)cand * p.P + cx[h].pt] = R;
-                        if (p.scale) p.scale[(size_t)cand * p.P + cx[h].pt] = S;
+                        if (p.resid) p.resid[(size_t)cand * p.P + pt[h]] = R;
+                        if (p.scale) p.scale[(size_t)cand * p.P + pt[h]] = S;
                     } else {
                         const double aR = fabs(R);
                         const bool fin = (aR <= 1.79769313486231570e308) && (S <= 1.79769313486231570e308) && (S > 0.0);
@@ -517,9 +585,9 @@ validate_kernel(const ValidateParams p) {
                             if (ratio > best_ratio) { best_ratio = ratio; best_S = S; }
                             max_R = fmax(max_R, aR);
                         }
-                        if (p.ref_rs && cx[h].pt < p.n_ref) {
-                            p.ref_rs[((size_t)cand * p.n_ref + cx[h].pt) * 2 + 0] = R;
-                            p.ref_rs[((size_t)cand * p.n_ref + cx[h].pt) * 2 + 1] = S;
+                        if (p.ref_rs && pt[h] < p.n_ref) {
+                            p.ref_rs[((size_t)cand * p.n_ref + pt[h]) * 2 + 0] = R;
+                            p.ref_rs[((size_t)cand * p.n_ref + pt[h]) * 2 + 1] = S;
                         }
                     }
                 }

@@ -66,8 +66,11 @@ def test_synth_validate_matches_oracle(cuda_device):
     osess = op.Session.for_problem("force_free")
     opts = np.ascontiguousarray(pts.T)
     oprim = [J.evaluate(op.compile_expr(s, osess).whole(), opts, 4, osess.const_vals, osess.pow_vals) for s in osyn.PRIM_EXPRS]
-    np.testing.assert_allclose(prim_t.cpu().numpy()[0], oprim[0], rtol=1e-13, atol=1e-15)
-    np.testing.assert_allclose(prim_t.cpu().numpy()[1], oprim[1], rtol=1e-13, atol=1e-15)
+    from pde_engine_b200.synthetic import unpack_primitive_table
+    assert tuple(prim_t.shape) == (2, P // 32, 16, 32)           # packed stripe-block device table
+    prim_np = unpack_primitive_table(prim_t, 15).cpu().numpy()
+    np.testing.assert_allclose(prim_np[0], oprim[0], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(prim_np[1], oprim[1], rtol=1e-13, atol=1e-15)
     n_cmp = n_bad_j = n_bad_r = 0
     for i, w in enumerate(osyn.trees(osyn.SEED_TREES, 0, n, 5)):
         u = J.evaluate(w, opts, 4, osess.const_vals, osess.pow_vals, oprim)

@@ -42,8 +42,37 @@ def _oracle_eval(problem, strs, pts_soa):
     return out
 
 
-def _compare_points(jets, resid, scale, oracle, strs):
+_OPAQUE = None
+
+
+def _exact_jet(problem, s, point, order):
+    """Normalised Taylor coefficients of u at one point from SymPy's exact derivatives (50 digits):
+    the arbiter when two float64 evaluation orders of an ill-conditioned jet disagree."""
+    import math
+    import sympy as sp
+    global _OPAQUE
+    if _OPAQUE is None:   # expression_operations.py:30-60 as sympify locals (GM:85-93)
+        _OPAQUE = {"neg": lambda x: -x, "inv": lambda x: 1 / x, "square": lambda x: x ** 2,
+                   "pow_3_2": lambda x: x ** sp.Rational(3, 2), "pow_neg_3_2": lambda x: x ** sp.Rational(-3, 2),
+                   "exp_neg": lambda x: sp.exp(-x)}
+    sess = op.Session.for_problem(problem)
+    v0, v1 = (sp.Symbol(n, real=True) for n in sess.var_names)
+    loc = dict(_OPAQUE); loc[sess.var_names[0]] = v0; loc[sess.var_names[1]] = v1
+    for k, v in sess.named_consts.items():
+        loc[k] = sp.nsimplify(v)
+    e = op.to_sympy(op.compile_expr(s, sess).whole(), sess, loc)
+    at = {v0: sp.Float(float(point[0]), 60), v1: sp.Float(float(point[1]), 60)}
+    out = np.zeros(J.ncoef(order))
+    for n in range(order + 1):
+        for j in range(n + 1):
+            d = sp.diff(e, v0, n - j, v1, j) if n else e
+            out[J.idx(n - j, j)] = float(sp.re(d.subs(at).evalf(50))) / (math.factorial(n - j) * math.factorial(j))
+    return out
+
+
+def _compare_points(jets, resid, scale, oracle, strs, problem=None, pts=None):
     n_cmp = 0
+    n_arbitrated = 0
     for i, o in enumerate(oracle):
         if o is None:
             continue
@@ -60,7 +89,20 @@ def _compare_points(jets, resid, scale, oracle, strs):
         err = np.max(np.abs(gj[:, ok] - u[:, ok]), axis=0)
         # value + first derivatives: cancellation free -> tight; higher orders relative to the jet magnitude
         assert np.all(np.abs(gj[:3, ok] - u[:3, ok]) <= RTOL * np.maximum(np.abs(u[:3, ok]), 1e-3 * mag + 1e-300)), strs[i]
-        assert np.all(err <= 1e-8 * mag + 1e-300), strs[i]
+        bad = np.flatnonzero(err > 1e-8 * mag + 1e-300)
+        if bad.size:
+            # Ill-conditioned jets (a smooth function written through a pole, e.g. inv(z/(1 - rho**2 + z**2))
+            # next to the pole of the inner quotient): the oracle's float64 recurrence is itself only
+            # accurate to ~1e-8 there, so two correct evaluation orders differ.  Arbitrate with exact
+            # derivatives: the device must be as accurate as the float64 oracle (up to a small factor).
+            assert problem is not None and bad.size <= 4, (strs[i], bad.size)
+            cols = np.flatnonzero(ok)[bad]
+            for c in cols:
+                ex = _exact_jet(problem, strs[i], pts[:, c], 4 if problem == "force_free" else 2)
+                e_dev = np.max(np.abs(gj[:, c] - ex)); e_orc = np.max(np.abs(u[:, c] - ex))
+                assert e_dev <= 4 * e_orc + 1e-9 * np.max(np.abs(ex)), (strs[i], c, e_dev, e_orc)
+                n_arbitrated += 1
+            assert n_arbitrated <= 40
         okr = ok & np.isfinite(R) & np.isfinite(S) & np.isfinite(gR) & np.isfinite(gS) & (S > 0)
         # a (numerically) constant u has derivatives, R and S at pure round-off level: nothing to compare
         magf = np.zeros(u.shape[1])
@@ -85,7 +127,7 @@ def test_eval_points_matches_oracle(problem, cuda_device, enum_ff, enum_kerr):
                                         pts_t, tab_t, None, spill_slots=8)
     torch.cuda.synchronize()
     oracle = _oracle_eval(problem, strs, pts)
-    n = _compare_points(jets.cpu().numpy(), resid.cpu().numpy(), scale.cpu().numpy(), oracle, strs)
+    n = _compare_points(jets.cpu().numpy(), resid.cpu().numpy(), scale.cpu().numpy(), oracle, strs, problem, pts)
     assert n > 0.8 * 64 * len(strs) * 0.8
 
 
