@@ -389,6 +389,9 @@ __device__ __forceinline__ void jet_abs(Jet<N>& t) {
 // ---------------------------------------------------------------------------------
 #define PDE_H for (int h = 0; h < NP; ++h)
 
+// One accumulator chain per output coefficient: the 15 outputs are independent, which is all the
+// ILP the in-order issue needs, and every extra instruction costs an issue slot (a second chain
+// per output added 14 DADDs to the 70 multiply-adds).
 template <int N, int NP>
 __device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP]) {
 #pragma unroll
@@ -396,26 +399,20 @@ __device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP])
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
-            double acc[NP], acc1[NP];
+            double acc[NP];
 #pragma unroll
-            PDE_H { acc[h] = t[h].c[jidx(gi, gj)] * u[h].c[0]; acc1[h] = 0.0; }
-            int cnt = 0;
+            PDE_H acc[h] = t[h].c[jidx(gi, gj)] * u[h].c[0];
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == gi && bj == gj) continue;
-                    if ((cnt++ & 1) == 0) {
 #pragma unroll
-                        PDE_H acc1[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc1[h]);
-                    } else {
-#pragma unroll
-                        PDE_H acc[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc[h]);
-                    }
+                    PDE_H acc[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc[h]);
                 }
             }
 #pragma unroll
-            PDE_H t[h].c[jidx(gi, gj)] = cnt > 0 ? acc[h] + acc1[h] : acc[h];
+            PDE_H t[h].c[jidx(gi, gj)] = acc[h];
         }
     }
 }
@@ -431,26 +428,20 @@ __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP])
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
-            double acc[NP], acc1[NP];
+            double acc[NP];
 #pragma unroll
-            PDE_H { acc[h] = t[h].c[jidx(gi, gj)]; acc1[h] = 0.0; }
-            int cnt = 0;
+            PDE_H acc[h] = t[h].c[jidx(gi, gj)];
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == 0 && bj == 0) continue;
-                    if ((cnt++ & 1) == 0) {
 #pragma unroll
-                        PDE_H acc[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc[h]);
-                    } else {
-#pragma unroll
-                        PDE_H acc1[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc1[h]);
-                    }
+                    PDE_H acc[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc[h]);
                 }
             }
 #pragma unroll
-            PDE_H t[h].c[jidx(gi, gj)] = (cnt > 1 ? acc[h] + acc1[h] : acc[h]) * r0[h];
+            PDE_H t[h].c[jidx(gi, gj)] = acc[h] * r0[h];
         }
     }
 }
@@ -617,7 +608,7 @@ __device__ __forceinline__ void jetv_compose_level(Jet<N> (&t)[NP], Jet<N> (&a)[
         for (int gj = 0; gj <= m; ++gj) {
             const int gi = m - gj;
             const int nterms = (gi + 1) * (gj + 1) - 1;
-            const bool two = nterms > 3;      // long sums: two chains halve the dependent-DFMA depth
+            const bool two = false;           // one chain per output (independent outputs supply the ILP)
             double acc[NP], acc1[NP];
 #pragma unroll
             PDE_H { acc[h] = 0.0; acc1[h] = 0.0; }

@@ -179,11 +179,10 @@ static int upload_tables(const pde_session* s, cudaStream_t st) {
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_const, cv, sizeof(cv), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconst, rv, sizeof(rv), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow, pv, sizeof(pv), 0, cudaMemcpyHostToDevice, st));
-    // Taylor-ratio rows: x**k has f_{j+1}/f_j = (k - j)/(j + 1) / x_0; exp has 1/(j + 1)
+    // Taylor-ratio rows: x**k has f_{j+1}/f_j = (k - j)/(j + 1) / x_0
     double fr[kNRows][4];
     for (int sl = 0; sl < kNRows; ++sl) {
-        const double k = sl < PDE_N_POW ? pv[sl] : -1.0;
-        for (int j = 0; j < 4; ++j) fr[sl][j] = sl == kRowExp ? 1.0 / (j + 1) : (k - j) / (j + 1);
+        for (int j = 0; j < 4; ++j) fr[sl][j] = (pv[sl] - j) / (j + 1);
     }
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_frow, fr, sizeof(fr), 0, cudaMemcpyHostToDevice, st));
     return PDE_OK;
@@ -213,12 +212,15 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
     return PDE_OK;
 }
 
-// Kernel configuration: W warps per CTA sweep a round of W candidates together.
-//   W = 16 (one 512-thread CTA per SM, 122 registers): every warp of the SM runs the same micro-op
-//          stream -> one i-cache working set per SM; needs >= 16 stripes per candidate to keep the warps busy;
-//   W = 4  (four CTAs per SM): small grids, or spill areas too large for the 16-warp CTA.
+// Kernel configuration: a CTA is W/4 groups of 4 warps (validate.cuh).  One CTA per SM:
+//   W = 24 (768 threads, 80 registers): most warps per scheduler; fits up to 2 spill slots per lane;
+//   W = 16 (512 threads, 104 registers): up to 3 spill slots;
+//   W = 4  (four 128-thread CTAs per SM): small grids / deep spill stacks, and the DUMP (tooling) mode.
 // Two points per lane in separate registers (NP = 2) was measured SLOWER on B200 (204 registers -> 8 warps
-// per SM, or 168 with spills; i-cache hit rate 75-93 %), see DESIGN.md 4.1.  PDE_B200_VARIANT=4 forces W = 4.
+// per SM, or 168 with spills), see DESIGN.md 4.1.  PDE_B200_VARIANT=4|16 forces a smaller configuration.
+#ifndef PDE_W_BIG
+#define PDE_W_BIG 24
+#endif
 static int g_variant = -1;
 template <int PROBLEM, bool DUMP>
 static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
@@ -226,8 +228,12 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
     if constexpr (DUMP) {
         return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4>(vp, st, nullptr);
     } else {
-        if (g_variant != 4 && vp.P >= 1024) {
-            bool fits = false;
+        bool fits = false;
+        if (g_variant != 4 && g_variant != 16 && vp.P >= 128) {
+            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, 1, 1>(vp, st, &fits);
+            if (rc || fits) return rc;
+        }
+        if (g_variant != 4 && PDE_W_BIG != 16 && vp.P >= 128) {
             int rc = launch_validate_cfg<PROBLEM, DUMP, 16, 1, 1>(vp, st, &fits);
             if (rc || fits) return rc;
         }

@@ -28,9 +28,8 @@ constexpr int kMaxL = 256;
 __constant__ double c_const[PDE_N_CONST];
 __constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
 __constant__ double c_pow[PDE_N_POW];
-// Taylor-ratio rows of the scalar functions behind U_POW / U_INV / U_EXP: f_{j+1} = f_j * r * row[j]
-// (x**k: row[j] = (k - j)/(j + 1), r = 1/x_0;  exp: row[j] = 1/(j + 1), r = +-1)
-constexpr int kRowInv = PDE_N_POW, kRowExp = PDE_N_POW + 1, kNRows = PDE_N_POW + 2;
+// Taylor-ratio rows of x**k (U_POW): f_{j+1} = f_j * row[j] / x_0, row[j] = (k - j)/(j + 1)
+constexpr int kNRows = PDE_N_POW;
 __constant__ double c_frow[kNRows][4];
 
 // Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel so the interpreter's
@@ -51,6 +50,7 @@ enum UKind : uint8_t {
     U_RSUB_S,                                 // T = U - T
     U_MUL_S, U_MUL_P,                         // T = T * U
     U_DIV_P,                                  // T = T / U
+    U_RDIV_S, U_RDIV_P,                       // T = U / T  (in place on U, copied back)
     U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
     U_NEG, U_ABS, U_SQRT, U_SQUARE,
@@ -168,8 +168,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             sp -= 2;
             const unsigned o = b - PDE_OP_ADD;  // 0 add 1 sub 2 mul 3 div
             if (aa == V_JET_S && bb == V_JET_T) {                                   // S op T
-                if (o == 3) { emit(U_INV, 0); emit(U_MUL_S, 0); }                   // S / T = S * (1 / T)
-                else emit(o == 0 ? U_ADD_S : o == 1 ? U_RSUB_S : U_MUL_S, 0);
+                emit(o == 0 ? U_ADD_S : o == 1 ? U_RSUB_S : o == 2 ? U_MUL_S : U_RDIV_S, 0);
                 --ns;
             } else if (aa == V_JET_T && bb != V_JET_S) {
                 bin_leaf_right(o, bb);
@@ -178,7 +177,8 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                 else if (o == 1) {                                                  // leaf - T
                     if (aa >= PDE_OP_CONST0) emit(U_RSUBC, aa - PDE_OP_CONST0);
                     else { emit(U_NEG, 0); bin_leaf_right(0, aa); }
-                } else { emit(U_INV, 0); bin_leaf_right(2, aa); }                   // leaf / T = (1 / T) * leaf
+                } else if (op_is_prim(aa)) emit(U_RDIV_P, aa - PDE_OP_PRIM0);        // PRIM / T
+                else { emit(U_INV, 0); bin_leaf_right(2, aa); }                     // x / T = (1 / T) * x (sparse)
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
                 if (!spill_t()) return 2;
                 set_leaf(aa);
@@ -232,8 +232,7 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                                             size_t prim_stride, const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
     constexpr int NC = Jet<N>::NC;
     Jet<N> U[NP];
-    double f[NP][N + 1], rr[NP];
-    int row = 0;
+    double f[NP][N + 1];
     int sp = 0;  // spill depth
     unsigned ins = uc[0], ins_next = uc[1];
     uc += 2;
@@ -317,6 +316,15 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
             case U_DIV_P: PDE_FETCH_P
                 jetv_div<N, NP>(T, U);
                 break;
+            // U / T: the division runs in place on the numerator U; the copy back is opaque to the
+            // register allocator (jet_copy, jet.cuh) and costs 30 moves against 76 FP64 instructions
+            case U_RDIV_S: PDE_FETCH_S goto l_rdiv;
+            case U_RDIV_P: PDE_FETCH_P
+            l_rdiv:
+                jetv_div<N, NP>(U, T);
+#pragma unroll
+                PDE_EACH jet_copy(T[h], U[h]);
+                break;
             case U_ADDC:
 #pragma unroll
                 PDE_EACH T[h].c[0] += c_const[arg];
@@ -381,32 +389,40 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
             case U_SQUARE: jetv_square<N, NP>(T); break;
             // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
             // shared in-place Horner body
-            case U_INV:
+            case U_INV:                      // f_j = (-1)^j / x^(j+1)
 #pragma unroll
-                PDE_EACH { rr[h] = fast_rcp(T[h].c[0]); f[h][0] = rr[h]; }
-                row = kRowInv;
-                goto l_compose;
-            case U_EXP:
+                PDE_EACH {
+                    const double r = fast_rcp(T[h].c[0]);
+                    f[h][0] = r;
 #pragma unroll
-                PDE_EACH { f[h][0] = exp(T[h].c[0]); rr[h] = 1.0; }
-                row = kRowExp;
-                goto l_compose;
-            case U_EXPN:
-#pragma unroll
-                PDE_EACH { f[h][0] = exp(-T[h].c[0]); rr[h] = -1.0; }
-                row = kRowExp;
-                goto l_compose;
-            case U_POW:
-#pragma unroll
-                PDE_EACH { f[h][0] = pow0(T[h].c[0], c_pow[arg]); rr[h] = fast_rcp(T[h].c[0]); }
-                row = (int)arg;
-            l_compose:
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const double cj = c_frow[row][j];
-#pragma unroll
-                    PDE_EACH f[h][j + 1] = f[h][j] * (rr[h] * cj);
+                    for (int j = 0; j < N; ++j) f[h][j + 1] = -f[h][j] * r;
                 }
+                goto l_compose;
+            case U_EXP:                      // f_j = exp(x) / j!
+#pragma unroll
+                PDE_EACH {
+                    f[h][0] = exp(T[h].c[0]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (1.0 / (j + 1));
+                }
+                goto l_compose;
+            case U_EXPN:                     // f_j = (-1)^j exp(-x) / j!
+#pragma unroll
+                PDE_EACH {
+                    f[h][0] = exp(-T[h].c[0]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (-1.0 / (j + 1));
+                }
+                goto l_compose;
+            case U_POW:                      // f_{j+1} = f_j (k - j)/(j + 1) / x
+#pragma unroll
+                PDE_EACH {
+                    const double r = fast_rcp(T[h].c[0]);
+                    f[h][0] = pow0(T[h].c[0], c_pow[arg]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (r * c_frow[arg][j]);
+                }
+            l_compose:
                 jetv_compose<N, NP>(T, U, f);
                 break;
             default: __builtin_unreachable();
@@ -468,14 +484,16 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
 };
 
 // ---------------------------------------------------------------------------------
-// Work decomposition.  A warp OWNS a candidate: it stages + translates its bytecode and
-// each of its lanes owns collocation points (two per 64-point stripe, one LDG.128 per
-// coordinate).  W warps of a CTA run their W candidates as a round: after every warp has
-// translated its own candidate, the W warps sweep the candidates of the round TOGETHER
-// (warp w takes stripes w, w+W, ... of each candidate) so that all warps of the CTA
-// execute the same micro-op stream at the same time -- one instruction-cache working
-// set per CTA instead of one per warp (v1 ran at a 75 % i-cache hit rate) -- and the
-// per-candidate votes/maxima are combined by warp shuffles + one shared-memory row.
+// Work decomposition.  Warps own candidates, lanes own collocation points.  A CTA is G groups
+// of 4 warps -- one warp of a group on each of the SM's four schedulers (warp id mod 4).  A group
+// takes a chunk of 4 consecutive candidates: each of its warps stages + translates one of them,
+// then the 4 warps sweep the chunk's candidates one after the other (warp wg takes the 32-point
+// stripes wg, wg+4, ...), so a candidate's micro-op stream is fetched by all four schedulers at
+// the same time.  Different groups are at different candidates, hence the warps that SHARE a
+// scheduler are in different phases (one dispatching or fetching an operand while another streams
+// DFMAs): v5/v6 swept one candidate with all 16 warps in lockstep and the FP64 pipe idled whenever
+// the whole SM was in a dispatch phase (66 % pipe-active, profiles/README.md).  Groups never
+// synchronise with each other (named barriers, 128 threads); chunks are dealt round-robin.
 // ---------------------------------------------------------------------------------
 struct WarpPartial {
     double best_ratio, best_S, max_R;
@@ -484,11 +502,15 @@ struct WarpPartial {
 
 template <int N, int NP>
 __host__ __device__ constexpr size_t cta_smem_bytes(int L, int ns, int W) {
-    // per candidate of the round: code[L] | vstack[L] | ucode[2L+4] u32 ; then partials[W][W] ; then
+    // per warp: code[L] | vstack[L] | ucode[2L+6] u32 ; then partials[W][4] ; status[W] ; then
     // spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
     return ((size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 4 + 15) / 16 * 16) * W +
-           (size_t)W * W * sizeof(WarpPartial) + 16 * W +
+           (size_t)W * 4 * sizeof(WarpPartial) + 16 * W +
            (size_t)ns * Jet<N>::NC * NP * 32 * W * 8;
+}
+
+__device__ __forceinline__ void group_barrier(int g) {
+    asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 }
 
 template <int PROBLEM, bool DUMP, int W, int NP, int MINB>
@@ -498,8 +520,11 @@ validate_kernel(const ValidateParams p) {
     constexpr int N = Res::N;
     constexpr int NC = Jet<N>::NC;
     constexpr int TPB = W * 32;
+    constexpr int G = W / 4;
+    static_assert(W % 4 == 0, "a CTA is made of 4-warp groups");
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 2, wg = warp & 3;
     const int Lp = (p.L + 15) / 16 * 16;
     const int ucb = (kUcodeMax(p.L) * 4 + 15) / 16 * 16;
     const size_t per_cand = (size_t)Lp * 2 + ucb;
@@ -507,16 +532,16 @@ validate_kernel(const ValidateParams p) {
     uint8_t* s_code = my;
     uint8_t* s_vst = my + Lp;
     uint32_t* s_uc_mine = reinterpret_cast<uint32_t*>(my + 2 * Lp);
-    WarpPartial* s_part = reinterpret_cast<WarpPartial*>(smem + per_cand * W);
-    int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial));
-    double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * W * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
+    WarpPartial* s_part = reinterpret_cast<WarpPartial*>(smem + per_cand * W) + grp * 16;   // [cand slot][warp of group]
+    int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial)) + grp * 4;
+    double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
 
-    const long long n_rounds = (p.n + W - 1) / W;
-    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-        const long long cand0 = round * W;
-        // ---- phase 1: every warp stages + translates its own candidate ----
+    const long long n_chunks = (p.n + 3) / 4;
+    for (long long chunk = (long long)blockIdx.x * G + grp; chunk < n_chunks; chunk += (long long)gridDim.x * G) {
+        const long long cand0 = chunk * 4;
+        // ---- phase 1: every warp of the group stages + translates its own candidate ----
         {
-            const long long cand = cand0 + warp;
+            const long long cand = cand0 + wg;
             int status = -1;
             if (cand < p.n) {
                 const int len = p.len[cand];
@@ -526,24 +551,24 @@ validate_kernel(const ValidateParams p) {
                 __syncwarp();
                 if (lane == 0) {
                     status = (len == 0) ? -1 : translate(s_code, len, s_uc_mine, s_vst, p.ns);
-                    s_status[warp] = status;
+                    s_status[wg] = status;
                 }
             } else if (lane == 0) {
-                s_status[warp] = -9;   // no candidate in this slot
+                s_status[wg] = -9;   // no candidate in this slot
             }
         }
-        __syncthreads();
-        // ---- phase 2: the W warps sweep the round's candidates together ----
-        for (int c = 0; c < W; ++c) {
+        group_barrier(grp);
+        // ---- phase 2: the group's 4 warps sweep the chunk's candidates together ----
+        for (int c = 0; c < 4; ++c) {
             const long long cand = cand0 + c;
             const int status = s_status[c];
             if (status != 0) continue;
-            const uint32_t* uc = reinterpret_cast<const uint32_t*>(smem + per_cand * c + 2 * Lp);
+            const uint32_t* uc = reinterpret_cast<const uint32_t*>(smem + per_cand * (grp * 4 + c) + 2 * Lp);
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
             const size_t prim_stride = (size_t)p.P * 16;
 #pragma unroll 1
-            for (int stripe = warp * 32 * NP; stripe < p.P; stripe += TPB * NP) {
+            for (int stripe = wg * 32 * NP; stripe < p.P; stripe += 128 * NP) {
                 PointCtx<N> cx[NP];
                 if (NP == 2) {
                     // one 128-bit load per coordinate: two consecutive points per lane
@@ -607,14 +632,14 @@ validate_kernel(const ValidateParams p) {
                 if (lane == 0) {
                     WarpPartial wp;
                     wp.best_ratio = best_ratio; wp.best_S = best_S; wp.max_R = max_R; wp.n_fin = n_fin; wp.n_vote = n_vote;
-                    s_part[c * W + warp] = wp;
+                    s_part[c * 4 + wg] = wp;
                 }
             }
         }
-        __syncthreads();
-        // ---- phase 3: one thread per candidate of the round writes the row ----
-        if (!DUMP && threadIdx.x < W) {
-            const int c = threadIdx.x;
+        group_barrier(grp);
+        // ---- phase 3: every warp writes the row of the candidate it translated ----
+        if (!DUMP && lane == 0) {
+            const int c = wg;
             const long long cand = cand0 + c;
             const int status = s_status[c];
             if (cand < p.n) {
@@ -625,9 +650,9 @@ validate_kernel(const ValidateParams p) {
                     if (p.ref_rs) for (int k = 0; k < 2 * p.n_ref; ++k) p.ref_rs[(size_t)cand * 2 * p.n_ref + k] = __longlong_as_double(0x7ff8000000000000LL);
                     atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
                 } else {
-                    WarpPartial t = s_part[c * W];
-                    for (int w = 1; w < W; ++w) {
-                        const WarpPartial o = s_part[c * W + w];
+                    WarpPartial t = s_part[c * 4];
+                    for (int w = 1; w < 4; ++w) {
+                        const WarpPartial o = s_part[c * 4 + w];
                         t.n_fin += o.n_fin; t.n_vote += o.n_vote;
                         if (o.best_ratio > t.best_ratio) { t.best_ratio = o.best_ratio; t.best_S = o.best_S; }
                         t.max_R = fmax(t.max_R, o.max_R);
@@ -642,7 +667,8 @@ validate_kernel(const ValidateParams p) {
                 }
             }
         }
-        __syncthreads();
+        // no barrier here: a warp only overwrites its OWN status/ucode slot in the next phase 1, and the
+        // partial rows of its candidate are rewritten only after the next phase-1 barrier
     }
 }
 
