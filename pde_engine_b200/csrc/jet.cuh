@@ -52,6 +52,32 @@ __device__ __forceinline__ double fast_sqrt(double x, double& half_rsqrt) {
     return s;
 }
 
+// exp(x), branch free, constants as constant-bank operands (the library exp materialises its
+// eleven 64-bit coefficients with two UMOVs each and carries a slow-path branch):
+// n = rint(x log2 e) by the 2^52+2^51 trick, r = x - n ln2 (two-term Cody-Waite), Taylor to degree 13
+// on |r| <= ln2/2 (remainder 4e-18 relative), scaled by 2^n in two halves so that overflow gives inf
+// and underflow is gradual.  NaN propagates; |x| > 750 is clamped first (exp is 0 / inf there).
+__constant__ double c_expc[16] = {
+    1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
+    6.93147180369123816490e-01, 1.90821492927058770002e-10};     // ln2 hi / lo
+__device__ __forceinline__ double fast_exp(double x) {
+    const double xc = fmin(fmax(x, -750.0), 750.0);
+    const double magic = 6755399441055744.0;
+    const double nf = fma(xc, 1.4426950408889634074, magic);
+    const int n = __double2loint(nf);
+    const double nr = nf - magic;
+    double r = fma(-nr, c_expc[14], xc);
+    r = fma(-nr, c_expc[15], r);
+    double p = c_expc[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = fma(p, r, c_expc[k]);
+    const int n1 = n >> 1, n2 = n - n1;
+    p *= __hiloint2double((n1 + 1023) << 20, 0);
+    p *= __hiloint2double((n2 + 1023) << 20, 0);
+    return (x != x) ? x : p;
+}
+
 template <int N>
 struct Jet {
     static constexpr int NC = (N + 1) * (N + 2) / 2;
@@ -107,10 +133,12 @@ __device__ __forceinline__ void jet_scale(Jet<N>& t, double s) {
     for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] *= s;
 }
 
+// sign flip on the high word: an integer-pipe LOP3 per coefficient instead of a half-rate FP64 op
 template <int N>
 __device__ __forceinline__ void jet_neg(Jet<N>& t) {
 #pragma unroll
-    for (int g = 0; g < Jet<N>::NC; ++g) t.c[g] = -t.c[g];
+    for (int g = 0; g < Jet<N>::NC; ++g)
+        t.c[g] = __hiloint2double(__double2hiint(t.c[g]) ^ (int)0x80000000, __double2loint(t.c[g]));
 }
 
 // t = t * u   (in place: descending total degree; c_g only reads t_b with b <= g)
@@ -599,7 +627,8 @@ __device__ __forceinline__ void jetv_pow(Jet<N> (&o)[NP], const Jet<N> (&t)[NP],
 // result lands in t's own registers: no out-of-place body, no copy-back.  One body serves
 // 1/x, x**k, exp(x) and exp(-x); `a` is scratch (the operand jet, dead during unary ops).
 // N = 4: 2 + 9 + 25 + 55 = 91 multiply-adds.
-// one Horner level: K > 0: a <- f_K + delta * a (order N-K, in place);  K == 0: t <- f_0 + delta * a
+// one Horner level: K > 0: a <- f_K + delta * a (order N-K, in place);  K == 0: t <- f_0 + delta * a.
+// The constant term of `a` is never stored: at level K it is f_{K+1}.
 template <int N, int NP, int K>
 __device__ __forceinline__ void jetv_compose_level(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
 #pragma unroll
@@ -607,11 +636,7 @@ __device__ __forceinline__ void jetv_compose_level(Jet<N> (&t)[NP], Jet<N> (&a)[
 #pragma unroll
         for (int gj = 0; gj <= m; ++gj) {
             const int gi = m - gj;
-            const int nterms = (gi + 1) * (gj + 1) - 1;
-            const bool two = false;           // one chain per output (independent outputs supply the ILP)
-            double acc[NP], acc1[NP];
-#pragma unroll
-            PDE_H { acc[h] = 0.0; acc1[h] = 0.0; }
+            double acc[NP];
             int cnt = 0;
 #pragma unroll
             for (int bi = 0; bi <= gi; ++bi) {
@@ -621,40 +646,30 @@ __device__ __forceinline__ void jetv_compose_level(Jet<N> (&t)[NP], Jet<N> (&a)[
                     const int ib = jidx(bi, bj), ic = jidx(gi - bi, gj - bj);
                     if (cnt == 0) {
 #pragma unroll
-                        PDE_H acc[h] = t[h].c[ib] * a[h].c[ic];
-                    } else if (two && cnt == 1) {
-#pragma unroll
-                        PDE_H acc1[h] = t[h].c[ib] * a[h].c[ic];
-                    } else if (!two || (cnt & 1) == 0) {
-#pragma unroll
-                        PDE_H acc[h] = fma(t[h].c[ib], a[h].c[ic], acc[h]);
+                        PDE_H acc[h] = t[h].c[ib] * (ic == 0 ? f[h][K + 1] : a[h].c[ic]);
                     } else {
 #pragma unroll
-                        PDE_H acc1[h] = fma(t[h].c[ib], a[h].c[ic], acc1[h]);
+                        PDE_H acc[h] = fma(t[h].c[ib], ic == 0 ? f[h][K + 1] : a[h].c[ic], acc[h]);
                     }
                     ++cnt;
                 }
             }
 #pragma unroll
             PDE_H {
-                if (two) acc[h] += acc1[h];
                 if (K > 0) a[h].c[jidx(gi, gj)] = acc[h];
                 else t[h].c[jidx(gi, gj)] = acc[h];
             }
         }
     }
-#pragma unroll
-    PDE_H {
-        if (K > 0) a[h].c[0] = f[h][K];
-        else t[h].c[0] = f[h][0];
-    }
     if constexpr (K > 0) jetv_compose_level<N, NP, K - 1>(t, a, f);
+    else {
+#pragma unroll
+        PDE_H t[h].c[0] = f[h][0];
+    }
 }
 
 template <int N, int NP>
 __device__ __forceinline__ void jetv_compose(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
-#pragma unroll
-    PDE_H a[h].c[0] = f[h][N];
     jetv_compose_level<N, NP, N - 1>(t, a, f);
 }
 #undef PDE_H

@@ -218,6 +218,9 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 //   W = 4  (four 128-thread CTAs per SM): small grids / deep spill stacks, and the DUMP (tooling) mode.
 // Two points per lane in separate registers (NP = 2) was measured SLOWER on B200 (204 registers -> 8 warps
 // per SM, or 168 with spills), see DESIGN.md 4.1.  PDE_B200_VARIANT=4|16 forces a smaller configuration.
+#ifndef PDE_NP_BIG
+#define PDE_NP_BIG 1
+#endif
 #ifndef PDE_W_BIG
 #define PDE_W_BIG 24
 #endif
@@ -230,7 +233,7 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
     } else {
         bool fits = false;
         if (g_variant != 4 && g_variant != 16 && vp.P >= 128) {
-            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, 1, 1>(vp, st, &fits);
+            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, PDE_NP_BIG, 1>(vp, st, &fits);
             if (rc || fits) return rc;
         }
         if (g_variant != 4 && PDE_W_BIG != 16 && vp.P >= 128) {

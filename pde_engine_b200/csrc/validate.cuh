@@ -31,11 +31,15 @@ __constant__ double c_pow[PDE_N_POW];
 // Taylor-ratio rows of x**k (U_POW): f_{j+1} = f_j * row[j] / x_0, row[j] = (k - j)/(j + 1)
 constexpr int kNRows = PDE_N_POW;
 __constant__ double c_frow[kNRows][4];
+__constant__ double c_one = 1.0;                       // constant-bank operand: no register, no per-dispatch move
+__constant__ double c_sign[2] = {1.0, -1.0};
+__constant__ double c_rfact[4] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4};   // 1/(j + 1)
 
 // Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel so the interpreter's
 // code stays inside the instruction cache: an earlier version that inlined the bodies per
 // call site ran at a 75 % i-cache hit rate (profiles/r1_v1_*).
-// Word layout (u32): bits 0-7 kind | 8-15 arg (constant slot, exponent slot or PRIM index).
+// Word layout (u32): bits 0-7 kind | 8-15 arg (constant slot, exponent slot, PRIM index or
+// coordinate) | 16-23 flags (bit 0: spill T first; FN kinds: bits 1-2 function, 3-7 exponent slot).
 // The kinds are DENSE and the interpreter is one `switch` compiled with --jump-table-density:
 // a micro-op costs one indexed branch (LDC + BRX) instead of the 5-level compare tree of v5
 // (33 % of all warp stall samples were dispatch, profiles/README.md).  Binary bodies have one
@@ -43,8 +47,8 @@ __constant__ double c_frow[kNRows][4];
 // the operand jet U and falls into the shared body.
 enum UKind : uint8_t {
     U_END = 0,
-    U_SPILL,                                  // S[sp++] = T
-    U_SETV0, U_SETV1, U_SETC, U_SETP,         // T = leaf (first leaf of a sub-tree)
+    U_SETV0, U_SETV1, U_SETC, U_SETP,         // T = leaf (first leaf of a sub-tree); flag bit 0: S[sp++] = T first
+    U_FNV, U_FNC,                             // T = F(coordinate), F(constant): F's Taylor coefficients ARE the jet
     U_ADD_S, U_ADD_P,                         // T = T + U
     U_SUB_P,                                  // T = T - U
     U_RSUB_S,                                 // T = U - T
@@ -54,11 +58,13 @@ enum UKind : uint8_t {
     U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
     U_NEG, U_ABS, U_SQRT, U_SQUARE,
-    U_INV,                                    // T = 1 / T          } one shared Horner body
-    U_EXP, U_EXPN,                            // exp(T), exp(-T)    } (jetv_compose), in place
-    U_POW,                                    // arg = exponent slot }
+    U_INV,                                    // T = 1 / T            } one shared Horner body
+    U_EXP,                                    // exp(+-T), arg = sign } (jetv_compose), in place
+    U_POW,                                    // arg = exponent slot  }
     U_NKINDS
 };
+constexpr unsigned F_SPILL = 1u << 16;
+enum UFn : unsigned { FN_INV = 0, FN_EXP = 1, FN_EXPN = 2, FN_POW = 3 };
 
 struct ValidateParams {
     const uint8_t* code;
@@ -108,17 +114,19 @@ __host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 // spilled in stack order, leaves never occupy a jet.
 __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* vst, int ns_max) {
     int sp = 0, nu = 0, ns = 0, tpos = -1;
-    auto emit = [&](unsigned kind, unsigned arg) { uc[nu++] = kind | (arg << 8); };
-    auto spill_t = [&]() -> bool {
+    auto emit = [&](unsigned kind, unsigned arg, unsigned flags = 0) { uc[nu++] = kind | (arg << 8) | flags; };
+    // T is about to be overwritten by a leaf: its value moves to the spill stack (a flag of the SET/FN op)
+    auto spill_t = [&](unsigned& flag) -> bool {
+        flag = 0;
         if (tpos < 0) return true;
         if (ns >= ns_max) return false;
-        emit(U_SPILL, 0); vst[tpos] = V_JET_S; ++ns;
+        flag = F_SPILL; vst[tpos] = V_JET_S; ++ns;
         return true;
     };
-    auto set_leaf = [&](unsigned leaf) {
-        if (leaf >= PDE_OP_CONST0) emit(U_SETC, leaf - PDE_OP_CONST0);
-        else if (op_is_prim(leaf)) emit(U_SETP, leaf - PDE_OP_PRIM0);
-        else emit(leaf == PDE_OP_VAR0 ? U_SETV0 : U_SETV1, 0);
+    auto set_leaf = [&](unsigned leaf, unsigned flag) {
+        if (leaf >= PDE_OP_CONST0) emit(U_SETC, leaf - PDE_OP_CONST0, flag);
+        else if (op_is_prim(leaf)) emit(U_SETP, leaf - PDE_OP_PRIM0, flag);
+        else emit(leaf == PDE_OP_VAR0 ? U_SETV0 : U_SETV1, 0, flag);
     };
     // T = T op leaf (leaf on the right); o: 0 add 1 sub 2 mul 3 div
     auto bin_leaf_right = [&](unsigned o, unsigned leaf) {
@@ -137,31 +145,42 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
         } else if (op_is_unary(b)) {
             if (sp < 1) return 1;
             const unsigned top = vst[sp - 1];
-            if (top != V_JET_T) {
-                if (top == V_JET_S) return 1;
-                if (!spill_t()) return 2;
-                set_leaf(top);
-                vst[sp - 1] = V_JET_T; tpos = sp - 1;
-            }
+            // the unary op as (function, exponent slot); 4 = not one of the scalar-function kinds
+            unsigned fn = 4, slot = 0, kind = U_NEG, arg = 0;
             switch (b) {
-                case PDE_OP_NEG: case PDE_OP_FN_NEG: emit(U_NEG, 0); break;
-                case PDE_OP_ABS: emit(U_ABS, 0); break;
-                case PDE_OP_SQRT: emit(U_SQRT, 0); break;
-                case PDE_OP_EXP: emit(U_EXP, 0); break;
-                case PDE_OP_FN_INV: emit(U_INV, 0); break;
-                case PDE_OP_FN_SQUARE: emit(U_SQUARE, 0); break;
-                case PDE_OP_FN_POW32: emit(U_POW, 0); break;
-                case PDE_OP_FN_POWN32: emit(U_POW, 1); break;
-                case PDE_OP_FN_EXPNEG: emit(U_EXPN, 0); break;
+                case PDE_OP_NEG: case PDE_OP_FN_NEG: kind = U_NEG; break;
+                case PDE_OP_ABS: kind = U_ABS; break;
+                case PDE_OP_SQRT: kind = U_SQRT; break;
+                case PDE_OP_FN_SQUARE: kind = U_SQUARE; break;
+                case PDE_OP_EXP: kind = U_EXP; arg = 0; fn = FN_EXP; break;
+                case PDE_OP_FN_EXPNEG: kind = U_EXP; arg = 1; fn = FN_EXPN; break;
+                case PDE_OP_FN_INV: kind = U_INV; fn = FN_INV; break;
+                case PDE_OP_FN_POW32: kind = U_POW; arg = 0; fn = FN_POW; slot = 0; break;
+                case PDE_OP_FN_POWN32: kind = U_POW; arg = 1; fn = FN_POW; slot = 1; break;
                 default: {
-                    const unsigned slot = b - PDE_OP_POW0;
+                    slot = b - PDE_OP_POW0;
                     const double k = c_pow[slot];
-                    if (k == 2.0) emit(U_SQUARE, 0);
-                    else if (k == 0.5) emit(U_SQRT, 0);
-                    else if (k == -1.0) emit(U_INV, 0);
-                    else emit(U_POW, slot);
+                    if (k == 2.0) kind = U_SQUARE;
+                    else if (k == 0.5) kind = U_SQRT;
+                    else if (k == -1.0) { kind = U_INV; fn = FN_INV; }
+                    else { kind = U_POW; arg = slot; fn = FN_POW; }
                 }
             }
+            if (top != V_JET_T) {
+                if (top == V_JET_S) return 1;
+                unsigned flag;
+                if (!spill_t(flag)) return 2;
+                vst[sp - 1] = V_JET_T; tpos = sp - 1;
+                if (fn < 4 && slot < 32 && !op_is_prim(top)) {
+                    // F(coordinate) / F(constant): the jet is F's own Taylor expansion, no jet arithmetic
+                    const unsigned fl = flag | (fn << 17) | (slot << 19);
+                    if (top >= PDE_OP_CONST0) emit(U_FNC, top - PDE_OP_CONST0, fl);
+                    else emit(U_FNV, top - PDE_OP_VAR0, fl);
+                    continue;
+                }
+                set_leaf(top, flag);
+            }
+            emit(kind, arg);
         } else if (op_is_binary(b)) {
             if (sp < 2) return 1;
             const unsigned bb = vst[sp - 1], aa = vst[sp - 2];
@@ -180,8 +199,9 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                 } else if (op_is_prim(aa)) emit(U_RDIV_P, aa - PDE_OP_PRIM0);        // PRIM / T
                 else { emit(U_INV, 0); bin_leaf_right(2, aa); }                     // x / T = (1 / T) * x (sparse)
             } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
-                if (!spill_t()) return 2;
-                set_leaf(aa);
+                unsigned flag;
+                if (!spill_t(flag)) return 2;
+                set_leaf(aa, flag);
                 bin_leaf_right(o, bb);
             } else {
                 return 1;
@@ -192,7 +212,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
         }
     }
     if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) set_leaf(vst[0]);
+    if (vst[0] != V_JET_T) set_leaf(vst[0], 0);
     emit(U_END, 0);
     emit(U_END, 0);      // the interpreter prefetches two words ahead
     return 0;
@@ -225,25 +245,97 @@ __device__ __forceinline__ double lazy_rcp(double x) {
     return fma(r, e, r);
 }
 
+// Shared-memory accesses of the interpreter go through 32-bit shared-window addresses held in
+// registers: with ordinary pointers ptxas re-derives the window base (S2R SR_CgaCtaId + LEA + IMAD)
+// and the thread's column (S2R SR_TID) in front of EVERY micro-op instead of keeping two registers.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned keep_in_register(unsigned v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v) : "memory");
+}
+// slot element k = coef * NP + point lives at byte offset k * TPB * 8: an immediate of the LDS/STS
+template <int N, int NP, int TPB, int K = 0>
+__device__ __forceinline__ void spill_store(unsigned addr, const Jet<N> (&T)[NP]) {
+    if constexpr (K < Jet<N>::NC * NP) {
+        sts_f64<K * TPB * 8>(addr, T[K % NP].c[K / NP]);
+        spill_store<N, NP, TPB, K + 1>(addr, T);
+    }
+}
+template <int N, int NP, int TPB, int K = 0>
+__device__ __forceinline__ void spill_load(unsigned addr, Jet<N> (&U)[NP]) {
+    if constexpr (K < Jet<N>::NC * NP) {
+        U[K % NP].c[K / NP] = lds_f64<K * TPB * 8>(addr);
+        spill_load<N, NP, TPB, K + 1>(addr, U);
+    }
+}
+
+// Taylor coefficients f_j = F^(j)(x)/j! of the scalar functions (UFn) at x
+template <int N>
+__device__ __forceinline__ void scalar_taylor(unsigned fn, unsigned slot, double x, double (&f)[N + 1]) {
+    if (fn == FN_INV) {                  // (-1)^j / x^(j+1)
+        const double r = fast_rcp(x);
+        f[0] = r;
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j + 1] = -f[j] * r;
+    } else if (fn == FN_POW) {           // f_{j+1} = f_j (k - j)/(j + 1) / x
+        const double r = fast_rcp(x);
+        f[0] = pow0(x, c_pow[slot]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j + 1] = f[j] * (r * c_frow[slot][j]);
+    } else {                             // exp(+-x): (+-1)^j exp(+-x) / j!
+        const double sg = c_sign[fn == FN_EXPN];
+        f[0] = fast_exp(sg * x);
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j + 1] = f[j] * (sg * c_rfact[j]);
+    }
+}
+
+#ifndef PDE_PREFETCH
+#define PDE_PREFETCH 0
+#endif
+
 // Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
-// Spill layout: [(slot * NC + coef) * NP + point][thread]  (conflict free).
-template <int N, int NP>
-__device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, double* __restrict__ spill, int stride,
+// uc: shared address of the micro-op words; sp_addr: shared address of this thread's spill column
+// (layout [(slot * NC + coef) * NP + point][thread], conflict free), moved up and down by one slot.
+template <int N, int NP, int TPB>
+__device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
                                             size_t prim_stride, const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
     constexpr int NC = Jet<N>::NC;
+    constexpr unsigned kSlotBytes = NC * NP * TPB * 8;
     Jet<N> U[NP];
     double f[NP][N + 1];
-    int sp = 0;  // spill depth
-    unsigned ins = uc[0], ins_next = uc[1];
-    uc += 2;
+#if PDE_PREFETCH == 2
+    unsigned ins = lds_u32(uc), ins_next = lds_u32(uc + 4);
+    uc += 8;
+#elif PDE_PREFETCH == 1
+    unsigned ins_next = lds_u32(uc);
+    uc += 4;
+#endif
 #define PDE_EACH for (int h = 0; h < NP; ++h)
+#define PDE_SPILL_IF_FLAGGED                                                                 \
+    if (ins_cur & F_SPILL) {                                                                 \
+        spill_store<N, NP, TPB>(sp_addr, T);                                                 \
+        sp_addr += kSlotBytes;                                                               \
+    }
 #define PDE_FETCH_S                                                                          \
     {                                                                                        \
-        --sp;                                                                                \
-        const double* from = spill + (size_t)sp * NC * NP * stride;                          \
-        _Pragma("unroll") PDE_EACH {                                                         \
-            _Pragma("unroll") for (int g = 0; g < NC; ++g) U[h].c[g] = from[(g * NP + h) * stride]; \
-        }                                                                                    \
+        sp_addr -= kSlotBytes;                                                               \
+        spill_load<N, NP, TPB>(sp_addr, U);                                                  \
     }
 #define PDE_FETCH_P                                                                          \
     {                                                                                        \
@@ -254,46 +346,77 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
     }
 #pragma unroll 1
     for (;;) {
-        const unsigned kind = ins & 0xffu, arg = ins >> 8;
+#if PDE_PREFETCH == 2
+        const unsigned ins_cur = ins;
         ins = ins_next;
-        ins_next = *uc++;          // two-deep prefetch: the LDS latency hides even behind one-instruction bodies
+        ins_next = lds_u32(uc); uc += 4;   // two-deep prefetch
+#elif PDE_PREFETCH == 1
+        const unsigned ins_cur = ins_next;
+        ins_next = lds_u32(uc); uc += 4;
+#else
+        const unsigned ins_cur = lds_u32(uc); uc += 4;
+#endif
+        const unsigned kind = ins_cur & 0xffu, arg = (ins_cur >> 8) & 0xffu;
         switch (kind) {
             case U_END: return;
-            case U_SPILL: {
-                double* dst = spill + (size_t)sp * NC * NP * stride;
-#pragma unroll
-                PDE_EACH {
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) dst[(g * NP + h) * stride] = T[h].c[g];
-                }
-                ++sp;
-            } break;
             // The SET bodies go through an opaque zero: a case that only assigns constants becomes an
             // EMPTY block, the indexed branch then jumps straight to the loop header and the header's
             // phi copies (30 register moves) land in front of the branch -- executed by EVERY micro-op.
             case U_SETV0: {
+                PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x0; T[h].c[1] = z + 1.0; }
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x0; T[h].c[1] = c_one; }
             } break;
             case U_SETV1: {
+                PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x1; T[h].c[2] = z + 1.0; }
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x1; T[h].c[2] = c_one; }
             } break;
             case U_SETC: {
+                PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
                 PDE_EACH { jet_fill(T[h], z); T[h].c[0] = c_const[arg]; }
             } break;
-            case U_SETP:
+            case U_SETP: {
+                PDE_SPILL_IF_FLAGGED
 #pragma unroll
                 PDE_EACH {
                     const double* from = cx[h].prim + (size_t)arg * prim_stride;
 #pragma unroll
                     for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(from + g * 32);
                 }
-                break;
+            } break;
+            // F(coordinate): the jet of F(x_k + dx_k) is F's Taylor expansion along dx_k
+            case U_FNV: {
+                PDE_SPILL_IF_FLAGGED
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH {
+                    scalar_taylor<N>((ins_cur >> 17) & 3u, ins_cur >> 19, arg ? cx[h].x1 : cx[h].x0, f[h]);
+                    jet_fill(T[h], z);
+                    T[h].c[0] = f[h][0];
+                    if (arg) {
+#pragma unroll
+                        for (int k = 1; k <= N; ++k) T[h].c[jidx(0, k)] = f[h][k];
+                    } else {
+#pragma unroll
+                        for (int k = 1; k <= N; ++k) T[h].c[jidx(k, 0)] = f[h][k];
+                    }
+                }
+            } break;
+            case U_FNC: {
+                PDE_SPILL_IF_FLAGGED
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH {
+                    scalar_taylor<N>((ins_cur >> 17) & 3u, ins_cur >> 19, c_const[arg], f[h]);
+                    jet_fill(T[h], z);
+                    T[h].c[0] = f[h][0];
+                }
+            } break;
             case U_ADD_S: PDE_FETCH_S goto l_add;
             case U_ADD_P: PDE_FETCH_P
             l_add:
@@ -347,19 +470,19 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
                 break;
             case U_ADDV0:
 #pragma unroll
-                PDE_EACH { T[h].c[0] += cx[h].x0; T[h].c[1] += 1.0; }
+                PDE_EACH { T[h].c[0] += cx[h].x0; T[h].c[1] += c_one; }
                 break;
             case U_ADDV1:
 #pragma unroll
-                PDE_EACH { T[h].c[0] += cx[h].x1; T[h].c[2] += 1.0; }
+                PDE_EACH { T[h].c[0] += cx[h].x1; T[h].c[2] += c_one; }
                 break;
             case U_SUBV0:
 #pragma unroll
-                PDE_EACH { T[h].c[0] -= cx[h].x0; T[h].c[1] -= 1.0; }
+                PDE_EACH { T[h].c[0] -= cx[h].x0; T[h].c[1] -= c_one; }
                 break;
             case U_SUBV1:
 #pragma unroll
-                PDE_EACH { T[h].c[0] -= cx[h].x1; T[h].c[2] -= 1.0; }
+                PDE_EACH { T[h].c[0] -= cx[h].x1; T[h].c[2] -= c_one; }
                 break;
             case U_MULV0:
 #pragma unroll
@@ -389,45 +512,24 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ uc, dou
             case U_SQUARE: jetv_square<N, NP>(T); break;
             // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
             // shared in-place Horner body
-            case U_INV:                      // f_j = (-1)^j / x^(j+1)
+            case U_INV:
 #pragma unroll
-                PDE_EACH {
-                    const double r = fast_rcp(T[h].c[0]);
-                    f[h][0] = r;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) f[h][j + 1] = -f[h][j] * r;
-                }
+                PDE_EACH scalar_taylor<N>(FN_INV, 0, T[h].c[0], f[h]);
                 goto l_compose;
-            case U_EXP:                      // f_j = exp(x) / j!
+            case U_EXP:
 #pragma unroll
-                PDE_EACH {
-                    f[h][0] = exp(T[h].c[0]);
-#pragma unroll
-                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (1.0 / (j + 1));
-                }
+                PDE_EACH scalar_taylor<N>(FN_EXP + arg, 0, T[h].c[0], f[h]);
                 goto l_compose;
-            case U_EXPN:                     // f_j = (-1)^j exp(-x) / j!
+            case U_POW:
 #pragma unroll
-                PDE_EACH {
-                    f[h][0] = exp(-T[h].c[0]);
-#pragma unroll
-                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (-1.0 / (j + 1));
-                }
-                goto l_compose;
-            case U_POW:                      // f_{j+1} = f_j (k - j)/(j + 1) / x
-#pragma unroll
-                PDE_EACH {
-                    const double r = fast_rcp(T[h].c[0]);
-                    f[h][0] = pow0(T[h].c[0], c_pow[arg]);
-#pragma unroll
-                    for (int j = 0; j < N; ++j) f[h][j + 1] = f[h][j] * (r * c_frow[arg][j]);
-                }
+                PDE_EACH scalar_taylor<N>(FN_POW, arg, T[h].c[0], f[h]);
             l_compose:
                 jetv_compose<N, NP>(T, U, f);
                 break;
             default: __builtin_unreachable();
         }
     }
+#undef PDE_SPILL_IF_FLAGGED
 #undef PDE_FETCH_S
 #undef PDE_FETCH_P
 #undef PDE_EACH
@@ -536,6 +638,7 @@ validate_kernel(const ValidateParams p) {
     int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial)) + grp * 4;
     double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
 
+    const unsigned spill_addr = keep_in_register(smem_addr(s_spill));
     const long long n_chunks = (p.n + 3) / 4;
     for (long long chunk = (long long)blockIdx.x * G + grp; chunk < n_chunks; chunk += (long long)gridDim.x * G) {
         const long long cand0 = chunk * 4;
@@ -563,7 +666,7 @@ validate_kernel(const ValidateParams p) {
             const long long cand = cand0 + c;
             const int status = s_status[c];
             if (status != 0) continue;
-            const uint32_t* uc = reinterpret_cast<const uint32_t*>(smem + per_cand * (grp * 4 + c) + 2 * Lp);
+            const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 2 * Lp));
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
             const size_t prim_stride = (size_t)p.P * 16;
@@ -588,7 +691,7 @@ validate_kernel(const ValidateParams p) {
                     Res::fetch(p.tab, p.P, pt[h], coef[h]);      // issued early: latency hides behind the program
                 }
                 Jet<N> T[NP];
-                run_program<N, NP>(uc, s_spill, TPB, prim_stride, cx, T);
+                run_program<N, NP, TPB>(uc, spill_addr, prim_stride, cx, T);
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
                     double R, S;
