@@ -213,16 +213,18 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 }
 
 // Kernel configuration: a CTA is W/4 groups of 4 warps (validate.cuh).  One CTA per SM:
-//   W = 24 (768 threads, 80 registers): most warps per scheduler; fits up to 2 spill slots per lane;
+//   W = 20 (640 threads, 94 registers, no local-memory spills): five warps per scheduler; fits up to
+//          2 spill slots per lane (154 KB); W = 24 (80 registers, 128 B of register spills) measured equal;
 //   W = 16 (512 threads, 104 registers): up to 3 spill slots;
 //   W = 4  (four 128-thread CTAs per SM): small grids / deep spill stacks, and the DUMP (tooling) mode.
-// Two points per lane in separate registers (NP = 2) was measured SLOWER on B200 (204 registers -> 8 warps
-// per SM, or 168 with spills), see DESIGN.md 4.1.  PDE_B200_VARIANT=4|16 forces a smaller configuration.
+// Two points per lane in separate registers (NP = 2) was measured SLOWER on B200 again in v9 (194 registers,
+// 8 warps/SM: 193 ms; 168 registers, 12 warps/SM: 167 ms; vs 138 ms for NP = 1 with 20 warps), DESIGN.md 4.1.
+// PDE_B200_VARIANT=4|16 forces a smaller configuration.
 #ifndef PDE_NP_BIG
 #define PDE_NP_BIG 1
 #endif
 #ifndef PDE_W_BIG
-#define PDE_W_BIG 24
+#define PDE_W_BIG 20
 #endif
 static int g_variant = -1;
 template <int PROBLEM, bool DUMP>
