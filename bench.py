@@ -301,6 +301,12 @@ def run_ours(args):
         from pde_engine_b200.distributed import shard_range
         first4, cnt4 = shard_range(len(uniq4), rank, world)
         mine = uniq4[first4:first4 + cnt4]
+        # untimed warm-up of the exact code path on a small slice (first use of the 3-spill-slot kernel
+        # configuration loads its module: a one-off cost of the process, not of the validation)
+        esw = sess.compile(mine[:256])
+        cw, lw = esw.programs(128)
+        pb.validate(sess, prog, torch.from_numpy(cw).to(dev), torch.from_numpy(lw).to(dev), pts_t, tab_t, None,
+                    tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=3)
         barrier()
         t0 = time.perf_counter()
         es4 = sess.compile(mine)                                    # host compiler: strings -> bytecode
@@ -329,7 +335,8 @@ def run_ours(args):
                   "n": len(uniq4), "points": P, "wall_ms_host_strings_to_survivor_bits": float(w[0]),
                   "host_compile_ms": float(w[1]), "kernel_ms": float(w[2]),
                   "survivors_for_cpu_confirmation": int(tot[0]), "not_device_evaluable": int(tot[1]),
-                  "note": "span A = host compile + H2D + kernel + D2H (max over ranks); the host compiler dominates, so scaling over GPUs is flat by construction"}
+                  "host_threads": min(os.cpu_count() or 1, 16),
+                  "note": "span A = host compile (multi-threaded C++ parser) + H2D + kernel + D2H, max over ranks; every rank compiles and validates its own contiguous shard of the strings"}
     except Exception as e:   # the fixture is optional for the headline metric
         depth4 = {"error": repr(e)[:200]}
 

@@ -95,9 +95,16 @@ class ExprSet:
     def __init__(self, session: Session, strs: Sequence[str]):
         self.session = session
         self.n = len(strs)
-        arr = (C.c_char_p * max(1, self.n))(*[s.encode() for s in strs])
+        # one NUL-separated blob + offsets: building a ctypes array of 10^5 char pointers costs more
+        # than compiling them
+        blob = ("\0".join(strs) + "\0").encode() if self.n else b"\0"
+        lens = np.fromiter(map(len, strs), dtype=np.int64, count=self.n)
+        if self.n and len(blob) != int(lens.sum()) + self.n:          # non-ASCII input: byte lengths differ
+            lens = np.fromiter((len(s.encode()) for s in strs), dtype=np.int64, count=self.n)
+        off = np.zeros(self.n + 1, dtype=np.uint32)
+        np.cumsum(lens + 1, out=off[1:])
         h = C.c_void_p()
-        check(lib.pde_compile_exprs(session._h, arr, self.n, C.byref(h)))
+        check(lib.pde_compile_exprs_packed(session._h, blob, _np_ptr(off), self.n, C.byref(h)))
         self._h = h
 
     def __del__(self):

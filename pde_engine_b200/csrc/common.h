@@ -20,6 +20,12 @@ bool have_device();
 
 }  // namespace pde
 
+struct pde_exprset;
+namespace pde {
+void exprset_ensure_rank(pde_exprset* e);      // compiler.cpp
+int exprset_ensure_device(pde_exprset* e);     // compiler.cpp
+}
+
 // ---- opaque handles ------------------------------------------------------
 struct pde_session {
     std::string var[2];
@@ -29,6 +35,9 @@ struct pde_session {
     std::vector<double> const_vals;
     std::vector<std::string> pow_keys;
     std::vector<double> pow_vals;
+    // numeric mirrors of the keys (numerator, denominator; denominator 0 = named constant index):
+    // rebuilt by the compiler whenever their size differs from the key tables
+    std::vector<long long> const_num, const_den, pow_num, pow_den;
 };
 
 struct pde_exprset {
@@ -39,7 +48,10 @@ struct pde_exprset {
     std::vector<int8_t> term_sign;      // [nt]
     std::vector<uint32_t> term_off;     // [nt+1]
     std::vector<uint8_t> pool;
-    // device mirrors (cudaMalloc'd by the library, on the device current at compile time)
+    std::vector<char> str_blob;         // the source strings (NUL separated): lazy lexicographic rank
+    std::vector<uint32_t> str_off;      // [n+1]
+    bool rank_ready = false;
+    // device mirrors (cudaMalloc'd by the library on first use by the enumerator)
     int device = -1;
     uint8_t* d_flags = nullptr;
     uint8_t* d_attrs = nullptr;

@@ -22,6 +22,7 @@
 #include <memory>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -69,13 +70,21 @@ struct Node {
     Node* b = nullptr;
 };
 
+// bump allocator, reset per expression (a node per malloc was 20 % of the compile time)
 struct Arena {
-    std::vector<std::unique_ptr<Node>> nodes;
+    std::vector<std::unique_ptr<Node[]>> chunks;
+    size_t used = 0;                      // nodes handed out since the last reset
+    static constexpr size_t kChunk = 256;
     Node* make(Kind k) {
-        nodes.emplace_back(new Node());
-        nodes.back()->kind = k;
-        return nodes.back().get();
+        const size_t c = used / kChunk, o = used % kChunk;
+        if (c == chunks.size()) chunks.emplace_back(new Node[kChunk]);
+        ++used;
+        Node* x = &chunks[c][o];
+        *x = Node();
+        x->kind = k;
+        return x;
     }
+    void reset() { used = 0; }
 };
 
 struct Parser {
@@ -183,7 +192,7 @@ struct Parser {
         if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') {
             size_t st = pos;
             while (pos < n && ((s[pos] >= 'a' && s[pos] <= 'z') || (s[pos] >= 'A' && s[pos] <= 'Z') || (s[pos] >= '0' && s[pos] <= '9') || s[pos] == '_')) ++pos;
-            std::string name(s + st, pos - st);
+            const std::string name(s + st, pos - st);
             if (peek('(')) {
                 ++pos;
                 int opc = func_opcode(name);
@@ -238,26 +247,20 @@ static std::string rat_key(const Rat& r) {
     return r.d == 1 ? std::to_string(r.n) : std::to_string(r.n) + "/" + std::to_string(r.d);
 }
 
-struct Emitter {
-    pde_session* sess;
-    Arena& ar;
+// A CONST / POW byte whose table slot is assigned later, in expression order (the tables are
+// append-only per session and their numbering is part of the bytecode, so the parallel parse
+// must not decide it).
+struct Fix {
+    uint32_t pos;        // byte position in the worker's pool
+    uint8_t is_pow;
+    uint8_t named;       // named constant (M, a, E): num = index into session->named
+    i64 num, den;
+};
 
-    int const_slot(const std::string& key, double val) {
-        for (size_t i = 0; i < sess->const_keys.size(); ++i)
-            if (sess->const_keys[i] == key) return (int)i;
-        if ((int)sess->const_keys.size() >= PDE_N_CONST) throw TableFull();
-        sess->const_keys.push_back(key);
-        sess->const_vals.push_back(val);
-        return (int)sess->const_keys.size() - 1;
-    }
-    int pow_slot(const std::string& key, double val) {
-        for (size_t i = 0; i < sess->pow_keys.size(); ++i)
-            if (sess->pow_keys[i] == key) return (int)i;
-        if ((int)sess->pow_keys.size() >= PDE_N_POW) throw TableFull();
-        sess->pow_keys.push_back(key);
-        sess->pow_vals.push_back(val);
-        return (int)sess->pow_keys.size() - 1;
-    }
+struct Emitter {
+    std::vector<uint8_t>& out;
+    std::vector<Fix>& fixes;
+    Arena& ar;
 
     struct Term { int sign; Node* body; };
 
@@ -275,7 +278,7 @@ struct Emitter {
         return t;
     }
 
-    void split_terms(Node* ir, std::vector<Term>& out) {
+    void split_terms(Node* ir, std::vector<Term>& terms) {
         std::vector<Term> chain;
         while (ir->kind == K_BIN && (ir->op == '+' || ir->op == '-')) {
             chain.push_back({ir->op == '+' ? 1 : -1, ir->b});
@@ -285,39 +288,37 @@ struct Emitter {
         for (size_t i = chain.size(); i-- > 0;) {
             int sign = chain[i].sign;
             Node* body = extract_sign(chain[i].body, sign);
-            out.push_back({sign, body});
+            terms.push_back({sign, body});
         }
     }
 
-    void emit(Node* ir, std::vector<uint8_t>& out) {
+    void emit(Node* ir) {
         std::vector<Term> terms;
         split_terms(ir, terms);
         for (size_t k = 0; k < terms.size(); ++k) {
-            emit_term(terms[k].body, out);
+            emit_term(terms[k].body);
             if (k == 0) { if (terms[k].sign < 0) out.push_back(PDE_OP_NEG); }
             else out.push_back(terms[k].sign > 0 ? PDE_OP_ADD : PDE_OP_SUB);
         }
     }
 
-    void emit_term(Node* t, std::vector<uint8_t>& out) {
+    void placeholder(bool is_pow, bool named, i64 num, i64 den) {
+        fixes.push_back({(uint32_t)out.size(), (uint8_t)is_pow, (uint8_t)named, num, den});
+        out.push_back(is_pow ? PDE_OP_POW0 : PDE_OP_CONST0);
+    }
+
+    void emit_term(Node* t) {
         switch (t->kind) {
-            case K_CONST:
-                out.push_back((uint8_t)(PDE_OP_CONST0 + const_slot(rat_key(t->rat), (double)t->rat.n / (double)t->rat.d)));
-                break;
-            case K_NCONST:
-                out.push_back((uint8_t)(PDE_OP_CONST0 + const_slot(sess->named[t->idx], sess->named_vals[t->idx])));
-                break;
+            case K_CONST: placeholder(false, false, t->rat.n, t->rat.d); break;
+            case K_NCONST: placeholder(false, true, t->idx, 0); break;
             case K_VAR: out.push_back((uint8_t)(PDE_OP_VAR0 + t->idx)); break;
-            case K_NEG: emit(t->a, out); out.push_back(PDE_OP_NEG); break;
+            case K_NEG: emit(t->a); out.push_back(PDE_OP_NEG); break;
             case K_BIN:
-                if (t->op == '+' || t->op == '-') emit(t, out);
-                else { emit(t->a, out); emit(t->b, out); out.push_back(t->op == '*' ? PDE_OP_MUL : PDE_OP_DIV); }
+                if (t->op == '+' || t->op == '-') emit(t);
+                else { emit(t->a); emit(t->b); out.push_back(t->op == '*' ? PDE_OP_MUL : PDE_OP_DIV); }
                 break;
-            case K_POW:
-                emit(t->a, out);
-                out.push_back((uint8_t)(PDE_OP_POW0 + pow_slot(rat_key(t->rat), (double)t->rat.n / (double)t->rat.d)));
-                break;
-            case K_CALL: emit(t->a, out); out.push_back((uint8_t)t->idx); break;
+            case K_POW: emit(t->a); placeholder(true, false, t->rat.n, t->rat.d); break;
+            case K_CALL: emit(t->a); out.push_back((uint8_t)t->idx); break;
         }
     }
 };
@@ -325,6 +326,150 @@ struct Emitter {
 static bool has_vars(const char* s) {
     // LBF:134-136: ('r' in s) or ('x' in s) or ('rho' in s) or ('z' in s)
     return strchr(s, 'r') || strchr(s, 'x') || strchr(s, 'z');
+}
+
+// ---- parallel front end: one worker per contiguous range of strings ----
+struct Worker {
+    int lo = 0, hi = 0;
+    std::vector<uint8_t> pool;
+    std::vector<int8_t> term_sign;
+    std::vector<uint32_t> term_off;     // end offset (in `pool`) of every term
+    std::vector<Fix> fixes;
+    std::vector<uint32_t> n_terms, pool_end, fix_end;   // per expression (cumulative ends)
+    std::vector<uint8_t> flags;
+
+    void run(const char* blob, const uint32_t* off, const pde_session* sess) {
+        Arena ar;
+        const int n = hi - lo;
+        n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0);
+        pool.reserve((size_t)n * 24);
+        std::vector<Emitter::Term> terms;
+        for (int k = 0; k < n; ++k) {
+            const char* str = blob + off[lo + k];
+            const size_t pool0 = pool.size(), nt0 = term_sign.size(), nf0 = fixes.size();
+            try {
+                ar.reset();
+                Parser ps(str, sess, ar);
+                Node* ir = ps.parse_expr();
+                ps.ws();
+                if (ps.pos != ps.n) throw Unsupported();
+                Emitter em{pool, fixes, ar};
+                terms.clear();
+                em.split_terms(ir, terms);
+                for (auto& t : terms) {
+                    em.emit_term(t.body);
+                    term_sign.push_back((int8_t)t.sign);
+                    term_off.push_back((uint32_t)pool.size());
+                }
+                // whole program length: bodies + (NEG for a leading minus) + (nterms-1) ADD/SUB
+                const size_t whole = pool.size() - pool0 + (terms[0].sign < 0 ? 1 : 0) + (terms.size() - 1);
+                if (whole > 255) flags[k] = PDE_FLAG_TOO_LONG;
+            } catch (const Unsupported&) {
+                flags[k] = PDE_FLAG_UNSUPPORTED;
+            }
+            if (flags[k]) { pool.resize(pool0); term_sign.resize(nt0); term_off.resize(nt0); fixes.resize(nf0); }
+            n_terms[k] = (uint32_t)(term_sign.size() - nt0);
+            pool_end[k] = (uint32_t)pool.size();
+            fix_end[k] = (uint32_t)fixes.size();
+        }
+    }
+};
+
+// slot of a constant / exponent in the session tables; appends; -1 = table full
+static int table_slot(pde_session* s, const Fix& f) {
+    std::vector<std::string>& keys = f.is_pow ? s->pow_keys : s->const_keys;
+    std::vector<double>& vals = f.is_pow ? s->pow_vals : s->const_vals;
+    std::vector<long long>& num = f.is_pow ? s->pow_num : s->const_num;
+    std::vector<long long>& den = f.is_pow ? s->pow_den : s->const_den;
+    if (num.size() != keys.size()) {        // (re)build the numeric mirror of the keys
+        num.assign(keys.size(), 0); den.assign(keys.size(), -1);
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const std::string& k = keys[i];
+            bool named = false;
+            for (size_t j = 0; j < s->named.size() && !f.is_pow; ++j) if (s->named[j] == k) { num[i] = (long long)j; den[i] = 0; named = true; }
+            if (named) continue;
+            const size_t sl = k.find('/');
+            num[i] = atoll(k.c_str());
+            den[i] = sl == std::string::npos ? 1 : atoll(k.c_str() + sl + 1);
+        }
+    }
+    const long long fn = f.num, fd = f.named ? 0 : f.den;
+    for (size_t i = 0; i < num.size(); ++i) if (num[i] == fn && den[i] == fd) return (int)i;
+    const int cap = f.is_pow ? PDE_N_POW : PDE_N_CONST;
+    if ((int)keys.size() >= cap) return -1;
+    if (f.named) { keys.push_back(s->named[f.num]); vals.push_back(s->named_vals[f.num]); }
+    else { Rat r; r.n = f.num; r.d = f.den; keys.push_back(rat_key(r)); vals.push_back((double)f.num / (double)f.den); }
+    num.push_back(fn); den.push_back(fd);
+    return (int)keys.size() - 1;
+}
+
+static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, int n, pde_exprset** out) {
+    std::unique_ptr<pde_exprset> e(new pde_exprset());
+    e->n = n;
+    e->flags.assign(n, 0);
+    e->attrs.assign(n, 0);
+    e->term_begin.assign(n + 1, 0);
+    e->term_off.push_back(0);
+    e->str_off.assign(off, off + n + (n > 0 ? 1 : 0));
+    if (n > 0) e->str_blob.assign(blob, blob + off[n]);
+    // ---- phase A (parallel): parse + emit with deferred table slots ----
+    int nthreads = 1;
+    if (const char* ev = getenv("PDE_B200_COMPILE_THREADS")) nthreads = atoi(ev);
+    else nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    nthreads = std::max(1, std::min(nthreads, n / 4096 + 1));
+    std::vector<Worker> workers(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        workers[t].lo = (int)((long long)n * t / nthreads);
+        workers[t].hi = (int)((long long)n * (t + 1) / nthreads);
+    }
+    if (nthreads == 1) workers[0].run(blob, off, s);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] { workers[t].run(blob, off, s); });
+        for (auto& x : th) x.join();
+    }
+    // ---- phase B (sequential, in expression order): table slots, pool assembly ----
+    size_t total_pool = 0, total_terms = 0;
+    for (auto& w : workers) { total_pool += w.pool.size(); total_terms += w.term_sign.size(); }
+    e->pool.reserve(total_pool); e->term_sign.reserve(total_terms); e->term_off.reserve(total_terms + 1);
+    for (auto& w : workers) {
+        uint32_t p0 = 0, f0 = 0, t0 = 0;
+        for (int k = 0; k < w.hi - w.lo; ++k) {
+            const int i = w.lo + k;
+            const char* str = blob + off[i];
+            uint8_t attr = 0;
+            if (has_vars(str)) attr |= PDE_ATTR_HAS_VARS;
+            if (strcmp(str, "1") == 0) attr |= PDE_ATTR_IS_ONE;
+            if (strncmp(str, "inv(", 4) == 0) attr |= PDE_ATTR_STARTS_INV;
+            e->attrs[i] = attr;
+            e->term_begin[i] = (uint32_t)e->term_sign.size();
+            e->flags[i] = w.flags[k];
+            const uint32_t p1 = w.pool_end[k], f1 = w.fix_end[k], nt = w.n_terms[k];
+            if (!e->flags[i]) {
+                const size_t nc0 = s->const_keys.size(), np0 = s->pow_keys.size();
+                for (uint32_t f = f0; f < f1; ++f) {
+                    const int slot = table_slot(s, w.fixes[f]);
+                    if (slot < 0) { e->flags[i] = PDE_FLAG_TABLE_FULL; break; }
+                    w.pool[w.fixes[f].pos] = (uint8_t)((w.fixes[f].is_pow ? PDE_OP_POW0 : PDE_OP_CONST0) + slot);
+                }
+                if (e->flags[i]) {   // tables stay append-only only for successful compiles
+                    s->const_keys.resize(nc0); s->const_vals.resize(nc0); s->const_num.resize(nc0); s->const_den.resize(nc0);
+                    s->pow_keys.resize(np0); s->pow_vals.resize(np0); s->pow_num.resize(np0); s->pow_den.resize(np0);
+                } else {
+                    const uint32_t base = (uint32_t)e->pool.size();
+                    e->pool.insert(e->pool.end(), w.pool.begin() + p0, w.pool.begin() + p1);
+                    for (uint32_t t = 0; t < nt; ++t) {
+                        e->term_sign.push_back(w.term_sign[t0 + t]);
+                        e->term_off.push_back(base + (w.term_off[t0 + t] - p0));
+                    }
+                }
+            }
+            p0 = p1; f0 = f1; t0 += nt;
+        }
+    }
+    e->term_begin[n] = (uint32_t)e->term_sign.size();
+    *out = e.release();
+    return PDE_OK;
 }
 
 template <typename T>
@@ -341,95 +486,75 @@ static int upload(T** dptr, const std::vector<T>& v) {
 
 }  // namespace
 
+namespace pde {
+
+// Dense lexicographic rank (Python str comparison == byte comparison for ASCII): only the enumerator's
+// `a > b` / `a == b` tests need it (LBF:168-195), so it is computed on first use, not by every compile.
+void exprset_ensure_rank(pde_exprset* e) {
+    if (e->rank_ready) return;
+    const int n = e->n;
+    e->rank.assign(n, 0);
+    const char* blob = e->str_blob.data();
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        int c = strcmp(blob + e->str_off[a], blob + e->str_off[b]);
+        return c < 0 || (c == 0 && a < b);
+    });
+    uint32_t r = 0;
+    for (int k = 0; k < n; ++k) {
+        if (k > 0 && strcmp(blob + e->str_off[order[k]], blob + e->str_off[order[k - 1]]) != 0) ++r;
+        e->rank[order[k]] = r;
+    }
+    e->rank_ready = true;
+}
+
+// Device mirrors of the operand set: needed by the enumerator only, uploaded on first use
+// to the device current at that time.
+int exprset_ensure_device(pde_exprset* e) {
+    if (e->device >= 0) return PDE_OK;
+    if (!have_device()) { set_error("exprset has no device mirror: no CUDA device"); return PDE_E_NODEVICE; }
+    exprset_ensure_rank(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int rc;
+    if ((rc = upload(&e->d_flags, e->flags))) return rc;
+    if ((rc = upload(&e->d_attrs, e->attrs))) return rc;
+    if ((rc = upload(&e->d_rank, e->rank))) return rc;
+    if ((rc = upload(&e->d_term_begin, e->term_begin))) return rc;
+    if ((rc = upload(&e->d_term_sign, e->term_sign))) return rc;
+    if ((rc = upload(&e->d_term_off, e->term_off))) return rc;
+    if ((rc = upload(&e->d_pool, e->pool))) return rc;
+    e->device = dev;
+    return PDE_OK;
+}
+
+}  // namespace pde
+
 extern "C" {
 
 int pde_compile_exprs(pde_session* s, const char* const* strs, int n, pde_exprset** out) {
     if (!s || !out || n < 0 || (n > 0 && !strs)) { pde::set_error("pde_compile_exprs: bad argument"); return PDE_E_INVALID; }
-    std::unique_ptr<pde_exprset> e(new pde_exprset());
-    e->n = n;
-    e->flags.assign(n, 0);
-    e->attrs.assign(n, 0);
-    e->rank.assign(n, 0);
-    e->term_begin.assign(n + 1, 0);
-    e->term_off.push_back(0);
+    std::string blob;
+    std::vector<uint32_t> off(n + 1, 0);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += strlen(strs[i]) + 1;
+    if (total >= 0xffffffffULL) { pde::set_error("pde_compile_exprs: input too large"); return PDE_E_OVERFLOW; }
+    blob.reserve(total);
+    for (int i = 0; i < n; ++i) { off[i] = (uint32_t)blob.size(); blob.append(strs[i]); blob.push_back('\0'); }
+    off[n] = (uint32_t)blob.size();
+    return compile_impl(s, blob.data(), off.data(), n, out);
+}
+
+int pde_compile_exprs_packed(pde_session* s, const char* blob, const uint32_t* offsets, int n, pde_exprset** out) {
+    if (!s || !out || n < 0 || (n > 0 && (!blob || !offsets))) { pde::set_error("pde_compile_exprs_packed: bad argument"); return PDE_E_INVALID; }
     for (int i = 0; i < n; ++i) {
-        const char* str = strs[i];
-        e->term_begin[i] = (uint32_t)e->term_sign.size();
-        uint8_t attr = 0;
-        if (has_vars(str)) attr |= PDE_ATTR_HAS_VARS;
-        if (strcmp(str, "1") == 0) attr |= PDE_ATTR_IS_ONE;
-        if (strncmp(str, "inv(", 4) == 0) attr |= PDE_ATTR_STARTS_INV;
-        e->attrs[i] = attr;
-        const size_t pool0 = e->pool.size(), nt0 = e->term_sign.size();
-        const size_t nc0 = s->const_keys.size(), np0 = s->pow_keys.size();
-        try {
-            Arena ar;
-            Parser ps(str, s, ar);
-            Node* ir = ps.parse_expr();
-            ps.ws();
-            if (ps.pos != ps.n) throw Unsupported();
-            Emitter em{s, ar};
-            std::vector<Emitter::Term> terms;
-            em.split_terms(ir, terms);
-            size_t total = 0;
-            for (auto& t : terms) {
-                std::vector<uint8_t> body;
-                em.emit_term(t.body, body);
-                e->pool.insert(e->pool.end(), body.begin(), body.end());
-                e->term_sign.push_back((int8_t)t.sign);
-                e->term_off.push_back((uint32_t)e->pool.size());
-                total += body.size() + 1;
-            }
-            // whole program length: bodies + (NEG for a leading minus) + (nterms-1) ADD/SUB
-            size_t whole = e->pool.size() - pool0 + (terms[0].sign < 0 ? 1 : 0) + (terms.size() - 1);
-            if (whole > 255) {
-                e->flags[i] = PDE_FLAG_TOO_LONG;
-                throw 0;
-            }
-        } catch (const TableFull&) {
-            e->flags[i] = PDE_FLAG_TABLE_FULL;
-        } catch (const Unsupported&) {
-            e->flags[i] = PDE_FLAG_UNSUPPORTED;
-        } catch (int) {
-        }
-        if (e->flags[i]) {
-            // roll back partial output (tables stay append-only only for successful compiles)
-            e->pool.resize(pool0);
-            e->term_sign.resize(nt0);
-            e->term_off.resize(nt0 + 1);
-            s->const_keys.resize(nc0); s->const_vals.resize(nc0);
-            s->pow_keys.resize(np0); s->pow_vals.resize(np0);
+        if (offsets[i + 1] <= offsets[i] || blob[offsets[i + 1] - 1] != '\0') {
+            pde::set_error("pde_compile_exprs_packed: string %d is not NUL terminated at offsets[%d] - 1", i, i + 1);
+            return PDE_E_INVALID;
         }
     }
-    e->term_begin[n] = (uint32_t)e->term_sign.size();
-    // dense lexicographic rank (Python str comparison == byte comparison for ASCII)
-    {
-        std::vector<int> order(n);
-        std::iota(order.begin(), order.end(), 0);
-        std::sort(order.begin(), order.end(), [&](int a, int b) {
-            int c = strcmp(strs[a], strs[b]);
-            return c < 0 || (c == 0 && a < b);
-        });
-        uint32_t r = 0;
-        for (int k = 0; k < n; ++k) {
-            if (k > 0 && strcmp(strs[order[k]], strs[order[k - 1]]) != 0) ++r;
-            e->rank[order[k]] = r;
-        }
-    }
-    // device mirrors (skipped when there is no device: host-only use in CPU tests)
-    if (pde::have_device()) {
-        cudaGetDevice(&e->device);
-        int rc;
-        if ((rc = upload(&e->d_flags, e->flags))) return rc;
-        if ((rc = upload(&e->d_attrs, e->attrs))) return rc;
-        if ((rc = upload(&e->d_rank, e->rank))) return rc;
-        if ((rc = upload(&e->d_term_begin, e->term_begin))) return rc;
-        if ((rc = upload(&e->d_term_sign, e->term_sign))) return rc;
-        if ((rc = upload(&e->d_term_off, e->term_off))) return rc;
-        if ((rc = upload(&e->d_pool, e->pool))) return rc;
-    }
-    *out = e.release();
-    return PDE_OK;
+    return compile_impl(s, blob, offsets, n, out);
 }
 
 void pde_exprset_free(pde_exprset* e) {
@@ -454,7 +579,7 @@ int pde_exprset_export(const pde_exprset* e, uint8_t* flags, uint8_t* attrs, uin
     if (!e) { pde::set_error("null exprset"); return PDE_E_INVALID; }
     if (flags) memcpy(flags, e->flags.data(), e->flags.size());
     if (attrs) memcpy(attrs, e->attrs.data(), e->attrs.size());
-    if (rank) memcpy(rank, e->rank.data(), e->rank.size() * 4);
+    if (rank) { pde::exprset_ensure_rank(const_cast<pde_exprset*>(e)); memcpy(rank, e->rank.data(), e->rank.size() * 4); }
     if (term_begin) memcpy(term_begin, e->term_begin.data(), e->term_begin.size() * 4);
     if (term_sign) memcpy(term_sign, e->term_sign.data(), e->term_sign.size());
     if (term_off) memcpy(term_off, e->term_off.data(), e->term_off.size() * 4);
@@ -464,22 +589,34 @@ int pde_exprset_export(const pde_exprset* e, uint8_t* flags, uint8_t* attrs, uin
 
 int pde_exprset_programs(const pde_exprset* e, int L, uint8_t* code, uint8_t* len) {
     if (!e || !code || !len || L < 1 || L > 256) { pde::set_error("pde_exprset_programs: bad argument"); return PDE_E_INVALID; }
-    memset(code, 0, (size_t)e->n * L);
-    for (int i = 0; i < e->n; ++i) {
-        len[i] = 0;
-        if (e->flags[i]) continue;
-        uint8_t buf[512];
-        int w = 0;
-        for (uint32_t t = e->term_begin[i]; t < e->term_begin[i + 1]; ++t) {
-            uint32_t b0 = e->term_off[t], b1 = e->term_off[t + 1];
-            memcpy(buf + w, e->pool.data() + b0, b1 - b0);
-            w += (int)(b1 - b0);
-            if (t == e->term_begin[i]) { if (e->term_sign[t] < 0) buf[w++] = PDE_OP_NEG; }
-            else buf[w++] = e->term_sign[t] > 0 ? PDE_OP_ADD : PDE_OP_SUB;
+    auto fill = [&](int lo, int hi) {
+        memset(code + (size_t)lo * L, 0, (size_t)(hi - lo) * L);
+        for (int i = lo; i < hi; ++i) {
+            len[i] = 0;
+            if (e->flags[i]) continue;
+            uint8_t buf[512];
+            int w = 0;
+            for (uint32_t t = e->term_begin[i]; t < e->term_begin[i + 1]; ++t) {
+                uint32_t b0 = e->term_off[t], b1 = e->term_off[t + 1];
+                memcpy(buf + w, e->pool.data() + b0, b1 - b0);
+                w += (int)(b1 - b0);
+                if (t == e->term_begin[i]) { if (e->term_sign[t] < 0) buf[w++] = PDE_OP_NEG; }
+                else buf[w++] = e->term_sign[t] > 0 ? PDE_OP_ADD : PDE_OP_SUB;
+            }
+            if (w > L || w > 255) continue;
+            memcpy(code + (size_t)i * L, buf, w);
+            len[i] = (uint8_t)w;
         }
-        if (w > L || w > 255) continue;
-        memcpy(code + (size_t)i * L, buf, w);
-        len[i] = (uint8_t)w;
+    };
+    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char* ev = getenv("PDE_B200_COMPILE_THREADS")) nthreads = atoi(ev);
+    nthreads = std::max(1, std::min(nthreads, e->n / 8192 + 1));
+    if (nthreads == 1) fill(0, e->n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back(fill, (int)((long long)e->n * t / nthreads), (int)((long long)e->n * (t + 1) / nthreads));
+        for (auto& x : th) x.join();
     }
     return PDE_OK;
 }

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) synth_kernel(unsigned long long seed, lon
 
 static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int depth, int prune, EnumParams& p) {
     if (!e || !depth_begin || depth < 2 || depth > kMaxDepth) { set_error("enumerate: bad argument (depth 2..%d)", kMaxDepth); return PDE_E_INVALID; }
-    if (e->device < 0) { set_error("exprset has no device mirror"); return PDE_E_NODEVICE; }
+    if (int rc = exprset_ensure_device(const_cast<pde_exprset*>(e))) return rc;
     if (depth_begin[0] != 0 || depth_begin[depth - 1] != e->n) { set_error("depth_begin must start at 0 and end at n_expr"); return PDE_E_INVALID; }
     p.flags = e->d_flags; p.attrs = e->d_attrs; p.rank = e->d_rank; p.term_begin = e->d_term_begin;
     p.term_sign = e->d_term_sign; p.term_off = e->d_term_off; p.pool = e->d_pool;
