@@ -50,10 +50,10 @@ enum UKind : uint8_t {
     U_SETV0, U_SETV1, U_SETC, U_SETP,         // T = leaf (first leaf of a sub-tree); flag bit 0: S[sp++] = T first
     U_FNV, U_FNC,                             // T = F(coordinate), F(constant): F's Taylor coefficients ARE the jet
     U_ADD_S, U_ADD_P,                         // T = T + U
-    U_SUB_P,                                  // T = T - U
+    U_SUB_S, U_SUB_P,                         // T = T - U
     U_RSUB_S,                                 // T = U - T
     U_MUL_S, U_MUL_P,                         // T = T * U
-    U_DIV_P,                                  // T = T / U
+    U_DIV_S, U_DIV_P,                         // T = T / U  (in place on the numerator)
     U_RDIV_S, U_RDIV_P,                       // T = U / T  (in place on U, copied back)
     U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
@@ -104,26 +104,67 @@ __device__ __forceinline__ bool op_is_unary(unsigned b) {
            (b >= PDE_OP_POW0 && b < PDE_OP_POW0 + PDE_N_POW);
 }
 
-constexpr uint8_t V_JET_T = 0x03;  // virtual-stack markers (unused opcode values)
-constexpr uint8_t V_JET_S = 0x04;
-
 __host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 
 // Postfix bytecode -> micro-ops.  Returns 0 ok, 1 malformed, 2 spill overflow.
-// Invariant: the top-most jet of the virtual stack is always T; older jets are
-// spilled in stack order, leaves never occupy a jet.
-__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* vst, int ns_max) {
-    int sp = 0, nu = 0, ns = 0, tpos = -1;
+//
+// Machine model: the most recent unfinished value is the register jet T, older ones are spilled in
+// stack order, leaves never occupy a jet (they are fused into the op that consumes them, or set into
+// T by the first op of a sub-tree -- which spills T if it holds a live value).
+// Evaluation ORDER is chosen per binary node (Sethi-Ullman): when both operands are sub-trees the one
+// that needs more spill slots is evaluated first, so need(node) = min(max(nl, nr + 1), max(nr, nl + 1))
+// instead of the postfix order's max(nl, nr + 1).  On the 143 461 real depth-4 force-free uniques the
+// postfix order needs up to 7 slots (12 473 candidates need more than 2); this order needs at most 2 for
+// every one of them.  Ties evaluate a denominator first: T / S then runs in place on the numerator.
+//   pass 1: sub-tree start and spill need of every position (stack of root positions in `stk`);
+//   pass 2: emission with an explicit frame stack (position, phase) in `stk`.
+// start[], need[] and stk[] are caller-provided byte arrays of L, L and 2L bytes.
+__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* start, uint8_t* need, uint8_t* stk, int ns_max) {
+    // ---- pass 1 ----
+    int sp = 0;
+    for (int i = 0; i < len; ++i) {
+        const unsigned b = code[i];
+        if (op_is_leaf(b)) {
+            start[i] = (uint8_t)i; need[i] = 0; stk[sp++] = (uint8_t)i;
+        } else if (op_is_unary(b)) {
+            if (sp < 1) return 1;
+            const int c = stk[sp - 1];
+            start[i] = start[c]; need[i] = need[c] & 0x7f; stk[sp - 1] = (uint8_t)i;
+        } else if (op_is_binary(b)) {
+            if (sp < 2) return 1;
+            const int r = stk[sp - 1], l = stk[sp - 2];
+            sp -= 2;
+            start[i] = start[l];
+            const bool lf_l = op_is_leaf(code[l]), lf_r = op_is_leaf(code[r]);
+            const int nl = need[l] & 0x7f, nr = need[r] & 0x7f;
+            if (!lf_l && !lf_r) {
+                const int left_first = nl > nr + 1 ? nl : nr + 1, right_first = nr > nl + 1 ? nr : nl + 1;
+                const bool rf = right_first < left_first || (right_first == left_first && b == PDE_OP_DIV);
+                need[i] = (uint8_t)((rf ? right_first : left_first) | (rf ? 0x80 : 0));
+            } else {
+                need[i] = (uint8_t)(lf_l ? (lf_r ? 0 : nr) : nl);
+            }
+            stk[sp++] = (uint8_t)i;
+        } else {
+            return 1;
+        }
+    }
+    if (sp != 1) return 1;
+    const int root = stk[0];
+    if ((need[root] & 0x7f) > ns_max) return 2;
+
+    // ---- pass 2 ----
+    int nu = 0, ns = 0;
+    bool t_live = false;
     auto emit = [&](unsigned kind, unsigned arg, unsigned flags = 0) { uc[nu++] = kind | (arg << 8) | flags; };
-    // T is about to be overwritten by a leaf: its value moves to the spill stack (a flag of the SET/FN op)
-    auto spill_t = [&](unsigned& flag) -> bool {
-        flag = 0;
-        if (tpos < 0) return true;
-        if (ns >= ns_max) return false;
-        flag = F_SPILL; vst[tpos] = V_JET_S; ++ns;
-        return true;
+    // T is about to be overwritten by a leaf: a live value moves to the spill stack (a flag of the SET/FN op)
+    auto spill_flag = [&]() -> unsigned {
+        if (!t_live) { t_live = true; return 0; }
+        ++ns;
+        return F_SPILL;
     };
-    auto set_leaf = [&](unsigned leaf, unsigned flag) {
+    auto set_leaf = [&](unsigned leaf) {
+        const unsigned flag = spill_flag();
         if (leaf >= PDE_OP_CONST0) emit(U_SETC, leaf - PDE_OP_CONST0, flag);
         else if (op_is_prim(leaf)) emit(U_SETP, leaf - PDE_OP_PRIM0, flag);
         else emit(leaf == PDE_OP_VAR0 ? U_SETV0 : U_SETV1, 0, flag);
@@ -138,83 +179,101 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             emit(o == 0 ? U_ADD_P : o == 1 ? U_SUB_P : o == 2 ? U_MUL_P : U_DIV_P, leaf - PDE_OP_PRIM0);
         }
     };
-    for (int pc = 0; pc < len; ++pc) {
-        const unsigned b = code[pc];
-        if (op_is_leaf(b)) {
-            vst[sp++] = (uint8_t)b;
-        } else if (op_is_unary(b)) {
-            if (sp < 1) return 1;
-            const unsigned top = vst[sp - 1];
-            // the unary op as (function, exponent slot); 4 = not one of the scalar-function kinds
-            unsigned fn = 4, slot = 0, kind = U_NEG, arg = 0;
-            switch (b) {
-                case PDE_OP_NEG: case PDE_OP_FN_NEG: kind = U_NEG; break;
-                case PDE_OP_ABS: kind = U_ABS; break;
-                case PDE_OP_SQRT: kind = U_SQRT; break;
-                case PDE_OP_FN_SQUARE: kind = U_SQUARE; break;
-                case PDE_OP_EXP: kind = U_EXP; arg = 0; fn = FN_EXP; break;
-                case PDE_OP_FN_EXPNEG: kind = U_EXP; arg = 1; fn = FN_EXPN; break;
-                case PDE_OP_FN_INV: kind = U_INV; fn = FN_INV; break;
-                case PDE_OP_FN_POW32: kind = U_POW; arg = 0; fn = FN_POW; slot = 0; break;
-                case PDE_OP_FN_POWN32: kind = U_POW; arg = 1; fn = FN_POW; slot = 1; break;
-                default: {
-                    slot = b - PDE_OP_POW0;
-                    const double k = c_pow[slot];
-                    if (k == 2.0) kind = U_SQUARE;
-                    else if (k == 0.5) kind = U_SQRT;
-                    else if (k == -1.0) { kind = U_INV; fn = FN_INV; }
-                    else { kind = U_POW; arg = slot; fn = FN_POW; }
-                }
+    // the unary op at position i applied to T, or fused with its leaf operand
+    auto unary = [&](unsigned b, int leaf_operand /* -1: operand is T */) {
+        unsigned fn = 4, slot = 0, kind = U_NEG, arg = 0;     // fn 4 = not one of the scalar-function kinds
+        switch (b) {
+            case PDE_OP_NEG: case PDE_OP_FN_NEG: kind = U_NEG; break;
+            case PDE_OP_ABS: kind = U_ABS; break;
+            case PDE_OP_SQRT: kind = U_SQRT; break;
+            case PDE_OP_FN_SQUARE: kind = U_SQUARE; break;
+            case PDE_OP_EXP: kind = U_EXP; arg = 0; fn = FN_EXP; break;
+            case PDE_OP_FN_EXPNEG: kind = U_EXP; arg = 1; fn = FN_EXPN; break;
+            case PDE_OP_FN_INV: kind = U_INV; fn = FN_INV; break;
+            case PDE_OP_FN_POW32: kind = U_POW; arg = 0; fn = FN_POW; slot = 0; break;
+            case PDE_OP_FN_POWN32: kind = U_POW; arg = 1; fn = FN_POW; slot = 1; break;
+            default: {
+                slot = b - PDE_OP_POW0;
+                const double k = c_pow[slot];
+                if (k == 2.0) kind = U_SQUARE;
+                else if (k == 0.5) kind = U_SQRT;
+                else if (k == -1.0) { kind = U_INV; fn = FN_INV; }
+                else { kind = U_POW; arg = slot; fn = FN_POW; }
             }
-            if (top != V_JET_T) {
-                if (top == V_JET_S) return 1;
-                unsigned flag;
-                if (!spill_t(flag)) return 2;
-                vst[sp - 1] = V_JET_T; tpos = sp - 1;
-                if (fn < 4 && slot < 32 && !op_is_prim(top)) {
-                    // F(coordinate) / F(constant): the jet is F's own Taylor expansion, no jet arithmetic
-                    const unsigned fl = flag | (fn << 17) | (slot << 19);
-                    if (top >= PDE_OP_CONST0) emit(U_FNC, top - PDE_OP_CONST0, fl);
-                    else emit(U_FNV, top - PDE_OP_VAR0, fl);
-                    continue;
-                }
-                set_leaf(top, flag);
+        }
+        if (leaf_operand >= 0) {
+            const unsigned leaf = (unsigned)leaf_operand;
+            if (fn < 4 && slot < 32 && !op_is_prim(leaf)) {
+                // F(coordinate) / F(constant): the jet is F's own Taylor expansion, no jet arithmetic
+                const unsigned fl = spill_flag() | (fn << 17) | (slot << 19);
+                if (leaf >= PDE_OP_CONST0) emit(U_FNC, leaf - PDE_OP_CONST0, fl);
+                else emit(U_FNV, leaf - PDE_OP_VAR0, fl);
+                return;
             }
-            emit(kind, arg);
-        } else if (op_is_binary(b)) {
-            if (sp < 2) return 1;
-            const unsigned bb = vst[sp - 1], aa = vst[sp - 2];
-            sp -= 2;
-            const unsigned o = b - PDE_OP_ADD;  // 0 add 1 sub 2 mul 3 div
-            if (aa == V_JET_S && bb == V_JET_T) {                                   // S op T
-                emit(o == 0 ? U_ADD_S : o == 1 ? U_RSUB_S : o == 2 ? U_MUL_S : U_RDIV_S, 0);
-                --ns;
-            } else if (aa == V_JET_T && bb != V_JET_S) {
-                bin_leaf_right(o, bb);
-            } else if (bb == V_JET_T && aa != V_JET_S) {
-                if (o == 0 || o == 2) bin_leaf_right(o, aa);                        // commutative
-                else if (o == 1) {                                                  // leaf - T
-                    if (aa >= PDE_OP_CONST0) emit(U_RSUBC, aa - PDE_OP_CONST0);
-                    else { emit(U_NEG, 0); bin_leaf_right(0, aa); }
-                } else if (op_is_prim(aa)) emit(U_RDIV_P, aa - PDE_OP_PRIM0);        // PRIM / T
-                else { emit(U_INV, 0); bin_leaf_right(2, aa); }                     // x / T = (1 / T) * x (sparse)
-            } else if (aa != V_JET_S && bb != V_JET_S && aa != V_JET_T && bb != V_JET_T) {
-                unsigned flag;
-                if (!spill_t(flag)) return 2;
-                set_leaf(aa, flag);
-                bin_leaf_right(o, bb);
+            set_leaf(leaf);
+        }
+        emit(kind, arg);
+    };
+    if (op_is_leaf(code[root])) {
+        set_leaf(code[root]);
+    } else {
+        int fs = 0;     // frames: stk[2 f] = position, stk[2 f + 1] = phase
+        stk[0] = (uint8_t)root; stk[1] = 0; fs = 1;
+        while (fs > 0) {
+            const int i = stk[2 * fs - 2], ph = stk[2 * fs - 1];
+            const unsigned b = code[i];
+            if (op_is_unary(b)) {
+                const int c = i - 1;
+                if (ph == 0 && !op_is_leaf(code[c])) {
+                    stk[2 * fs - 1] = 1;
+                    stk[2 * fs] = (uint8_t)c; stk[2 * fs + 1] = 0; ++fs;
+                } else {
+                    --fs;
+                    unary(b, ph == 0 ? (int)code[c] : -1);
+                }
+                continue;
+            }
+            const int r = i - 1, l = start[r] - 1;
+            const unsigned bl = code[l], br = code[r], o = b - PDE_OP_ADD;
+            const bool lf_l = op_is_leaf(bl), lf_r = op_is_leaf(br), rf = (need[i] & 0x80) != 0;
+            if (ph == 0) {
+                if (lf_l && lf_r) {
+                    --fs;
+                    set_leaf(bl);
+                    bin_leaf_right(o, br);
+                } else {
+                    const int first = lf_r ? l : lf_l ? r : (rf ? r : l);
+                    stk[2 * fs - 1] = 1;
+                    stk[2 * fs] = (uint8_t)first; stk[2 * fs + 1] = 0; ++fs;
+                }
+            } else if (ph == 1) {
+                if (lf_r) {                                      // T op leaf
+                    --fs;
+                    bin_leaf_right(o, br);
+                } else if (lf_l) {                               // leaf op T
+                    --fs;
+                    if (o == 0 || o == 2) bin_leaf_right(o, bl);                        // commutative
+                    else if (o == 1) {                                                  // leaf - T
+                        if (bl >= PDE_OP_CONST0) emit(U_RSUBC, bl - PDE_OP_CONST0);
+                        else { emit(U_NEG, 0); bin_leaf_right(0, bl); }
+                    } else if (op_is_prim(bl)) emit(U_RDIV_P, bl - PDE_OP_PRIM0);        // PRIM / T
+                    else { emit(U_INV, 0); bin_leaf_right(2, bl); }                     // x / T = (1 / T) * x (sparse)
+                } else {
+                    const int second = rf ? l : r;
+                    if (ns >= ns_max) return 2;                  // the second sub-tree's first leaf will spill T
+                    stk[2 * fs - 1] = 2;
+                    stk[2 * fs] = (uint8_t)second; stk[2 * fs + 1] = 0; ++fs;
+                }
             } else {
-                return 1;
+                --fs;
+                // left first: S = a, T = b;  right first: S = b, T = a
+                if (rf) emit(o == 0 ? U_ADD_S : o == 1 ? U_SUB_S : o == 2 ? U_MUL_S : U_DIV_S, 0);
+                else emit(o == 0 ? U_ADD_S : o == 1 ? U_RSUB_S : o == 2 ? U_MUL_S : U_RDIV_S, 0);
+                --ns;
             }
-            vst[sp] = V_JET_T; tpos = sp; ++sp;
-        } else {
-            return 1;
         }
     }
-    if (sp != 1) return 1;
-    if (vst[0] != V_JET_T) set_leaf(vst[0], 0);
     emit(U_END, 0);
-    emit(U_END, 0);      // the interpreter prefetches two words ahead
     return 0;
 }
 
@@ -423,7 +482,9 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
 #pragma unroll
                 PDE_EACH jet_add(T[h], U[h]);
                 break;
+            case U_SUB_S: PDE_FETCH_S goto l_sub;
             case U_SUB_P: PDE_FETCH_P
+            l_sub:
 #pragma unroll
                 PDE_EACH jet_sub(T[h], U[h]);
                 break;
@@ -436,7 +497,9 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
             l_mul:
                 jetv_mul<N, NP>(T, U);
                 break;
+            case U_DIV_S: PDE_FETCH_S goto l_div;
             case U_DIV_P: PDE_FETCH_P
+            l_div:
                 jetv_div<N, NP>(T, U);
                 break;
             // U / T: the division runs in place on the numerator U; the copy back is opaque to the
@@ -604,9 +667,9 @@ struct WarpPartial {
 
 template <int N, int NP>
 __host__ __device__ constexpr size_t cta_smem_bytes(int L, int ns, int W) {
-    // per warp: code[L] | vstack[L] | ucode[2L+6] u32 ; then partials[W][4] ; status[W] ; then
-    // spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
-    return ((size_t)((L + 15) / 16 * 16) * 2 + (size_t)(kUcodeMax(L) * 4 + 15) / 16 * 16) * W +
+    // per warp: code[L] | start[L] | need[L] | frames[2L] | ucode[2L+6] u32 ; then partials[W][4] ; status[W] ;
+    // then spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
+    return ((size_t)((L + 15) / 16 * 16) * 5 + (size_t)(kUcodeMax(L) * 4 + 15) / 16 * 16) * W +
            (size_t)W * 4 * sizeof(WarpPartial) + 16 * W +
            (size_t)ns * Jet<N>::NC * NP * 32 * W * 8;
 }
@@ -629,11 +692,10 @@ validate_kernel(const ValidateParams p) {
     const int grp = warp >> 2, wg = warp & 3;
     const int Lp = (p.L + 15) / 16 * 16;
     const int ucb = (kUcodeMax(p.L) * 4 + 15) / 16 * 16;
-    const size_t per_cand = (size_t)Lp * 2 + ucb;
+    const size_t per_cand = (size_t)Lp * 5 + ucb;
     unsigned char* my = smem + per_cand * warp;
     uint8_t* s_code = my;
-    uint8_t* s_vst = my + Lp;
-    uint32_t* s_uc_mine = reinterpret_cast<uint32_t*>(my + 2 * Lp);
+    uint32_t* s_uc_mine = reinterpret_cast<uint32_t*>(my + 5 * Lp);
     WarpPartial* s_part = reinterpret_cast<WarpPartial*>(smem + per_cand * W) + grp * 16;   // [cand slot][warp of group]
     int* s_status = reinterpret_cast<int*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial)) + grp * 4;
     double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
@@ -653,7 +715,7 @@ validate_kernel(const ValidateParams p) {
                 for (int i = lane; i * 4 < len; i += 32) dst[i] = __ldg(src + i);
                 __syncwarp();
                 if (lane == 0) {
-                    status = (len == 0) ? -1 : translate(s_code, len, s_uc_mine, s_vst, p.ns);
+                    status = (len == 0) ? -1 : translate(s_code, len, s_uc_mine, my + Lp, my + 2 * Lp, my + 3 * Lp, p.ns);
                     s_status[wg] = status;
                 }
             } else if (lane == 0) {
@@ -666,7 +728,7 @@ validate_kernel(const ValidateParams p) {
             const long long cand = cand0 + c;
             const int status = s_status[c];
             if (status != 0) continue;
-            const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 2 * Lp));
+            const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 5 * Lp));
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
             const size_t prim_stride = (size_t)p.P * 16;

@@ -61,7 +61,7 @@ class BatchVerdict:
 class GpuBatchValidator:
     def __init__(self, cpu_validator: Any = None, problem: str = "force_free", P: int = 4096,
                  tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, L: int = 128,
-                 spill_slots: int = 3, sympify_locals: Optional[dict] = None, device=None):
+                 spill_slots: int = 2, sympify_locals: Optional[dict] = None, device=None):
         import torch
         self.cpu_validator = cpu_validator
         self.problem = canonical_slug(problem)
