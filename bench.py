@@ -376,12 +376,23 @@ def run_ours(args):
             except Exception:
                 pass
             gbs = n5 * bytes_per / (ems * 1e-3) / 1e9
+            # the enumerator only WRITES: pure-write HBM rate for context (fill of 2 GiB, best of 5)
+            wbuf = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+            wbuf.fill_(1)
+            wbest = 0.0
+            for _ in range(5):
+                wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                wa.record(); wbuf.fill_(2); wb.record(); torch.cuda.synchronize()
+                wbest = max(wbest, wbuf.numel() / (wa.elapsed_time(wb) * 1e-3) / 1e9)
+            del wbuf
             enum_info = {"depth": 5, "n_candidates": int(n5), "distinct_programs": int(nuniq), "L": Le,
                          "ms_per_pass": ems, "launches_per_pass": int((pb.launch_count() - l0) // 3),
                          "algorithmic_bytes_per_candidate": bytes_per, "achieved_GBps": gbs,
                          "peak_GBps": hbm_peak if hbm_peak else 6650.0,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6.65 TB/s (B200_PROFILING.md)",
                          "frac": gbs / (hbm_peak if hbm_peak else 6650.0),
+                         "write_only_peak_GBps": wbest, "frac_of_write_only_peak": gbs / wbest,
+                         "note": "the pass writes 149 B per candidate and reads ~0 (operands are L2 resident): the copy-rate peak counts read + write bytes, a write-only stream (torch fill) reaches write_only_peak_GBps on this GPU",
                          "candidates_per_s": n5 / (ems * 1e-3)}
             del cand, first
         except Exception as e:

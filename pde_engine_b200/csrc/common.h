@@ -60,6 +60,10 @@ struct pde_exprset {
     int8_t* d_term_sign = nullptr;
     uint32_t* d_term_off = nullptr;
     uint8_t* d_pool = nullptr;
+    std::vector<uint32_t> desc;         // [n][2] splice descriptors (enumerate.cu)
+    std::vector<uint8_t> wpool;         // whole programs, padded by 8 bytes
+    uint32_t* d_desc = nullptr;
+    uint8_t* d_wpool = nullptr;
 };
 
 struct pde_program {

@@ -515,9 +515,39 @@ int exprset_ensure_device(pde_exprset* e) {
     if (e->device >= 0) return PDE_OK;
     if (!have_device()) { set_error("exprset has no device mirror: no CUDA device"); return PDE_E_NODEVICE; }
     exprset_ensure_rank(e);
+    // splice descriptors + whole programs (enumerate.cu): whole(i) = t1 [NEG] (tk ADD|SUB)*
+    {
+        e->desc.assign((size_t)e->n * 2, 0);
+        e->wpool.clear();
+        e->wpool.reserve(e->pool.size() + e->term_sign.size() + 8);
+        for (int i = 0; i < e->n; ++i) {
+            const uint32_t t0 = e->term_begin[i], t1 = e->term_begin[i + 1];
+            const uint32_t off = (uint32_t)e->wpool.size();
+            unsigned fl = 0, first_len = 0, last_off = 0;
+            if (e->flags[i] || t1 == t0) fl = 8;                 // D_BAD
+            else {
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const uint32_t b0 = e->term_off[t], b1 = e->term_off[t + 1];
+                    if (t == t1 - 1) last_off = (unsigned)(e->wpool.size() - off);
+                    e->wpool.insert(e->wpool.end(), e->pool.begin() + b0, e->pool.begin() + b1);
+                    if (t == t0) { first_len = b1 - b0; if (e->term_sign[t] < 0) e->wpool.push_back(PDE_OP_NEG); }
+                    else e->wpool.push_back(e->term_sign[t] > 0 ? PDE_OP_ADD : PDE_OP_SUB);
+                }
+                if (e->term_sign[t0] < 0) fl |= 1;               // D_FIRST_NEG
+                if (e->term_sign[t1 - 1] < 0) fl |= 2;           // D_LAST_NEG
+                if (t1 - t0 > 1) fl |= 4;                        // D_MULTI
+            }
+            const unsigned len = (unsigned)(e->wpool.size() - off);   // <= 255 (longer programs are flagged TOO_LONG)
+            e->desc[2 * (size_t)i] = off;
+            e->desc[2 * (size_t)i + 1] = len | (first_len << 8) | (last_off << 16) | (fl << 24);
+        }
+        e->wpool.resize(e->wpool.size() + 8, 0);                 // the word-wise reader looks one word ahead
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     int rc;
+    if ((rc = upload(&e->d_desc, e->desc))) return rc;
+    if ((rc = upload(&e->d_wpool, e->wpool))) return rc;
     if ((rc = upload(&e->d_flags, e->flags))) return rc;
     if ((rc = upload(&e->d_attrs, e->attrs))) return rc;
     if ((rc = upload(&e->d_rank, e->rank))) return rc;
@@ -561,7 +591,7 @@ void pde_exprset_free(pde_exprset* e) {
     if (!e) return;
     if (e->device >= 0) {
         cudaFree(e->d_flags); cudaFree(e->d_attrs); cudaFree(e->d_rank); cudaFree(e->d_term_begin);
-        cudaFree(e->d_term_sign); cudaFree(e->d_term_off); cudaFree(e->d_pool);
+        cudaFree(e->d_term_sign); cudaFree(e->d_term_off); cudaFree(e->d_pool); cudaFree(e->d_desc); cudaFree(e->d_wpool);
     }
     delete e;
 }

@@ -26,23 +26,28 @@
 
 namespace pde {
 
-constexpr int kEnumThreads = 128;
+constexpr int kEnumThreads = 160;     // a block = 160 consecutive slots of the reference's loop nest
 constexpr int kMaxDepth = 8;
 constexpr int kMaxRow = 256;
 
+// Per-expression splice descriptor (built on the host next to the device mirror): every op of the
+// reference's textual templates (LBF:170-195) is a concatenation of at most 8 pieces, each a contiguous
+// range of the operand's WHOLE program  t1 [NEG] (tk ADD|SUB)*  or a literal byte:
+//   x = offset of the whole program in wpool
+//   y = whole length | first body length << 8 | offset of the last body << 16 | flags << 24
+enum : unsigned { D_FIRST_NEG = 1, D_LAST_NEG = 2, D_MULTI = 4, D_BAD = 8 };
+
 struct EnumParams {
-    const uint8_t* flags;
+    const uint2* desc;
+    const uint8_t* wpool;      // padded by 8 bytes
     const uint8_t* attrs;
     const uint32_t* rank;
-    const uint32_t* term_begin;
-    const int8_t* term_sign;
-    const uint32_t* term_off;
-    const uint8_t* pool;
     int depth;
     int prune;
     int depth_begin[kMaxDepth + 1];
-    long long seg_begin[kMaxDepth + 1];  // dense slot index where segment k starts (0 = unary)
-    long long n_slots;
+    // segment 0 = unary (160 consecutive slots per block), segment d1 >= 1 = binary (32 pairs x 5 ops per block)
+    long long seg_block[kMaxDepth + 1];    // first block of the segment; seg_block[depth] = number of blocks
+    long long seg_groups[kMaxDepth + 1];   // unary: slots; binary: pairs
 };
 
 // enumerator unary op index -> opcode (iteration order of UNARY_OPS, expression_operations.py:80-89)
@@ -54,19 +59,27 @@ __device__ const uint8_t kLeaf[5] = {PDE_OP_VAR0, PDE_OP_VAR1, PDE_OP_PRIM0, PDE
 struct Slot {
     int op;       // 0..7 unary, 8..12 binary
     int a, b;     // global operand indices after the add/mul swap (b = -1 for unary)
+    int local;    // position of the slot in the block, in the reference's order
     bool keep;
 };
 
-__device__ __forceinline__ Slot decode_slot(const EnumParams& p, long long s) {
+// Thread -> slot.  Unary blocks: thread t = slot t (every unary op takes the same splice path).  Binary
+// blocks: lane = pair, warp = op, so a warp executes ONE splice path (the v1 mapping, thread = slot, had
+// five paths per warp: 9.4 of 32 threads active per instruction, profiles/README.md).
+__device__ __forceinline__ Slot decode_slot(const EnumParams& p) {
     Slot r;
-    r.keep = true;
+    r.keep = false; r.op = 0; r.a = 0; r.b = -1;
     const int d = p.depth;
-    if (s < p.seg_begin[1]) {
+    const long long blk = blockIdx.x;
+    if (blk < p.seg_block[1]) {
         // unary, LBF:142-153
+        r.local = threadIdx.x;
+        const long long s = blk * kEnumThreads + threadIdx.x;
+        if (s >= p.seg_groups[0]) return r;
         const int e = (int)(s >> 3);
         r.op = (int)(s & 7);
         r.a = p.depth_begin[d - 2] + e;
-        r.b = -1;
+        r.keep = true;
         if (p.prune) {
             const unsigned at = p.attrs[r.a];
             if (!(at & PDE_ATTR_HAS_VARS)) r.keep = false;
@@ -76,20 +89,25 @@ __device__ __forceinline__ Slot decode_slot(const EnumParams& p, long long s) {
         return r;
     }
     int d1 = 1;
-    while (d1 < d - 1 && s >= p.seg_begin[d1 + 1]) ++d1;
-    const unsigned t = (unsigned)(s - p.seg_begin[d1]);      // every segment is < 2^32 slots (checked on the host)
+    while (d1 < d - 1 && blk >= p.seg_block[d1 + 1]) ++d1;
+    const int lane = threadIdx.x & 31, bop = threadIdx.x >> 5;
+    r.local = lane * 5 + bop;
+    const long long pair = (blk - p.seg_block[d1]) * 32 + lane;
+    if (pair >= p.seg_groups[d1]) return r;
     const int d2 = d - d1;
     const unsigned n2 = (unsigned)(p.depth_begin[d2] - p.depth_begin[d2 - 1]);
-    const unsigned pair = t / 5u;
-    const int bop = (int)(t - pair * 5u);
-    const unsigned i1 = pair / n2;
+    const unsigned i1 = (unsigned)pair / n2;                       // pairs < 2^32 (checked on the host)
     int a = p.depth_begin[d1 - 1] + (int)i1;
-    int b = p.depth_begin[d2 - 1] + (int)(pair - i1 * n2);
+    int b = p.depth_begin[d2 - 1] + (int)((unsigned)pair - i1 * n2);
     const unsigned ata = p.attrs[a], atb = p.attrs[b];
+    r.keep = true;
     if (p.prune && !((ata | atb) & PDE_ATTR_HAS_VARS)) r.keep = false;
     const uint32_t ra = p.rank[a], rb = p.rank[b];
-    if ((bop == 0 || bop == 2) && ra > rb) { int tmp = a; a = b; b = tmp; }   // LBF:168-169
-    const bool one_a = p.attrs[a] & PDE_ATTR_IS_ONE, one_b = p.attrs[b] & PDE_ATTR_IS_ONE;
+    bool one_a = ata & PDE_ATTR_IS_ONE, one_b = atb & PDE_ATTR_IS_ONE;
+    if ((bop == 0 || bop == 2) && ra > rb) {                      // LBF:168-169
+        const int t = a; a = b; b = t;
+        const bool tb = one_a; one_a = one_b; one_b = tb;
+    }
     if (p.prune) {
         if (bop == 1 && ra == rb) r.keep = false;                   // a - a
         if (bop == 2 && (one_a || one_b)) r.keep = false;           // * 1
@@ -102,8 +120,12 @@ __device__ __forceinline__ Slot decode_slot(const EnumParams& p, long long s) {
     return r;
 }
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+// exclusive prefix of the keep flags in SLOT order (slot_local), block total in `total`
+__device__ __forceinline__ int block_exclusive_scan(int keep, int slot_local, int* s_flag, int* s_warp, int& total) {
+    s_flag[slot_local] = keep;
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = s_flag[threadIdx.x];
     int x = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -120,37 +142,69 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
         if (w < warp) base += c;
         total += c;
     }
+    s_flag[threadIdx.x] = base + x - v;
     __syncthreads();
-    return base + x - v;
+    return s_flag[slot_local];
 }
 
 __global__ void __launch_bounds__(kEnumThreads) enum_count_kernel(const EnumParams p, unsigned* block_sums) {
-    __shared__ int s_warp[kEnumThreads / 32];
-    const long long s = (long long)blockIdx.x * kEnumThreads + threadIdx.x;
-    int keep = 0;
-    if (s < p.n_slots) keep = decode_slot(p, s).keep ? 1 : 0;
-    int total;
-    block_exclusive_scan(keep, s_warp, total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned)total;
+    const Slot sl = decode_slot(p);
+    const int n = __syncthreads_count(sl.keep ? 1 : 0);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned)n;
 }
 
-// single block: exclusive scan of block_sums -> block_off (int64), total
-__global__ void __launch_bounds__(1024) scan_sums_kernel(const unsigned* sums, long long* off, int nblocks, long long* total) {
-    __shared__ long long s_part[1024];
-    const int per = (nblocks + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, nblocks);
-    long long acc = 0;
-    for (int i = lo; i < hi; ++i) acc += sums[i];
+// Two-level exclusive scan of the per-block candidate counts (the first version scanned all ~10^5 counts
+// in ONE block with strided accesses: 93 us of a 0.68 ms pass).
+//   scan_tiles_kernel: tile t = 1024 consecutive counts: in-tile exclusive prefix (u32) + tile total
+//   scan_super_kernel: exclusive prefix of the tile totals (one block), grand total
+// A block's base = tile_off[b / 1024] + in_tile[b].
+constexpr int kScanTile = 1024;
+
+__global__ void __launch_bounds__(kScanTile) scan_tiles_kernel(const unsigned* sums, unsigned* in_tile, unsigned long long* tile_total, int nblocks) {
+    __shared__ unsigned s_w[kScanTile / 32];
+    const int i = blockIdx.x * kScanTile + threadIdx.x;
+    const unsigned v = i < nblocks ? sums[i] : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = s_w[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, t, off);
+            if (lane >= off) t += y;
+        }
+        s_w[lane] = t;            // inclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const unsigned base = warp ? s_w[warp - 1] : 0u;
+    if (i < nblocks) in_tile[i] = base + x - v;
+    if (threadIdx.x == kScanTile - 1) tile_total[blockIdx.x] = (unsigned long long)base + x;
+}
+
+__global__ void __launch_bounds__(1024) scan_super_kernel(unsigned long long* tile_total, int ntiles, long long* total) {
+    // ntiles is small (blocks / 1024): serial chunks per thread, then a serial pass over 1024 partials
+    __shared__ unsigned long long s_part[1024];
+    const int per = (ntiles + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, ntiles);
+    unsigned long long acc = 0;
+    for (int i = lo; i < hi; ++i) acc += tile_total[i];
     s_part[threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long run = 0;
-        for (int i = 0; i < 1024; ++i) { long long c = s_part[i]; s_part[i] = run; run += c; }
-        *total = run;
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) { const unsigned long long c = s_part[i]; s_part[i] = run; run += c; }
+        *total = (long long)run;
     }
     __syncthreads();
-    long long run = s_part[threadIdx.x];
-    for (int i = lo; i < hi; ++i) { off[i] = run; run += sums[i]; }
+    unsigned long long run = s_part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) { const unsigned long long c = tile_total[i]; tile_total[i] = run; run += c; }
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -169,111 +223,168 @@ __device__ __forceinline__ unsigned long long hash_row(const uint8_t* row, int l
     return h;
 }
 
+// Row assembly in 32-bit words: pieces are appended through a 64-bit shift register and flushed a word at
+// a time; source bytes come from two aligned loads + a funnel shift (the v1 writer moved single bytes with
+// a bounds check each: ~6 instructions per byte).
 struct RowWriter {
-    uint8_t* row;
+    uint32_t* dst;            // shared-memory row, cap words
     int cap;
-    int n;
-    bool ok;
-    __device__ void put(unsigned b) { if (n < cap) row[n] = (uint8_t)b; else ok = false; ++n; }
-    __device__ void copy(const uint8_t* src, int len) { for (int i = 0; i < len; ++i) put(src[i]); }
+    unsigned long long acc;   // pending bytes, low k
+    int k, nw, n;
+    __device__ __forceinline__ void flush() {
+        if (nw < cap) dst[nw] = (uint32_t)acc;
+        ++nw; acc >>= 32; k -= 4;
+    }
+    __device__ __forceinline__ void put(unsigned b) {
+        acc |= (unsigned long long)b << (8 * k);
+        ++k; ++n;
+        if (k == 4) flush();
+    }
+    __device__ __forceinline__ void copy(const uint32_t* pool32, unsigned src, int len) {
+        n += len;
+        while (len > 0) {
+            const unsigned al = src >> 2, sh = (src & 3u) * 8u;
+            uint32_t v = __funnelshift_r(__ldg(pool32 + al), __ldg(pool32 + al + 1), sh);   // 4 bytes from src
+            const int m = len < 4 ? len : 4;
+            if (m < 4) v &= (1u << (8 * m)) - 1u;
+            acc |= (unsigned long long)v << (8 * k);
+            k += m;
+            if (k >= 4) flush();
+            src += (unsigned)m; len -= m;
+        }
+    }
+    __device__ __forceinline__ void finish() {       // last partial word (the tile is pre-zeroed)
+        if (k > 0) { if (nw < cap) dst[nw] = (uint32_t)acc; ++nw; }
+    }
 };
 
-// emit `whole` form of terms [t0, t1) of an expression; first_sign overrides the sign of the first term
-__device__ __forceinline__ void emit_terms(RowWriter& w, const EnumParams& p, uint32_t t0, uint32_t t1, bool fresh, int first_sign_mul) {
-    for (uint32_t t = t0; t < t1; ++t) {
-        const uint32_t b0 = p.term_off[t], b1 = p.term_off[t + 1];
-        w.copy(p.pool + b0, (int)(b1 - b0));
-        int sg = p.term_sign[t];
-        if (t == t0) sg *= first_sign_mul;
-        if (fresh && t == t0) { if (sg < 0) w.put(PDE_OP_NEG); }
-        else w.put(sg > 0 ? PDE_OP_ADD : PDE_OP_SUB);
+struct Desc {
+    unsigned off, len, first_len, last_off, fl;
+    __device__ __forceinline__ explicit Desc(const uint2 d)
+        : off(d.x), len(d.y & 0xffu), first_len((d.y >> 8) & 0xffu), last_off((d.y >> 16) & 0xffu), fl(d.y >> 24) {}
+    // bytes of `whole` taken by the first term in fresh mode: body + optional NEG
+    __device__ __forceinline__ unsigned skip() const { return first_len + ((fl & D_FIRST_NEG) ? 1u : 0u); }
+    __device__ __forceinline__ unsigned last_len() const {
+        return len - last_off - ((fl & D_MULTI) ? 1u : ((fl & D_FIRST_NEG) ? 1u : 0u));
     }
-}
+};
 
-__device__ void splice(RowWriter& w, const EnumParams& p, const Slot& sl) {
-    const uint32_t a0 = p.term_begin[sl.a], a1 = p.term_begin[sl.a + 1];
-    if (sl.op < 8) {
-        emit_terms(w, p, a0, a1, true, 1);
-        w.put(kUnary[sl.op]);
+// The reference's templates on whole programs (see the file header):
+//   unary  whole(a) op
+//   add    whole(a) body1(b) (ADD|SUB by sign1(b)) rest(b)          sub: sign flipped
+//   mul    lead(a) last(a) body1(b) [NEG] MUL sign(last a) rest(b)
+//   div    lead(a) last(a) whole(b) DIV sign(last a)
+//   geom   lead(a) last(a) 1 body1(b) [NEG] SUB rest(b) DIV sign(last a)
+// lead(a) = whole(a) up to its last body; rest(b) = whole(b) after its first term; sign(last a) = ADD|SUB
+// for a multi-term a, NEG for a negative single term.
+__device__ __forceinline__ void splice(RowWriter& w, const uint32_t* pool32, int op, const Desc& A, const Desc& B) {
+    if (op < 8) {
+        w.copy(pool32, A.off, (int)A.len);
+        w.put(kUnary[op]);
         return;
     }
-    const uint32_t b0 = p.term_begin[sl.b], b1 = p.term_begin[sl.b + 1];
-    const int bop = sl.op - 8;
-    if (bop == 0) {            // terms(a) ++ terms(b)
-        emit_terms(w, p, a0, a1, true, 1);
-        emit_terms(w, p, b0, b1, false, 1);
-    } else if (bop == 1) {     // terms(a) ++ [-t1(b)] ++ rest(b)
-        emit_terms(w, p, a0, a1, true, 1);
-        emit_terms(w, p, b0, b1, false, -1);
-    } else {
-        // leading terms of a, then the combined last term carrying last(a)'s sign
-        emit_terms(w, p, a0, a1 - 1, true, 1);
-        const uint32_t tl = a1 - 1;
-        w.copy(p.pool + p.term_off[tl], (int)(p.term_off[tl + 1] - p.term_off[tl]));
-        if (bop == 2) {        // last(a) * first(b)
-            w.copy(p.pool + p.term_off[b0], (int)(p.term_off[b0 + 1] - p.term_off[b0]));
-            if (p.term_sign[b0] < 0) w.put(PDE_OP_NEG);
-            w.put(PDE_OP_MUL);
-        } else if (bop == 3) { // last(a) / (whole b)
-            emit_terms(w, p, b0, b1, true, 1);
-            w.put(PDE_OP_DIV);
-        } else {               // last(a) / (1 - t1(b) +- ...)
-            w.put(PDE_OP_CONST0);   // CONST(0) = 1
-            w.copy(p.pool + p.term_off[b0], (int)(p.term_off[b0 + 1] - p.term_off[b0]));
-            if (p.term_sign[b0] < 0) w.put(PDE_OP_NEG);
-            w.put(PDE_OP_SUB);
-            emit_terms(w, p, b0 + 1, b1, false, 1);
-            w.put(PDE_OP_DIV);
-        }
-        // sign of the combined term / position in the chain
-        const int sg = p.term_sign[tl];
-        if (a1 - a0 == 1) { if (sg < 0) w.put(PDE_OP_NEG); }
-        else w.put(sg > 0 ? PDE_OP_ADD : PDE_OP_SUB);
-        if (bop == 2) emit_terms(w, p, b0 + 1, b1, false, 1);
+    const int bop = op - 8;
+    const unsigned skip = B.skip();
+    const bool bneg = B.fl & D_FIRST_NEG;
+    if (bop <= 1) {
+        w.copy(pool32, A.off, (int)A.len);
+        w.copy(pool32, B.off, (int)B.first_len);
+        w.put((bneg != (bop == 1)) ? PDE_OP_SUB : PDE_OP_ADD);
+        w.copy(pool32, B.off + skip, (int)(B.len - skip));
+        return;
     }
+    w.copy(pool32, A.off, (int)(A.last_off + A.last_len()));          // lead(a) ++ last(a): contiguous
+    if (bop == 2) {
+        w.copy(pool32, B.off, (int)B.first_len);
+        if (bneg) w.put(PDE_OP_NEG);
+        w.put(PDE_OP_MUL);
+    } else if (bop == 3) {
+        w.copy(pool32, B.off, (int)B.len);
+        w.put(PDE_OP_DIV);
+    } else {
+        w.put(PDE_OP_CONST0);   // CONST(0) = 1
+        w.copy(pool32, B.off, (int)B.first_len);
+        if (bneg) w.put(PDE_OP_NEG);
+        w.put(PDE_OP_SUB);
+        w.copy(pool32, B.off + skip, (int)(B.len - skip));
+        w.put(PDE_OP_DIV);
+    }
+    if (A.fl & D_MULTI) w.put((A.fl & D_LAST_NEG) ? PDE_OP_SUB : PDE_OP_ADD);
+    else if (A.fl & D_FIRST_NEG) w.put(PDE_OP_NEG);
+    if (bop == 2) w.copy(pool32, B.off + skip, (int)(B.len - skip));
 }
 
+// Shared-memory rows are L + 16 bytes apart: with a stride of L = 128 bytes every lane's row starts in the
+// same bank and each word store of the row owners was a 32-way conflict (mio_throttle + short_scoreboard
+// were the top stalls, profiles/README.md); L + 16 keeps rows 16-byte aligned for the vector copy-out.
+__host__ __device__ constexpr int enum_row_stride(int L) { return L + 16; }
+
 __global__ void __launch_bounds__(kEnumThreads)
-enum_emit_kernel(const EnumParams p, const long long* block_off, long long first, long long count, int L,
+enum_emit_kernel(const EnumParams p, const unsigned* in_tile, const unsigned long long* tile_off, long long first, long long count, int L,
                  int32_t* triple, uint8_t* code, uint8_t* len_out, unsigned long long* hash_out) {
-    extern __shared__ __align__(16) uint8_t s_rows[];   // [kEnumThreads][L]
+    extern __shared__ __align__(16) uint8_t s_rows[];   // [kEnumThreads][L + 16] rows, then per-row hash / triple / len
+    __shared__ int s_flag[kEnumThreads];
     __shared__ int s_warp[kEnumThreads / 32];
-    const long long s = (long long)blockIdx.x * kEnumThreads + threadIdx.x;
-    Slot sl;
-    sl.keep = false;
-    if (s < p.n_slots) sl = decode_slot(p, s);
-    int total;
-    const int local = block_exclusive_scan(sl.keep ? 1 : 0, s_warp, total);
-    const long long base = block_off[blockIdx.x];
-    if (total == 0 || base + total <= first || base >= first + count) return;
-    {   // zero the block's tile with 16-byte stores (padding + unused rows)
+    const int Ls = enum_row_stride(L);
+    unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(s_rows + (size_t)kEnumThreads * Ls);
+    int* s_triple = reinterpret_cast<int*>(s_hash + kEnumThreads);
+    uint8_t* s_len = reinterpret_cast<uint8_t*>(s_triple + 3 * kEnumThreads);
+    {   // zero the tile with 16-byte stores (padding of every row); ordered before the splice by the scan's barriers
         uint4* z = reinterpret_cast<uint4*>(s_rows);
-        const int nz = total * L / 16;
+        const int nz = kEnumThreads * Ls / 16;
         for (int i = threadIdx.x; i < nz; i += kEnumThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
+    const Slot sl = decode_slot(p);
+    int total;
+    const int local = block_exclusive_scan(sl.keep ? 1 : 0, sl.local, s_flag, s_warp, total);
+    const long long base = (long long)(tile_off[blockIdx.x / kScanTile] + in_tile[blockIdx.x]);
+    if (total == 0 || base + total <= first || base >= first + count) return;
     if (sl.keep) {
-        uint8_t* row = s_rows + (size_t)local * L;
-        RowWriter w{row, L < 255 ? L : 255, 0, true};
-        if (p.flags[sl.a] || (sl.b >= 0 && p.flags[sl.b])) w.ok = false;
-        else splice(w, p, sl);
-        int n = w.ok ? w.n : 0;
-        if (!w.ok) for (int i = 0; i < L && i < w.n; ++i) row[i] = 0;      // overflowed rows are emitted empty
-        const long long c = base + local;
-        if (c >= first && c < first + count) {
-            const long long o = c - first;
-            triple[o * 3 + 0] = sl.op; triple[o * 3 + 1] = sl.a; triple[o * 3 + 2] = sl.b;
-            len_out[o] = (uint8_t)n;
-            hash_out[o] = hash_row(row, n);
+        uint8_t* row = s_rows + (size_t)local * Ls;
+        RowWriter w{reinterpret_cast<uint32_t*>(row), L / 4, 0ULL, 0, 0, 0};
+        const Desc A(__ldg(p.desc + sl.a));
+        const Desc B(sl.b >= 0 ? __ldg(p.desc + sl.b) : make_uint2(0u, 0u));
+        const bool bad = (A.fl | B.fl) & D_BAD;
+        if (!bad) splice(w, reinterpret_cast<const uint32_t*>(p.wpool), sl.op, A, B);
+        int n = w.n;
+        w.finish();
+        if (bad || n > L || n > 255) {                                   // not compilable / too long: emitted empty
+            n = 0;
+            for (int i = 0; i < L / 4 && i < w.nw; ++i) reinterpret_cast<uint32_t*>(row)[i] = 0u;
         }
+        s_len[local] = (uint8_t)n;
+        s_triple[3 * local + 0] = sl.op; s_triple[3 * local + 1] = sl.a; s_triple[3 * local + 2] = sl.b;
+        s_hash[local] = hash_row(row, n);
     }
     __syncthreads();
-    // coalesced 16-byte copy of the block's tile (rows [lo, hi) of this block)
+    // coalesced copy-out of the block's rows [lo, hi) (the window may cut the block)
     const long long lo = max(base, first), hi = min(base + (long long)total, first + count);
-    const uint4* src = reinterpret_cast<const uint4*>(s_rows + (size_t)(lo - base) * L);
-    uint4* dst = reinterpret_cast<uint4*>(code + (size_t)(lo - first) * L);
-    const int nvec = (int)((hi - lo) * L / 16);
-    for (int i = threadIdx.x; i < nvec; i += kEnumThreads) dst[i] = src[i];
+    const int r0 = (int)(lo - base), nr = (int)(hi - lo);
+    const long long o0 = lo - first;
+    {
+        // thread t copies 16-byte vectors t, t + 160, ...: (row, column) advance incrementally (no division
+        // per vector: i / (L / 16) was the hottest line of the kernel)
+        uint4* dst = reinterpret_cast<uint4*>(code + (size_t)o0 * L);
+        const int vpr = L / 16, nvec = nr * vpr;
+        const int dr = kEnumThreads / vpr, dc = kEnumThreads - dr * vpr;
+        int r = (int)threadIdx.x / vpr, c = (int)threadIdx.x - r * vpr;
+        const uint8_t* src = s_rows + (size_t)r0 * Ls;
+        for (int i = threadIdx.x; i < nvec; i += kEnumThreads) {
+            dst[i] = *reinterpret_cast<const uint4*>(src + r * Ls + c * 16);
+            r += dr; c += dc;
+            if (c >= vpr) { c -= vpr; ++r; }
+        }
+    }
+    {
+        unsigned long long* ho = hash_out + o0;
+        uint8_t* lo8 = len_out + o0;
+        int* to = triple + o0 * 3;
+        const unsigned long long* hs = s_hash + r0;
+        const uint8_t* ls = s_len + r0;
+        const int* ts = s_triple + 3 * r0;
+        for (int i = threadIdx.x; i < nr; i += kEnumThreads) { ho[i] = hs[i]; lo8[i] = ls[i]; }
+        for (int i = threadIdx.x; i < 3 * nr; i += kEnumThreads) to[i] = ts[i];
+    }
 }
 
 // ------------------------------------------------------------------ dedup
@@ -380,26 +491,26 @@ static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int dep
     if (!e || !depth_begin || depth < 2 || depth > kMaxDepth) { set_error("enumerate: bad argument (depth 2..%d)", kMaxDepth); return PDE_E_INVALID; }
     if (int rc = exprset_ensure_device(const_cast<pde_exprset*>(e))) return rc;
     if (depth_begin[0] != 0 || depth_begin[depth - 1] != e->n) { set_error("depth_begin must start at 0 and end at n_expr"); return PDE_E_INVALID; }
-    p.flags = e->d_flags; p.attrs = e->d_attrs; p.rank = e->d_rank; p.term_begin = e->d_term_begin;
-    p.term_sign = e->d_term_sign; p.term_off = e->d_term_off; p.pool = e->d_pool;
+    p.desc = reinterpret_cast<const uint2*>(e->d_desc); p.wpool = e->d_wpool; p.attrs = e->d_attrs; p.rank = e->d_rank;
     p.depth = depth; p.prune = prune;
     for (int k = 0; k < depth; ++k) {
         p.depth_begin[k] = depth_begin[k];
         if (k > 0 && depth_begin[k] < depth_begin[k - 1]) { set_error("depth_begin must be non-decreasing"); return PDE_E_INVALID; }
     }
-    long long s = 0;
-    p.seg_begin[0] = 0;
-    s += (long long)(depth_begin[depth - 1] - depth_begin[depth - 2]) * 8;
+    long long blk = 0;
+    p.seg_block[0] = 0;
+    p.seg_groups[0] = (long long)(depth_begin[depth - 1] - depth_begin[depth - 2]) * 8;
+    blk += (p.seg_groups[0] + kEnumThreads - 1) / kEnumThreads;
     for (int d1 = 1; d1 < depth; ++d1) {
-        p.seg_begin[d1] = s;
+        p.seg_block[d1] = blk;
         const int d2 = depth - d1;
         const long long n1 = depth_begin[d1] - depth_begin[d1 - 1], n2 = depth_begin[d2] - depth_begin[d2 - 1];
-        if (n1 * n2 * 5 >= 0xffffffffLL) { set_error("candidate index space too large"); return PDE_E_OVERFLOW; }
-        s += n1 * n2 * 5;
+        if (n1 * n2 >= 0xffffffffLL) { set_error("candidate index space too large"); return PDE_E_OVERFLOW; }
+        p.seg_groups[d1] = n1 * n2;
+        blk += (n1 * n2 + 31) / 32;
     }
-    p.seg_begin[depth] = s;
-    p.n_slots = s;
-    if (s / kEnumThreads + 1 > 0x7fffffffLL) { set_error("candidate index space too large"); return PDE_E_OVERFLOW; }
+    p.seg_block[depth] = blk;
+    if (blk + 1 > 0x7fffffffLL) { set_error("candidate index space too large"); return PDE_E_OVERFLOW; }
     return PDE_OK;
 }
 
@@ -409,29 +520,33 @@ using namespace pde;
 
 // scratch shared by count + emit (per process; one host thread per device)
 static unsigned* g_sums = nullptr;
-static long long* g_off = nullptr;
+static unsigned* g_in_tile = nullptr;
+static unsigned long long* g_tile = nullptr;
 static long long* g_total = nullptr;
 static long long g_cap = 0;
 
 static int ensure_scratch(long long nblocks) {
     if (nblocks <= g_cap) return PDE_OK;
-    cudaFree(g_sums); cudaFree(g_off); cudaFree(g_total);
-    g_sums = nullptr; g_off = nullptr; g_total = nullptr; g_cap = 0;
+    cudaFree(g_sums); cudaFree(g_in_tile); cudaFree(g_tile); cudaFree(g_total);
+    g_sums = nullptr; g_in_tile = nullptr; g_tile = nullptr; g_total = nullptr; g_cap = 0;
     PDE_CUDA(cudaMalloc(&g_sums, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&g_off, sizeof(long long) * nblocks));
+    PDE_CUDA(cudaMalloc(&g_in_tile, sizeof(unsigned) * nblocks));
+    PDE_CUDA(cudaMalloc(&g_tile, sizeof(unsigned long long) * (nblocks / kScanTile + 1)));
     PDE_CUDA(cudaMalloc(&g_total, sizeof(long long)));
     g_cap = nblocks;
     return PDE_OK;
 }
 
 static int run_count(const EnumParams& p, cudaStream_t st, long long* total_host) {
-    const long long nblocks = (p.n_slots + kEnumThreads - 1) / kEnumThreads;
+    const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0) { if (total_host) *total_host = 0; return PDE_OK; }
     int rc = ensure_scratch(nblocks);
     if (rc) return rc;
+    const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
     enum_count_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, g_sums);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(g_sums, g_off, (int)nblocks, g_total);
-    count_launch(2);
+    scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(g_sums, g_in_tile, g_tile, (int)nblocks);
+    scan_super_kernel<<<1, 1024, 0, st>>>(g_tile, ntiles, g_total);
+    count_launch(3);
     PDE_CUDA(cudaGetLastError());
     if (total_host) {
         PDE_CUDA(cudaMemcpyAsync(total_host, g_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -469,11 +584,11 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
     cudaStream_t st = (cudaStream_t)stream;
     rc = run_count(p, st, nullptr);
     if (rc) return rc;
-    const long long nblocks = (p.n_slots + kEnumThreads - 1) / kEnumThreads;
+    const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0) return PDE_OK;
-    const size_t smem = (size_t)kEnumThreads * L;
+    const size_t smem = (size_t)kEnumThreads * (enum_row_stride(L) + 8 + 12 + 1) + 16;
     PDE_CUDA(cudaFuncSetAttribute(enum_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enum_emit_kernel<<<(unsigned)nblocks, kEnumThreads, smem, st>>>(p, g_off, first, count, L, triple, code, len,
+    enum_emit_kernel<<<(unsigned)nblocks, kEnumThreads, smem, st>>>(p, g_in_tile, g_tile, first, count, L, triple, code, len,
                                                                     reinterpret_cast<unsigned long long*>(hash));
     count_launch();
     PDE_CUDA(cudaGetLastError());
