@@ -64,7 +64,7 @@ CREATE TABLE IF NOT EXISTS {table} (
 def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Optional[str] = None,
                   run_id: str = "gpu_run", db_normalize: Optional[Callable[[str], str]] = None,
                   is_degenerate: Optional[Callable[[Any], bool]] = None, batch_size: int = 2000,
-                  match_known: bool = True) -> Dict[str, Any]:
+                  match_known: bool = True, confirm_pool: Any = None) -> Dict[str, Any]:
     """Enumerate to ``max_depth`` and validate every unique (GM:1251-1411 semantics).
 
     spec          ProblemSpec whose ``validator`` is a GpuBatchValidator
@@ -73,6 +73,9 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
                   out of scope; returns None for rows the reference drops as degenerate);
                   None = use the expression string (no DB dedup)
     is_degenerate ``_has_degenerate_denominator`` of GM:134-199 (CPU, out of scope)
+    confirm_pool  a ``confirm.ConfirmationPool``: the survivors of each chunk are confirmed by its CPU
+                  worker processes (most plausible first, wall cap per candidate) instead of inline;
+                  rows that hit the cap get ``is_valid = None`` / status ``'timeout'``
     Returns {'rows': [...], 'stats': {...}}; rows carry the run-DB columns.
     """
     import sympy as sp
@@ -98,7 +101,18 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
             except Exception:
                 pass
 
+    def insert(row: dict) -> None:
+        rows.append(row)
+        if cur is not None:
+            cur.execute(f"INSERT INTO {table} (expression, normalized, signature, depth, validation_status, is_valid,"
+                        " validation_reason, validator_method, validator_math, is_paper_solution, paper_solution_name,"
+                        " validator_evidence, validated_at) VALUES (?,?,?,?,?,?,?,?,?,?,?,?,CURRENT_TIMESTAMP)",
+                        (row["expression"], row["normalized"], row["signature"], row["depth"], row["validation_status"],
+                         row["is_valid"], row["validation_reason"], row["validator_method"], row["validator_math"],
+                         row["is_paper_solution"], row["paper_solution_name"], row["validator_evidence"]))
+
     def emit(depth: int, expr_list: List[str]) -> None:
+        pending: List[dict] = []          # rows of this chunk, in order; survivors wait for the pool
         for expr_str in expr_list:
             try:
                 u = sp.sympify(expr_str, locals=locs)                      # GM:1257
@@ -113,19 +127,27 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
                 continue
             seen_norm.add(normalized)
             sig = int(hashlib.sha256(normalized.encode()).hexdigest()[:8], 16)   # GM:1281
+            row = dict(id=0, expression=expr_str, normalized=normalized, signature=sig, depth=depth,
+                       validator_method=desc.get("method_name"), validator_math=desc.get("math_definition"),
+                       is_paper_solution=0, paper_solution_name=None)
+            wait = False
             try:
                 if u is None:
                     u = sp.sympify(expr_str, locals=locs)
                 if not any(u.has(v) for v in coord):
-                    is_valid, reason = False, "constant-only (skipped)"   # GM:1293-1294
+                    is_valid, reason, evidence = False, "constant-only (skipped)", gv.last_evidence()   # GM:1293-1294
+                elif confirm_pool is not None:
+                    survivor, evidence, reason = gv.gpu_verdict(u)
+                    is_valid = False
+                    wait = survivor
                 else:
                     is_valid, reason = gv.validate(u, check_regularity=False, fast_point_only=False,
                                                    lean_first=True, defer_heavy_checks=True, enforce_anchor=False)
-                evidence = gv.last_evidence()
+                    evidence = gv.last_evidence()
             except Exception as e:                                         # GM:1336-1339
                 is_valid, reason, evidence = None, f"Validator Error: {e}", {}
             paper = None
-            if is_valid and known:                                         # GM:1785-1798 (the worker path's matching)
+            if not wait and is_valid and known:                            # GM:1785-1798 (the worker path's matching)
                 for k_expr, name in known.items():
                     try:
                         if sp.simplify(u - k_expr) == 0:
@@ -133,19 +155,25 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
                             break
                     except Exception:
                         pass
-            row = dict(id=len(rows) + 1, expression=expr_str, normalized=normalized, signature=sig, depth=depth,
-                       validation_status="completed" if is_valid is not None else "error", is_valid=is_valid,
-                       validation_reason=reason, validator_method=desc.get("method_name"),
-                       validator_math=desc.get("math_definition"), is_paper_solution=int(paper is not None),
-                       paper_solution_name=paper, validator_evidence=json.dumps(evidence, default=str))
-            rows.append(row)
-            if cur is not None:
-                cur.execute(f"INSERT INTO {table} (expression, normalized, signature, depth, validation_status, is_valid,"
-                            " validation_reason, validator_method, validator_math, is_paper_solution, paper_solution_name,"
-                            " validator_evidence, validated_at) VALUES (?,?,?,?,?,?,?,?,?,?,?,?,CURRENT_TIMESTAMP)",
-                            (row["expression"], row["normalized"], row["signature"], row["depth"], row["validation_status"],
-                             row["is_valid"], row["validation_reason"], row["validator_method"], row["validator_math"],
-                             row["is_paper_solution"], row["paper_solution_name"], row["validator_evidence"]))
+            row.update(is_valid=is_valid, validation_reason=reason, evidence=evidence, wait=wait, paper=paper)
+            pending.append(row)
+        if confirm_pool is not None:
+            # most plausible first: smallest residual ratio, unevaluated candidates last
+            todo = [k for k, r in enumerate(pending) if r["wait"]]
+            todo.sort(key=lambda k: (pending[k]["evidence"].get("n_finite", 0) <= 0, pending[k]["evidence"].get("ratio_max", 0.0)))
+            verdicts = confirm_pool.confirm([pending[k]["expression"] for k in todo])
+            for k, (ok, reason, paper) in zip(todo, verdicts):
+                pending[k].update(is_valid=ok, validation_reason=reason, paper=paper,
+                                  evidence={"gpu": pending[k]["evidence"], "confirmed_by": "confirm.ConfirmationPool"})
+                gv.stats["cpu_confirmed"] += 1
+        for r in pending:
+            ok, reason = r["is_valid"], r["validation_reason"]
+            status = "completed" if ok is not None else ("timeout" if str(reason).startswith("Timeout") else "error")
+            row = {k: r[k] for k in ("expression", "normalized", "signature", "depth", "validator_method", "validator_math")}
+            row.update(id=len(rows) + 1, validation_status=status, is_valid=ok, validation_reason=reason,
+                       is_paper_solution=int(r["paper"] is not None), paper_solution_name=r["paper"],
+                       validator_evidence=json.dumps(r["evidence"], default=str))
+            insert(row)
         if conn is not None:
             conn.commit()
 

@@ -128,8 +128,9 @@ class GpuBatchValidator:
         return (f"PDE residual != 0 (fast point check) | residual: gpu max|R|={ev['resid_max']:.3e}, "
                 f"|R|/S up to {ev['ratio_max']:.2e} at {ev['n_votes']}/{ev['n_finite']} points")
 
-    # ---- the validator protocol (PI:52) -----------------------------------
-    def validate(self, u: Any, check_regularity: bool = True, fast_point_only: bool = False, **kw) -> Tuple[bool, str]:
+    def gpu_verdict(self, u: Any) -> Tuple[bool, dict, Optional[str]]:
+        """The device filter's verdict for one expression (cache hit after `prefetch`):
+        (survivor, evidence, reject reason | None).  Survivors still need the CPU validator."""
         key = str(u)
         hit = self._cache.get(key)
         if hit is None:
@@ -138,9 +139,14 @@ class GpuBatchValidator:
             hit = (bool(bv.survivor[0]), bv.evidence(0), r0)
             self._cache[key] = hit
         survivor, ev, r0 = hit
+        return survivor, ev, (None if survivor else self._reject_reason(r0, ev))
+
+    # ---- the validator protocol (PI:52) -----------------------------------
+    def validate(self, u: Any, check_regularity: bool = True, fast_point_only: bool = False, **kw) -> Tuple[bool, str]:
+        survivor, ev, reason = self.gpu_verdict(u)
         self._last_evidence = ev
         if not survivor:
-            return False, self._reject_reason(r0, ev)
+            return False, reason
         if self.cpu_validator is None:
             return True, "GPU residual filter passed (no CPU validator attached)"
         self.stats["cpu_confirmed"] += 1
