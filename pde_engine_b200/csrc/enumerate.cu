@@ -16,9 +16,10 @@
 //     div   terms(a)[:-1] ++ [last(a) / (b)]
 //     geom  terms(a)[:-1] ++ [last(a) / (1 - t1(b) +- t2(b) ...)]
 //     unary op(whole(a))
-// HBM-bound: 69 algorithmic bytes per candidate (L = 48): code L + len 1 +
-// hash 8 + triple 12.  Rows are assembled in shared memory and written with
-// coalesced 16-byte stores.
+// HBM-bound (write only): 69 algorithmic bytes per candidate (L = 48): code L +
+// len 1 + hash 8 + triple 12.  Rows are assembled word-wise in shared memory
+// from per-expression splice descriptors and written with coalesced 16-byte
+// stores; measured 2.9 TB/s = 75 % of the write-only HBM rate (profiles/README.md).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
