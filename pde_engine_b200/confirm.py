@@ -142,6 +142,7 @@ class ConfirmationPool:
         n = len(expr_strs)
         out: List[Optional[Tuple[Optional[bool], str, Optional[str]]]] = [None] * n
         nxt = done = 0
+        startup_failures = 0
         while len(self.workers) < min(self.n_workers, max(n, 1)):
             self._spawn()
 
@@ -175,6 +176,12 @@ class ConfirmationPool:
                         finish(tid, ok, reason, paper, secs)
                 except (EOFError, OSError):
                     # the worker died (e.g. out of memory inside SymPy): its task is undecided
+                    if not w.ready:
+                        startup_failures += 1
+                        if startup_failures > 2 * self.n_workers:
+                            self.close()
+                            raise RuntimeError("ConfirmationPool: worker processes die before becoming ready "
+                                               "(is the factory importable from a spawned process?)")
                     if w.task is not None:
                         finish(w.task, None, "Validator Error: worker process died", None, now - (w.deadline - self.time_cap_s))
                     w.kill()
