@@ -340,6 +340,42 @@ def run_ours(args):
     except Exception as e:   # the fixture is optional for the headline metric
         depth4 = {"error": repr(e)[:200]}
 
+    # ---- BASELINE configs[3]: kerr_magnetosphere depth 3 (order-2 jets, 16 174 uniques), same span A ----
+    kerr3 = None
+    if rank == 0:
+        try:
+            with gzip.open(os.path.join(REPO, "tests", "golden", "enum_kerr_magnetosphere_d3.json.gz"), "rt") as f:
+                gk = json.load(f)["depths"]
+            uk = [s_ for d in sorted(gk, key=int) for s_ in gk[d]["uniques"]]
+            ksess = pb.Session.for_problem("kerr_magnetosphere")
+            kprog = pb.ResidualProgram.for_problem("kerr_magnetosphere")
+            kpts = collocation_grid("kerr_magnetosphere", P)
+            kpts_t = torch.from_numpy(kpts).to(dev)
+            ktab_t = torch.from_numpy(kprog.point_table(kpts)).to(dev)
+            ew = ksess.compile(uk[:256])
+            cw, lw = ew.programs(128)
+            pb.validate(ksess, kprog, torch.from_numpy(cw).to(dev), torch.from_numpy(lw).to(dev), kpts_t, ktab_t, None, spill_slots=2)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ek = ksess.compile(uk)
+            ck, lk = ek.programs(128)
+            t1 = time.perf_counter()
+            ckd, lkd = torch.from_numpy(ck).to(dev), torch.from_numpy(lk).to(dev)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            ok_ = pb.validate(ksess, kprog, ckd, lkd, kpts_t, ktab_t, None, tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=2)
+            k1.record()
+            kb = ok_["survivor_bits"].cpu()
+            knf = ok_["n_finite"].cpu()
+            t2 = time.perf_counter()
+            kerr3 = {"input": f"{len(uk)} kerr_magnetosphere uniques of depth <= 3 (tests/golden/enum_kerr_magnetosphere_d3.json.gz)",
+                     "n": len(uk), "points": P, "wall_ms_host_strings_to_survivor_bits": (t2 - t0) * 1e3,
+                     "host_compile_ms": (t1 - t0) * 1e3, "kernel_ms": k0.elapsed_time(k1),
+                     "survivors_for_cpu_confirmation": int(sum(bin(int(x) & 0xffffffff).count("1") for x in kb.tolist())),
+                     "not_device_evaluable": int((knf < 0).sum())}
+        except Exception as e:
+            kerr3 = {"error": repr(e)[:200]}
+
     # ---- stage 1 (HBM bound): depth-5 enumeration from the depth 1-4 unique sets ----
     enum_info = None
     if rank == 0 and world == 1 and isinstance(depth4, dict) and "error" not in depth4:
@@ -425,6 +461,7 @@ def run_ours(args):
                                         .reshape(-1, 1) >> np.arange(8) & 1).sum() / n),
             "evaluated_fraction": float((nf >= 0).float().mean().item()),
             "depth4_validation": depth4,
+            "kerr_depth3_validation": kerr3,
             "enumerator": enum_info,
         }
         if not args.no_cpu_baseline and world == 1:
