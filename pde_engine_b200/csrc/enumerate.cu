@@ -599,9 +599,9 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
 int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int64_t n, int L,
               uint8_t* first_occurrence, int64_t* n_unique, void* stream) {
     if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
+    if (n == 0) { if (n_unique) *n_unique = 0; return PDE_OK; }      // an empty batch is a no-op (its buffers may be null)
     if (!code || !len || !hash || !first_occurrence || n < 0 || (L % 16) != 0) { set_error("pde_dedup: bad argument"); return PDE_E_INVALID; }
     if (n >= 0xffffffffLL) { set_error("pde_dedup: n too large"); return PDE_E_OVERFLOW; }
-    if (n == 0) { if (n_unique) *n_unique = 0; return PDE_OK; }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned cap = 1024;
     while ((long long)cap < 2 * n) cap <<= 1;

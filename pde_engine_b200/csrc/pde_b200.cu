@@ -249,7 +249,7 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
 static int check_common(const pde_session* s, const pde_program* p, const void* code, const void* len,
                         int64_t n, int L, const void* pts, const void* tab, int P, int ns) {
     if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
-    if (!s || !p || !code || !len || !pts || !tab) { set_error("null argument"); return PDE_E_INVALID; }
+    if (!s || !p || !pts || !tab || (n > 0 && (!code || !len))) { set_error("null argument"); return PDE_E_INVALID; }
     if (n < 0 || L < 4 || L > kMaxL || (L % 4) != 0) { set_error("L must be a multiple of 4 in [4, %d]", kMaxL); return PDE_E_INVALID; }
     if (P < 64 || (P % 64) != 0) { set_error("P must be a positive multiple of 64"); return PDE_E_INVALID; }
     if (ns < 1 || ns > 8) { set_error("spill_slots must be in 1..8"); return PDE_E_INVALID; }
@@ -264,6 +264,7 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
                  const pde_validate_out* out, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
     if (rc) return rc;
+    if (n == 0) return PDE_OK;              // an empty batch is a no-op (its buffers may be null)
     if (!out || !out->ratio_max || !out->resid_max || !out->scale_at || !out->n_finite || !out->n_votes || !out->survivor_bits) {
         set_error("pde_validate: null output"); return PDE_E_INVALID;
     }

@@ -69,3 +69,36 @@ def test_table_overflow_is_flagged():
     assert fl[:120].sum() == 0 and (fl[130:] == 2).all()        # PDE_FLAG_TABLE_FULL
     osess = op.Session.for_problem("force_free")
     assert [op.compile_expr(s, osess).flags for s in strs] == list(fl)
+
+
+def test_bytecode_does_not_depend_on_the_thread_count(enum_ff, monkeypatch):
+    """The parse runs on up to 16 host threads; table slots are assigned afterwards in string order,
+    so programs, flags and tables are identical for any thread count -- including the roll-back of
+    expressions that hit a full constant table (they must not leave slots behind)."""
+    import hashlib
+    import pde_engine_b200 as pb
+    E = uniques_by_depth(enum_ff)
+    # > 128 distinct constants spread over the batch: the table fills in the middle of a worker's range
+    strs = E[4][:30000] + [f"{k}*rho + z/{k + 1}" for k in range(2, 140)] + E[4][30000:42000] + ["", "rho +", "I*z"]
+    ref = None
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("PDE_B200_COMPILE_THREADS", threads)
+        sess = pb.Session.for_problem("force_free")
+        es = sess.compile(strs)
+        code, ln = es.programs(128)
+        fl = es.flags()
+        got = (hashlib.sha256(code.tobytes() + ln.tobytes() + fl.tobytes()).hexdigest(), sess.const_keys(), sess.pow_keys())
+        if ref is None:
+            ref = got
+            assert (fl == 2).sum() > 10 and sess.tables()[1] == 128       # the table did fill
+            assert fl[-3:].tolist() == [1, 1, 1]
+        assert got == ref, threads
+
+
+def test_empty_batch_compiles():
+    import pde_engine_b200 as pb
+    sess = pb.Session.for_problem("force_free")
+    es = sess.compile([])
+    assert es.sizes() == (0, 0, 0)
+    code, ln = es.programs(16)
+    assert code.shape == (0, 16) and ln.shape == (0,)
