@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--depth", type=int, default=5)
     ap.add_argument("--L", type=int, default=48)
-    ap.add_argument("--cpu-sample", type=int, default=1200, help="trees in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=3600, help="trees in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

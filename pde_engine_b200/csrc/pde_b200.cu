@@ -223,6 +223,9 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 #ifndef PDE_NP_BIG
 #define PDE_NP_BIG 1
 #endif
+#ifndef PDE_NP_KERR
+#define PDE_NP_KERR 2      // points per lane for the order-2 (6-coefficient) Kerr jets: 46.7 vs 37.9 G evals/s (depth-3 uniques)
+#endif
 #ifndef PDE_W_BIG
 #define PDE_W_BIG 20
 #endif
@@ -235,7 +238,8 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
     } else {
         bool fits = false;
         if (g_variant != 4 && g_variant != 16 && vp.P >= 128) {
-            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, PDE_NP_BIG, 1>(vp, st, &fits);
+            constexpr int NPB = PROBLEM == PDE_PROBLEM_KERR ? PDE_NP_KERR : PDE_NP_BIG;
+            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, NPB, 1>(vp, st, &fits);
             if (rc || fits) return rc;
         }
         if (g_variant != 4 && PDE_W_BIG != 16 && vp.P >= 128) {
