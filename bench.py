@@ -223,6 +223,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     fp64_peak = pb.fp64_peak(20000)
+    fp64_peak_3op = pb.fp64_peak_3op(20000)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -455,6 +456,9 @@ def run_ours(args):
                          "traffic": 54.8 * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
                          "peak_source": "measured: pde_fp64_peak register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
+                         # context: a DFMA that reads three different register pairs (acc += a_i * b_j, the operand
+                         # pattern of every jet convolution) issues every 3 cycles, not 2 -- measured on this GPU
+                         "peak_3operand_dfma": fp64_peak_3op, "frac_of_3operand_peak": achieved / fp64_peak_3op,
                          "flops_per_candidate_point": flops_per_point / n, "kernel_ms": kernel_ms,
                          "kernel": "validate_kernel<force_free, reduce>"},
             "survivor_fraction": float((out["survivor_bits"].view(torch.uint8).cpu().numpy().view("uint8")

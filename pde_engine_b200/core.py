@@ -281,3 +281,11 @@ def fp64_peak(iters: int = 20000) -> float:
     t = C.c_double()
     check(lib.pde_fp64_peak(iters, C.byref(t), _stream_ptr()))
     return float(t.value)
+
+
+def fp64_peak_3op(iters: int = 20000) -> float:
+    """DFMA rate when every instruction reads three different register pairs (a jet convolution's
+    operand pattern) -> TFLOP/s; 2/3 of fp64_peak on B200."""
+    t = C.c_double()
+    check(lib.pde_fp64_peak_3op(iters, C.byref(t), _stream_ptr()))
+    return float(t.value)
