@@ -308,6 +308,9 @@ def run_ours(args):
         cw, lw = esw.programs(128)
         pb.validate(sess, prog, torch.from_numpy(cw).to(dev), torch.from_numpy(lw).to(dev), pts_t, tab_t, None,
                     tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=2)
+        if world > 1:     # same for the gather: NCCL sets up its buffers for a message size on first use
+            gather_survivors(torch.zeros((cnt4 + 31) // 32, dtype=torch.int32, device=dev),
+                             torch.zeros(cnt4, dtype=torch.int64, device=dev), cnt4)
         barrier()
         t0 = time.perf_counter()
         es4 = sess.compile(mine)                                    # host compiler: strings -> bytecode
