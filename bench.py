@@ -454,9 +454,9 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
-                         # DRAM bytes per launch: 54.8 B per tree from the ncu --set full capture
-                         # (profiles/r1_validate_full_metrics.csv: 10.96 MB read / 0 written per 200 k trees)
-                         "traffic": 54.8 * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
+                         # DRAM bytes per launch: 55.2 B per tree from the ncu --set full capture
+                         # (profiles/r1b_validate_full_metrics.csv: 11.03 MB read / 0 written per 200 k trees)
+                         "traffic": 55.2 * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
                          "peak_source": "measured: pde_fp64_peak register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
                          # context: a DFMA that reads three different register pairs (acc += a_i * b_j, the operand
