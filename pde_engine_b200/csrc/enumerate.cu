@@ -525,6 +525,10 @@ static unsigned* g_in_tile = nullptr;
 static unsigned long long* g_tile = nullptr;
 static long long* g_total = nullptr;
 static long long g_cap = 0;
+static unsigned long long* g_dedup_keys = nullptr;
+static unsigned* g_dedup_vals = nullptr;
+static unsigned long long* g_dedup_cnt = nullptr;
+static unsigned g_dedup_cap = 0;
 
 static int ensure_scratch(long long nblocks) {
     if (nblocks <= g_cap) return PDE_OK;
@@ -605,12 +609,19 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned cap = 1024;
     while ((long long)cap < 2 * n) cap <<= 1;
-    unsigned long long* keys = nullptr;
-    unsigned* vals = nullptr;
-    unsigned long long* cnt = nullptr;
-    PDE_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * cap));
-    PDE_CUDA(cudaMalloc(&vals, sizeof(unsigned) * cap));
-    PDE_CUDA(cudaMalloc(&cnt, sizeof(unsigned long long)));
+    // grow-only scratch table, kept across calls (allocating and freeing 400 MB per call cost 8-70 ms
+    // around 1.7 ms of kernels)
+    if (cap > g_dedup_cap) {
+        cudaFree(g_dedup_keys); cudaFree(g_dedup_vals); cudaFree(g_dedup_cnt);
+        g_dedup_keys = nullptr; g_dedup_vals = nullptr; g_dedup_cnt = nullptr; g_dedup_cap = 0;
+        PDE_CUDA(cudaMalloc(&g_dedup_keys, sizeof(unsigned long long) * cap));
+        PDE_CUDA(cudaMalloc(&g_dedup_vals, sizeof(unsigned) * cap));
+        PDE_CUDA(cudaMalloc(&g_dedup_cnt, sizeof(unsigned long long)));
+        g_dedup_cap = cap;
+    }
+    unsigned long long* keys = g_dedup_keys;
+    unsigned* vals = g_dedup_vals;
+    unsigned long long* cnt = g_dedup_cnt;
     PDE_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * cap, st));
     PDE_CUDA(cudaMemsetAsync(vals, 0xff, sizeof(unsigned) * cap, st));
     PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
@@ -624,7 +635,6 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     PDE_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
     PDE_CUDA(cudaStreamSynchronize(st));
     if (n_unique) *n_unique = (int64_t)c;
-    cudaFree(keys); cudaFree(vals); cudaFree(cnt);
     return PDE_OK;
 }
 
