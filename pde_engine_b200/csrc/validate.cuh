@@ -4,16 +4,19 @@
 // (general_method_paper_reproduction.py:1302-1316) and the validator worker
 // pool (GM:1672-1824) as a numerical FILTER in front of the symbolic check.
 //
-// Mapping (BASELINE.json north_star): one WARP owns a candidate, each LANE owns
-// collocation points (two per 64-point stripe, fetched with one 128-bit load
-// per coordinate).  Per candidate the warp
-//   1. stages the postfix bytecode in shared memory,
-//   2. translates it once into leaf-fused micro-ops (lane 0),
-//   3. for every point stripe interprets the micro-ops on a register-resident
-//      top-of-stack jet T (+ operand jet U); deeper stack entries spill to a
-//      per-lane column in shared memory (conflict free),
+// Mapping (BASELINE.json north_star): WARPS own candidates, each LANE owns
+// collocation points (32-point stripes; two points per lane for the small Kerr
+// jets).  A warp
+//   1. stages a candidate's postfix bytecode in shared memory,
+//   2. translates it once into leaf-fused micro-ops (lane 0; evaluation order
+//      chosen per binary node so that two spill slots always suffice),
+//   3. together with the 3 other warps of its group, for every point stripe
+//      interprets the micro-ops on a register-resident top-of-stack jet T
+//      (+ operand jet U); deeper stack entries spill to a per-lane column in
+//      shared memory (conflict free),
 //   4. applies the problem's residual operator to the finished jet,
 //   5. reduces votes / maxima over the lanes with warp shuffles.
+// Design history and the ncu evidence behind every choice: profiles/README.md.
 #pragma once
 #include <stdint.h>
 #include "jet.cuh"
@@ -364,10 +367,6 @@ __device__ __forceinline__ void scalar_taylor(unsigned fn, unsigned slot, double
     }
 }
 
-#ifndef PDE_PREFETCH
-#define PDE_PREFETCH 0
-#endif
-
 // Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
 // uc: shared address of the micro-op words; sp_addr: shared address of this thread's spill column
 // (layout [(slot * NC + coef) * NP + point][thread], conflict free), moved up and down by one slot.
@@ -378,13 +377,6 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
     constexpr unsigned kSlotBytes = NC * NP * TPB * 8;
     Jet<N> U[NP];
     double f[NP][N + 1];
-#if PDE_PREFETCH == 2
-    unsigned ins = lds_u32(uc), ins_next = lds_u32(uc + 4);
-    uc += 8;
-#elif PDE_PREFETCH == 1
-    unsigned ins_next = lds_u32(uc);
-    uc += 4;
-#endif
 #define PDE_EACH for (int h = 0; h < NP; ++h)
 #define PDE_SPILL_IF_FLAGGED                                                                 \
     if (ins_cur & F_SPILL) {                                                                 \
@@ -405,16 +397,9 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
     }
 #pragma unroll 1
     for (;;) {
-#if PDE_PREFETCH == 2
-        const unsigned ins_cur = ins;
-        ins = ins_next;
-        ins_next = lds_u32(uc); uc += 4;   // two-deep prefetch
-#elif PDE_PREFETCH == 1
-        const unsigned ins_cur = ins_next;
-        ins_next = lds_u32(uc); uc += 4;
-#else
+        // no software prefetch of the next word: measured equal (135.9 / 136.0 / 136.6 ms for depth 0 / 1 / 2),
+        // and every prefetched word costs a move per dispatch
         const unsigned ins_cur = lds_u32(uc); uc += 4;
-#endif
         const unsigned kind = ins_cur & 0xffu, arg = (ins_cur >> 8) & 0xffu;
         switch (kind) {
             case U_END: return;
