@@ -694,13 +694,14 @@ validate_kernel(const ValidateParams p) {
             const long long cand = cand0 + wg;
             int status = -1;
             if (cand < p.n) {
-                const int len = p.len[cand];
+                int len = p.len[cand];
+                if (len > p.L) len = p.L + 1;          // a length beyond the row is malformed input (never read past the row)
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code + (size_t)cand * p.L);
                 uint32_t* dst = reinterpret_cast<uint32_t*>(s_code);
-                for (int i = lane; i * 4 < len; i += 32) dst[i] = __ldg(src + i);
+                for (int i = lane; i * 4 < len && i * 4 < p.L; i += 32) dst[i] = __ldg(src + i);
                 __syncwarp();
                 if (lane == 0) {
-                    status = (len == 0) ? -1 : translate(s_code, len, s_uc_mine, my + Lp, my + 2 * Lp, my + 3 * Lp, p.ns);
+                    status = (len == 0) ? -1 : (len > p.L) ? 1 : translate(s_code, len, s_uc_mine, my + Lp, my + 2 * Lp, my + 3 * Lp, p.ns);
                     s_status[wg] = status;
                 }
             } else if (lane == 0) {

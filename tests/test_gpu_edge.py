@@ -97,6 +97,11 @@ def test_programs_the_kernel_hands_to_the_cpu(cuda_device):
     assert nf[4] == 256 and nf[5] == 0 and nf[6] == 256
     assert (bits & 0b0101111) == 0b0101111                     # everything not evaluated / not countable survives
     assert ((bits >> 6) & 1) == 0                              # rho*z is rejected
+    # a length beyond the row (caller error) is reported as malformed, never read
+    len_bad = len_t.clone()
+    len_bad[6] = 200
+    outb = pb.validate(sess, prog, code_t, len_bad, pts_t, tab_t, None, spill_slots=2)
+    assert outb["n_finite"].cpu().numpy()[6] == -2
     out1 = pb.validate(sess, prog, code_t, len_t, pts_t, tab_t, None, spill_slots=1)
     nf1 = out1["n_finite"].cpu().numpy()
     assert nf1[4] == -3 and nf1[6] == 256                      # one slot is not enough for (a*b) + (c*d) of sub-trees
