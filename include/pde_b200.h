@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 1
+#define PDE_B200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define PDE_OK            0
@@ -193,7 +193,8 @@ int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][
  *   prim[n_prim][P/32][16][32]  jets of PRIM(p) leaves in 32-point stripe blocks: coefficient g of
  *                            point q at [p][q / 32][g][q % 32] (rows n_coef..15 are padding), so a
  *                            warp reads a leaf with coalesced loads at immediate offsets; may be
- *                            NULL if no program uses PRIM
+ *                            NULL (n_prim = 0) if no program uses PRIM; a program that uses PRIM(p) with
+ *                            p >= n_prim is reported as malformed (n_finite = -2), never dereferenced
  * outputs (per candidate):
  *   ratio_max   max |R|/S over finite points        resid_max  max |R|
  *   scale_at    S at the arg-max of the ratio       n_finite, n_votes
@@ -215,7 +216,7 @@ typedef struct pde_validate_out {
 
 int  pde_validate(const pde_session *s, const pde_program *p,
                   const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
-                  const double *pts_dev, const double *table_dev, const double *prim_dev, int P,
+                  const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
                   double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
                   const pde_validate_out *out, void *stream);
 
@@ -224,7 +225,7 @@ int  pde_validate(const pde_session *s, const pde_program *p,
  *   resid[n, P], scale[n, P] (may be NULL) */
 int  pde_eval_points(const pde_session *s, const pde_program *p,
                      const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
-                     const double *pts_dev, const double *table_dev, const double *prim_dev, int P,
+                     const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
                      int spill_slots,
                      double *jets_dev, double *resid_dev, double *scale_dev, void *stream);
 

@@ -72,9 +72,9 @@ _sig("pde_program_free", None, c_void_p)
 _sig("pde_program_info", c_int, c_void_p, P(c_int), P(c_int), P(c_int))
 _sig("pde_program_point_table", c_int, c_void_p, c_void_p, c_int, c_void_p)
 _sig("pde_validate", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-     c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_double, c_int, c_int, P(ValidateOut), c_void_p)
+     c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_int, c_int, P(ValidateOut), c_void_p)
 _sig("pde_eval_points", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-     c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
+     c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_fp64_peak", c_int, c_int, P(c_double), c_void_p)
 _sig("pde_fp64_peak_3op", c_int, c_int, P(c_double), c_void_p)
 

@@ -201,7 +201,7 @@ def validate(session: Session, program: ResidualProgram, code, length, pts, tabl
     vo = _lib.ValidateOut(*[_dev_ptr(out[k]) for k in
                             ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "survivor_bits")])
     check(lib.pde_validate(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
-                           _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), Pn,
+                           _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
                            float(tau), int(min_finite), float(vote_frac), int(n_ref), int(spill_slots),
                            C.byref(vo), _stream_ptr(stream)))
     return out
@@ -218,7 +218,7 @@ def eval_points(session: Session, program: ResidualProgram, code, length, pts, t
     resid = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
     scale = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
     check(lib.pde_eval_points(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
-                              _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), Pn, int(spill_slots),
+                              _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn, int(spill_slots),
                               _dev_ptr(jets), _dev_ptr(resid), _dev_ptr(scale), _stream_ptr(stream)))
     return jets, resid, scale
 

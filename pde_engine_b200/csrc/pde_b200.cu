@@ -285,7 +285,7 @@ static int check_common(const pde_session* s, const pde_program* p, const void* 
 extern "C" {
 
 int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
-                 int64_t n, int L, const double* pts, const double* tab, const double* prim, int P,
+                 int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
                  double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
                  const pde_validate_out* out, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
@@ -301,7 +301,7 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
     if (rc) return rc;
     PDE_CUDA(cudaMemsetAsync(out->survivor_bits, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
     ValidateParams vp{};
-    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.P = P;
+    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
     vp.ns = spill_slots; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
     vp.ratio_max = out->ratio_max; vp.resid_max = out->resid_max; vp.scale_at = out->scale_at;
     vp.n_finite = out->n_finite; vp.n_votes = out->n_votes; vp.ref_rs = out->ref_rs; vp.survivor_bits = out->survivor_bits;
@@ -310,7 +310,7 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
 }
 
 int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
-                    int64_t n, int L, const double* pts, const double* tab, const double* prim, int P,
+                    int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
                     int spill_slots, double* jets, double* resid, double* scale, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
     if (rc) return rc;
@@ -319,7 +319,7 @@ int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* c
     rc = upload_tables(s, st);
     if (rc) return rc;
     ValidateParams vp{};
-    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.P = P;
+    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
     vp.ns = spill_slots; vp.jets = jets; vp.resid = resid; vp.scale = scale;
     if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true>(vp, st);
     return launch_validate<PDE_PROBLEM_KERR, true>(vp, st);

@@ -77,6 +77,7 @@ struct ValidateParams {
     const double* pts;    // [2][P]
     const double* tab;    // [cols][P]
     const double* prim;   // [n_prim][P/32][16][32]: per 32-point stripe, coefficient-major, lanes contiguous
+    int n_prim;           // PRIM(p) with p >= n_prim is malformed input
     int P;
     int ns;               // spill slots per lane
     double tau;
@@ -122,12 +123,13 @@ __host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 //   pass 1: sub-tree start and spill need of every position (stack of root positions in `stk`);
 //   pass 2: emission with an explicit frame stack (position, phase) in `stk`.
 // start[], need[] and stk[] are caller-provided byte arrays of L, L and 2L bytes.
-__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* start, uint8_t* need, uint8_t* stk, int ns_max) {
+__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* start, uint8_t* need, uint8_t* stk, int ns_max, int n_prim) {
     // ---- pass 1 ----
     int sp = 0;
     for (int i = 0; i < len; ++i) {
         const unsigned b = code[i];
         if (op_is_leaf(b)) {
+            if (op_is_prim(b) && (int)(b - PDE_OP_PRIM0) >= n_prim) return 1;      // no table row behind it
             start[i] = (uint8_t)i; need[i] = 0; stk[sp++] = (uint8_t)i;
         } else if (op_is_unary(b)) {
             if (sp < 1) return 1;
@@ -701,7 +703,7 @@ validate_kernel(const ValidateParams p) {
                 for (int i = lane; i * 4 < len && i * 4 < p.L; i += 32) dst[i] = __ldg(src + i);
                 __syncwarp();
                 if (lane == 0) {
-                    status = (len == 0) ? -1 : (len > p.L) ? 1 : translate(s_code, len, s_uc_mine, my + Lp, my + 2 * Lp, my + 3 * Lp, p.ns);
+                    status = (len == 0) ? -1 : (len > p.L) ? 1 : translate(s_code, len, s_uc_mine, my + Lp, my + 2 * Lp, my + 3 * Lp, p.ns, p.n_prim);
                     s_status[wg] = status;
                 }
             } else if (lane == 0) {

@@ -97,6 +97,11 @@ def test_programs_the_kernel_hands_to_the_cpu(cuda_device):
     assert nf[4] == 256 and nf[5] == 0 and nf[6] == 256
     assert (bits & 0b0101111) == 0b0101111                     # everything not evaluated / not countable survives
     assert ((bits >> 6) & 1) == 0                              # rho*z is rejected
+    # PRIM leaves without a table row behind them are malformed input, never dereferenced
+    prim_prog = [[bc.OP_PRIM0 + 1, V0, MUL], [bc.OP_PRIM0 + 5]]
+    cp, lp = _rows(prim_prog, 48, cuda_device)
+    outp = pb.validate(sess, prog, cp, lp, pts_t, tab_t, None, spill_slots=2)
+    assert outp["n_finite"].cpu().numpy().tolist() == [-2, -2]
     # a length beyond the row (caller error) is reported as malformed, never read
     len_bad = len_t.clone()
     len_bad[6] = 200
