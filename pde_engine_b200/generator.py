@@ -45,7 +45,8 @@ def candidate_string(op: int, a: str, b: Optional[str]) -> str:
 
 class GpuExpressionGenerator:
     def __init__(self, normalizer: Any = None, problem: str = "force_free", L: int = 128,
-                 session: Optional[core.Session] = None, pre_batch_hook: Optional[Callable[[int, List[str]], None]] = None):
+                 session: Optional[core.Session] = None, pre_batch_hook: Optional[Callable[[int, List[str]], None]] = None,
+                 last_depth_filter: Any = None):
         if normalizer is None:
             raise ValueError("GpuExpressionGenerator needs the CPU normaliser (an object with normalize_batch)")
         self.normalizer = normalizer
@@ -53,6 +54,11 @@ class GpuExpressionGenerator:
         self.session = session or core.Session.for_problem(self.problem)
         self.L = L
         self.pre_batch_hook = pre_batch_hook
+        # OPT-IN, not a drop-in: a GpuBatchValidator whose filter is applied to the RAW candidates of the last
+        # depth while they are still resident on the device, so that only survivors reach the CPU normaliser
+        # (candidates of the final depth are operands of nothing).  Rows the device rejects then never reach
+        # on_batch / the run database; the default (None) keeps the reference's stream bit for bit.
+        self.last_depth_filter = last_depth_filter
         self.seen_normalized = set()
         self.stats: Dict[int, Dict[str, int]] = {}
         self.last_enumeration: Dict[int, dict] = {}
@@ -112,8 +118,23 @@ class GpuExpressionGenerator:
         expressions_by_depth: Dict[int, List[str]] = {1: primitive_strs}
         seen_signatures = set()
         for depth in range(2, max_depth + 1):
-            enum = self.enumerate_depth(expressions_by_depth, depth, prune)
+            filt = self.last_depth_filter if depth == max_depth else None
+            enum = self.enumerate_depth(expressions_by_depth, depth, prune, keep_device=filt is not None)
             n, triple, first, strs = enum["n"], enum["triple"], enum["first"], enum["strings"]
+            n_filtered = 0
+            if filt is not None and n > 0:
+                # stage 1 -> stage 2 on the device: the spliced programs are validated where they were written
+                dev = enum.pop("device")
+                enum.pop("device_first", None)
+                out = core.validate(self.session, filt.program, dev["code"], dev["len"], filt.pts, filt.table, None,
+                                    tau=filt.tau, min_finite=filt.min_finite, vote_frac=filt.vote_frac, n_ref=0,
+                                    spill_slots=filt.spill_slots)
+                bits = out["survivor_bits"].cpu().numpy().view(np.uint32)
+                k = np.arange(n)
+                surv = ((bits[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool)
+                n_filtered = int((first & ~surv).sum())
+                first = first & surv
+                del dev, out
             print(f"Depth {depth}: {n} candidates to normalize")
             unique_expressions: List[str] = []
             n_normalized = 0
@@ -139,6 +160,7 @@ class GpuExpressionGenerator:
                     on_batch(depth, out_chunk)
             expressions_by_depth[depth] = unique_expressions
             self.stats[depth] = {"candidates": n, "normalized": n_normalized, "uniques": len(unique_expressions),
-                                 "exact_duplicates_dropped_on_device": n - n_normalized}
+                                 "exact_duplicates_dropped_on_device": n - n_normalized - n_filtered,
+                                 "rejected_on_device_before_normalisation": n_filtered}
             print(f"Depth {depth}: {len(unique_expressions)} unique expressions after normalization")
         self.expressions_by_depth = expressions_by_depth

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import uniques_by_depth
+from conftest import load_golden, uniques_by_depth
 from oracle import bytecode as bc
 from oracle import enumerate as oe
 from oracle import parser as op
@@ -142,3 +142,46 @@ def test_stream_generate_drop_in(problem, cuda_device, enum_ff, enum_kerr):
     assert gen.stats[3]["exact_duplicates_dropped_on_device"] > 0
     with pytest.raises(ValueError):
         gen.stream_generate(prims, {"neg": None}, binary, max_depth=2)
+
+
+def test_opt_in_device_filter_before_the_normaliser(cuda_device, enum_ff):
+    """OPT-IN (not a drop-in): with `last_depth_filter` the raw candidates of the LAST depth are validated on
+    the device where the enumerator wrote them, and only survivors reach the CPU normaliser.  Depths below the
+    last keep the reference's stream bit for bit; at the last depth the emitted uniques are a subset of the
+    reference's that still contains every expression the reference validates as a solution."""
+    from pde_engine_b200.generator import GpuExpressionGenerator, UNARY_NAMES, BINARY_NAMES, DEAD_BINARY_NAMES
+    from pde_engine_b200.validator import GpuBatchValidator
+    g = enum_ff
+    norm = OracleNormalizer()
+    for d in ("2", "3"):
+        norm.preload(dict(zip(g["depths"][d]["candidates"], g["depths"][d]["normalized"])))
+    gv = GpuBatchValidator(None, "force_free", P=4096)
+    gen = GpuExpressionGenerator(norm, "force_free", last_depth_filter=gv)
+
+    class _Prim:
+        def __init__(self, s):
+            self.s = s
+
+        def __str__(self):
+            return self.s
+
+    calls = []
+    gen.stream_generate([_Prim(s) for s in g["primitives"]], {k: None for k in UNARY_NAMES},
+                        {k: None for k in BINARY_NAMES + DEAD_BINARY_NAMES}, max_depth=3, batch_size=2000,
+                        on_batch=lambda d, xs: calls.append((d, list(xs))), prune=True)
+    got = {d: [s for dd, xs in calls if dd == d for s in xs] for d in (1, 2, 3)}
+    assert got[1] == g["depths"]["1"]["uniques"] and got[2] == g["depths"]["2"]["uniques"]      # untouched below the last depth
+    ref3 = g["depths"]["3"]["uniques"]
+    assert set(got[3]) <= set(ref3) and len(got[3]) < 0.5 * len(ref3)
+    # (the order can differ slightly from the reference's: a unique is emitted at its first SURVIVING candidate form,
+    # and an equivalent form may survive as "undecided" where the first form was rejected)
+    pos = {s: i for i, s in enumerate(ref3)}
+    st = gen.stats[3]
+    assert st["rejected_on_device_before_normalisation"] > 0.5 * st["candidates"]
+    assert st["normalized"] + st["rejected_on_device_before_normalisation"] + st["exact_duplicates_dropped_on_device"] == st["candidates"]
+    # every depth-3 expression the unmodified reference validated as a solution is still emitted
+    ver = load_golden("verdicts_force_free_d3.json")["records"]
+    valid3 = [r["s"] for r in ver if r["is_valid"] and r["s"] in pos]
+    assert len(valid3) > 20
+    missing = [s for s in valid3 if s not in set(got[3])]
+    assert not missing, missing
