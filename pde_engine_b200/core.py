@@ -95,14 +95,14 @@ class ExprSet:
     def __init__(self, session: Session, strs: Sequence[str]):
         self.session = session
         self.n = len(strs)
-        # one NUL-separated blob + offsets: building a ctypes array of 10^5 char pointers costs more
-        # than compiling them
+        # one NUL-separated blob + the offsets of the strings in it (found with two vectorised numpy passes):
+        # building a ctypes array of 10^5 char pointers costs more than compiling the strings
         blob = ("\0".join(strs) + "\0").encode() if self.n else b"\0"
-        lens = np.fromiter(map(len, strs), dtype=np.int64, count=self.n)
-        if self.n and len(blob) != int(lens.sum()) + self.n:          # non-ASCII input: byte lengths differ
-            lens = np.fromiter((len(s.encode()) for s in strs), dtype=np.int64, count=self.n)
+        ends = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0) if self.n else np.zeros(0, np.int64)
+        if len(ends) != self.n:
+            raise ValueError("expression strings must not contain NUL")
         off = np.zeros(self.n + 1, dtype=np.uint32)
-        np.cumsum(lens + 1, out=off[1:])
+        off[1:] = ends + 1
         h = C.c_void_p()
         check(lib.pde_compile_exprs_packed(session._h, blob, _np_ptr(off), self.n, C.byref(h)))
         self._h = h

@@ -16,12 +16,14 @@
 // tests/test_compiler.py checks the output byte-for-byte against
 // oracle/parser.py (which uses Python's own `ast`).
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <memory>
 #include <numeric>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -49,6 +51,16 @@ static i64 gcd64(i64 a, i64 b) {
 static Rat make_rat(__int128 n, __int128 d) {
     if (d == 0) throw Unsupported();
     if (d < 0) { n = -n; d = -d; }
+    if (d == 1 && n <= LIMIT && n >= -LIMIT) { Rat r; r.n = (i64)n; r.d = 1; return r; }      // integers: the common case
+    if (n < ((__int128)1 << 62) && n > -((__int128)1 << 62) && d < ((__int128)1 << 62)) {      // 64-bit gcd (128-bit % is a library call)
+        i64 a = (i64)(n < 0 ? -n : n), b = (i64)d;
+        while (b) { const i64 t = a % b; a = b; b = t; }
+        if (a == 0) a = 1;
+        const i64 nn = (i64)n / a, dd = (i64)d / a;
+        if (nn > LIMIT || nn < -LIMIT || dd > LIMIT) throw Unsupported();
+        Rat r; r.n = nn; r.d = dd;
+        return r;
+    }
     // reduce with 128-bit gcd
     __int128 a = n < 0 ? -n : n, b = d;
     while (b) { __int128 t = a % b; a = b; b = t; }
@@ -412,6 +424,9 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     e->term_off.push_back(0);
     e->str_off.assign(off, off + n + (n > 0 ? 1 : 0));
     if (n > 0) e->str_blob.assign(blob, blob + off[n]);
+    const bool prof = getenv("PDE_B200_PROFILE") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_a = tnow();
     // ---- phase A (parallel): parse + emit with deferred table slots ----
     int nthreads = 1;
     if (const char* ev = getenv("PDE_B200_COMPILE_THREADS")) nthreads = atoi(ev);
@@ -428,6 +443,7 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
         for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] { workers[t].run(blob, off, s); });
         for (auto& x : th) x.join();
     }
+    auto t_b = tnow();
     // ---- phase B (sequential, in expression order): table slots, pool assembly ----
     size_t total_pool = 0, total_terms = 0;
     for (auto& w : workers) { total_pool += w.pool.size(); total_terms += w.term_sign.size(); }
@@ -468,6 +484,11 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
         }
     }
     e->term_begin[n] = (uint32_t)e->term_sign.size();
+    if (prof) {
+        auto t_c = tnow();
+        fprintf(stderr, "[pde_compile] n=%d threads=%d parse %.2f ms, slots+assembly %.2f ms\n", n, nthreads,
+                std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count());
+    }
     *out = e.release();
     return PDE_OK;
 }

@@ -84,22 +84,52 @@ class GpuBatchValidator:
                 setattr(self, name, getattr(cpu_validator, name))
 
     # ---- batch path --------------------------------------------------------
+    PIPELINE_CHUNK = 262144     # strings per chunk for very large batches (a multiple of 32); bounds host memory
+
     def prefilter(self, expr_strs: Sequence[str]) -> BatchVerdict:
-        """GPU filter for a batch of expression strings (normalised uniques)."""
+        """GPU filter for a batch of expression strings (normalised uniques).
+
+        Very large batches go in chunks: the host compiler (multi-threaded C++, the GIL is released) works on
+        chunk k + 1 while the device validates chunk k -- launches are asynchronous and every chunk writes its own
+        slice of the output buffers (chunks are multiples of 32 so survivor words never straddle two of them).
+        For the 143 461 depth-4 uniques one shot is faster (measured 50.8 vs 53.9 ms with 32 k chunks: smaller
+        chunks parse on fewer threads and fill the device less evenly), so chunking only bounds memory."""
         import torch
-        exprs = self.session.compile(list(expr_strs))
-        code, ln = exprs.programs(self.L)
-        flags = exprs.flags()
-        code_t = torch.from_numpy(code).to(self.device, non_blocking=True)
-        len_t = torch.from_numpy(ln).to(self.device, non_blocking=True)
-        out = core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
-                            tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac,
-                            n_ref=3, spill_slots=self.spill_slots)
-        host = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
-        bv = BatchVerdict(expr_strs, flags, host)
-        self.stats["gpu_evaluated"] += len(bv.strs)
+        strs = list(expr_strs)
+        n = len(strs)
+        dev = self.device
+        out = {
+            "ratio_max": torch.empty(n, dtype=torch.float64, device=dev),
+            "resid_max": torch.empty(n, dtype=torch.float64, device=dev),
+            "scale_at": torch.empty(n, dtype=torch.float64, device=dev),
+            "n_finite": torch.empty(n, dtype=torch.int32, device=dev),
+            "n_votes": torch.empty(n, dtype=torch.int32, device=dev),
+            "ref_rs": torch.empty((n, 3, 2), dtype=torch.float64, device=dev),
+            "survivor_bits": torch.empty((n + 31) // 32, dtype=torch.int32, device=dev),
+        }
+        flags = np.zeros(n, np.uint8)
+        n_uncompiled = 0
+        step = self.PIPELINE_CHUNK if n > 2 * self.PIPELINE_CHUNK else max(n, 1)
+        keep = []                          # host/device buffers of chunks in flight stay alive until the final sync
+        for lo in range(0, n, step):
+            hi = min(lo + step, n)
+            exprs = self.session.compile(strs[lo:hi])
+            code, ln = exprs.programs(self.L)
+            flags[lo:hi] = exprs.flags()
+            n_uncompiled += int((ln == 0).sum())
+            code_t = torch.from_numpy(code).to(dev, non_blocking=True)
+            len_t = torch.from_numpy(ln).to(dev, non_blocking=True)
+            part = {k: (v[lo // 32:(hi + 31) // 32] if k == "survivor_bits" else v[lo:hi]) for k, v in out.items()}
+            core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
+                          tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac,
+                          n_ref=3, spill_slots=self.spill_slots, out=part)
+            keep.append((code, ln, code_t, len_t))
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        del keep
+        bv = BatchVerdict(strs, flags, host)
+        self.stats["gpu_evaluated"] += n
         self.stats["gpu_rejected"] += int(bv.rejected.sum())
-        self.stats["not_compilable"] += int((ln == 0).sum())
+        self.stats["not_compilable"] += n_uncompiled
         return bv
 
     def prefetch(self, depth: int, expr_strs: Sequence[str]) -> None:
