@@ -315,7 +315,7 @@ def run_ours(args):
         # (1) the public API path: GpuBatchValidator.prefilter = host compile pipelined with the device (chunks)
         from pde_engine_b200.validator import GpuBatchValidator
         gv4 = GpuBatchValidator(None, "force_free", P=P, device=dev)
-        gv4.prefilter(mine[:256])
+        gv4.prefilter(mine)          # warm-up at full size: the validator's pinned staging buffers are grown once and reused
         barrier()
         tp0 = time.perf_counter()
         bv4 = gv4.prefilter(mine)

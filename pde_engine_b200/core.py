@@ -133,9 +133,14 @@ class ExprSet:
         check(lib.pde_exprset_export(self._h, _np_ptr(f), None, None, None, None, None, None))
         return f
 
-    def programs(self, L: int) -> Tuple[np.ndarray, np.ndarray]:
-        code = np.zeros((self.n, L), np.uint8)
-        ln = np.zeros(self.n, np.uint8)
+    def programs(self, L: int, out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Whole programs as a zero-padded [n, L] array + lengths; `out` = caller-provided (e.g. pinned) buffers."""
+        if out is None:
+            code = np.empty((self.n, L), np.uint8)       # the library zero-fills
+            ln = np.empty(self.n, np.uint8)
+        else:
+            code, ln = out
+            assert code.shape == (self.n, L) and ln.shape == (self.n,) and code.flags.c_contiguous
         check(lib.pde_exprset_programs(self._h, L, _np_ptr(code), _np_ptr(ln)))
         return code, ln
 

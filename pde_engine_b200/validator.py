@@ -20,6 +20,7 @@ reference-valid row.
 from __future__ import annotations
 
 import json
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -76,6 +77,7 @@ class GpuBatchValidator:
         self.pts = torch.from_numpy(pts).to(self.device)
         self.table = torch.from_numpy(self.program.point_table(pts)).to(self.device)
         self._cache: Dict[str, Tuple[bool, dict, Optional[float]]] = {}
+        self._pin = None
         self._last_evidence: dict = {}
         self.stats = {"gpu_evaluated": 0, "gpu_rejected": 0, "cpu_confirmed": 0, "not_compilable": 0}
         # forwarded attributes the engine reads (GM:2071-2074)
@@ -85,6 +87,7 @@ class GpuBatchValidator:
 
     # ---- batch path --------------------------------------------------------
     PIPELINE_CHUNK = 262144     # strings per chunk for very large batches (a multiple of 32); bounds host memory
+    SPLIT_MIN = 65536           # from this size on a batch is processed in 3 parts (compile / validate overlap)
 
     def prefilter(self, expr_strs: Sequence[str]) -> BatchVerdict:
         """GPU filter for a batch of expression strings (normalised uniques).
@@ -92,8 +95,8 @@ class GpuBatchValidator:
         Very large batches go in chunks: the host compiler (multi-threaded C++, the GIL is released) works on
         chunk k + 1 while the device validates chunk k -- launches are asynchronous and every chunk writes its own
         slice of the output buffers (chunks are multiples of 32 so survivor words never straddle two of them).
-        For the 143 461 depth-4 uniques one shot is faster (measured 50.8 vs 53.9 ms with 32 k chunks: smaller
-        chunks parse on fewer threads and fill the device less evenly), so chunking only bounds memory."""
+        Few, large parts: 32 k chunks were slower than one shot (smaller chunks parse on fewer threads and fill the
+        device less evenly)."""
         import torch
         strs = list(expr_strs)
         n = len(strs)
@@ -109,23 +112,47 @@ class GpuBatchValidator:
         }
         flags = np.zeros(n, np.uint8)
         n_uncompiled = 0
-        step = self.PIPELINE_CHUNK if n > 2 * self.PIPELINE_CHUNK else max(n, 1)
-        keep = []                          # host/device buffers of chunks in flight stay alive until the final sync
+        # a few parts for large batches (part k + 1 is compiled while the device validates part k),
+        # fixed-size chunks only for very large ones
+        if n > 2 * self.PIPELINE_CHUNK:
+            step = self.PIPELINE_CHUNK
+        elif n >= self.SPLIT_MIN:
+            parts = int(os.environ.get("PDE_B200_SPLIT", "3"))     # measured on the 143 461 depth-4 uniques: 47 / 42 / 53 ms for 2 / 3 / 4 parts, 52 unsplit
+            step = ((n + parts - 1) // parts + 31) // 32 * 32
+        else:
+            step = max(n, 1)
+        copied = None                      # event: the previous chunk's H2D copies have left the staging buffers
+        # pinned staging buffers, grown on demand and reused: pageable copies of the 18 MB of programs and the
+        # 12 MB of results cost several milliseconds each way
+        cap = min(step, max(n, 1))
+        if self._pin is None or self._pin["code"].shape[0] < cap or self._pin["out_n"] < n:
+            self._pin = {"code": torch.empty((cap, self.L), dtype=torch.uint8).pin_memory(),
+                         "len": torch.empty(cap, dtype=torch.uint8).pin_memory(),
+                         "host": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}, "out_n": n}
         for lo in range(0, n, step):
             hi = min(lo + step, n)
             exprs = self.session.compile(strs[lo:hi])
-            code, ln = exprs.programs(self.L)
+            code_h, len_h = self._pin["code"][:hi - lo], self._pin["len"][:hi - lo]
+            if copied is not None:
+                copied.synchronize()       # (not the kernel: only the copies out of the staging buffers)
+            exprs.programs(self.L, out=(code_h.numpy(), len_h.numpy()))
             flags[lo:hi] = exprs.flags()
-            n_uncompiled += int((ln == 0).sum())
-            code_t = torch.from_numpy(code).to(dev, non_blocking=True)
-            len_t = torch.from_numpy(ln).to(dev, non_blocking=True)
+            n_uncompiled += int((len_h == 0).sum())
+            code_t = code_h.to(dev, non_blocking=True)
+            len_t = len_h.to(dev, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record()
             part = {k: (v[lo // 32:(hi + 31) // 32] if k == "survivor_bits" else v[lo:hi]) for k, v in out.items()}
             core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
                           tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac,
                           n_ref=3, spill_slots=self.spill_slots, out=part)
-            keep.append((code, ln, code_t, len_t))
-        host = {k: v.cpu().numpy() for k, v in out.items()}
-        del keep
+        host = {}
+        for k, v in out.items():
+            h = self._pin["host"][k][:v.shape[0]]
+            h.copy_(v, non_blocking=True)
+            host[k] = h
+        torch.cuda.current_stream().synchronize()
+        host = {k: v.numpy().copy() for k, v in host.items()}      # the staging buffers are reused by the next call
         bv = BatchVerdict(strs, flags, host)
         self.stats["gpu_evaluated"] += n
         self.stats["gpu_rejected"] += int(bv.rejected.sum())
