@@ -672,6 +672,94 @@ template <int N, int NP>
 __device__ __forceinline__ void jetv_compose(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
     jetv_compose_level<N, NP, N - 1>(t, a, f);
 }
+// Paterson-Stockmeyer form of the same composition:  F = f_0 + f_1 d + d^2 (f_2 + f_3 d + f_4 d^2),  d = t - t_0:
+// TWO truncated jet products (d^2 with its symmetry, then d^2 * G) instead of Horner's three nested ones, and the
+// scalar-times-jet parts share their scalar between consecutive multiply-adds:  23 + 8 + 35 + 14 = 80 multiply-adds
+// for N = 4 (Horner 91), about 50 of them with three different register pairs (Horner 61).  In place on t;
+// `a` holds d^2 (degrees 2..N) and, in its degree-1 slots, the degree-1 part of G.   Valid for N <= 4.
+template <int N, int NP>
+__device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
+    static_assert(N <= 4, "G = f_2 + f_3 d + f_4 d^2 covers N <= 4");
+    // ---- d^2, degrees 2..N: unordered pairs once, doubled, plus the square of the middle term ----
+#pragma unroll
+    for (int n = 2; n <= N; ++n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj;
+            double acc[NP], sq[NP];
+            int cnt = 0;
+            bool has_sq = false;
+#pragma unroll
+            PDE_H { acc[h] = 0.0; sq[h] = 0.0; }
+#pragma unroll
+            for (int bi = 0; bi <= gi; ++bi) {
+#pragma unroll
+                for (int bj = 0; bj <= gj; ++bj) {
+                    const int ci = gi - bi, cj = gj - bj;
+                    if ((bi == 0 && bj == 0) || (ci == 0 && cj == 0)) continue;
+                    const int ib = jidx(bi, bj), ic = jidx(ci, cj);
+                    if (ib > ic) continue;
+                    if (ib == ic) {
+                        has_sq = true;
+#pragma unroll
+                        PDE_H sq[h] = t[h].c[ib] * t[h].c[ib];
+                    } else if (cnt++ == 0) {
+#pragma unroll
+                        PDE_H acc[h] = t[h].c[ib] * t[h].c[ic];
+                    } else {
+#pragma unroll
+                        PDE_H acc[h] = fma(t[h].c[ib], t[h].c[ic], acc[h]);
+                    }
+                }
+            }
+#pragma unroll
+            PDE_H a[h].c[jidx(gi, gj)] = cnt == 0 ? sq[h] : has_sq ? fma(2.0, acc[h], sq[h]) : acc[h] + acc[h];
+        }
+    }
+    // ---- G = f_2 + f_3 d + f_4 d^2, truncated at degree N - 2: g1 (degree 1) in a.c[1..2], g2 (degree 2) in locals ----
+    double g2[NP][3];
+    if (N >= 3) {
+#pragma unroll
+        PDE_H { a[h].c[1] = f[h][3] * t[h].c[1]; a[h].c[2] = f[h][3] * t[h].c[2]; }
+    }
+    if (N >= 4) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            PDE_H g2[h][k] = fma(f[h][4], a[h].c[3 + k], f[h][3] * t[h].c[3 + k]);
+        }
+    }
+    // ---- t_g = f_1 t_g + sum_{|b| >= 2} d2_b G_{g-b}  (descending degree; G_0 = f_2) ----
+#pragma unroll
+    for (int n = N; n >= 2; --n) {
+#pragma unroll
+        for (int gj = 0; gj <= n; ++gj) {
+            const int gi = n - gj, g = jidx(gi, gj);
+            double acc[NP];
+#pragma unroll
+            PDE_H acc[h] = fma(f[h][2], a[h].c[g], f[h][1] * t[h].c[g]);
+#pragma unroll
+            for (int ci = 0; ci <= gi; ++ci) {
+#pragma unroll
+                for (int cj = 0; cj <= gj; ++cj) {
+                    const int m = ci + cj;                 // degree of the G factor
+                    if (m == 0 || m > N - 2 || n - m < 2) continue;
+                    const int ib = jidx(gi - ci, gj - cj);
+#pragma unroll
+                    PDE_H acc[h] = fma(a[h].c[ib], m == 1 ? a[h].c[jidx(ci, cj)] : g2[h][cj], acc[h]);
+                }
+            }
+#pragma unroll
+            PDE_H t[h].c[g] = acc[h];
+        }
+    }
+#pragma unroll
+    PDE_H {
+        if (N >= 1) { t[h].c[1] *= f[h][1]; t[h].c[2] *= f[h][1]; }
+        t[h].c[0] = f[h][0];
+    }
+}
+
 #undef PDE_H
 
 __host__ __device__ __forceinline__ constexpr double factorial(int n) {

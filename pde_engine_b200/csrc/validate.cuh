@@ -23,6 +23,10 @@
 #include "residual_ff_gen.cuh"
 #include "../../include/pde_b200.h"
 
+#ifndef PDE_COMPOSE_PS
+#define PDE_COMPOSE_PS 1      // 1: Paterson-Stockmeyer body (80 multiply-adds), 0: Horner body (91); measured 136.1 vs 138.3 ms
+#endif
+
 namespace pde {
 
 constexpr int kMaxL = 256;
@@ -574,7 +578,11 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
 #pragma unroll
                 PDE_EACH scalar_taylor<N>(FN_POW, arg, T[h].c[0], f[h]);
             l_compose:
+#if PDE_COMPOSE_PS
+                jetv_compose_ps<N, NP>(T, U, f);
+#else
                 jetv_compose<N, NP>(T, U, f);
+#endif
                 break;
             default: __builtin_unreachable();
         }
