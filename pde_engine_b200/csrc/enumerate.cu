@@ -530,7 +530,14 @@ static unsigned* g_dedup_vals = nullptr;
 static unsigned long long* g_dedup_cnt = nullptr;
 static unsigned g_dedup_cap = 0;
 
+// the scratch buffers belong to the device that was current when they were allocated: a process that switches
+// devices (one process per GPU is the normal deployment) gets fresh ones
+static int g_scratch_dev = -1, g_dedup_dev = -1;
+static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+
 static int ensure_scratch(long long nblocks) {
+    const int dev = current_device();
+    if (dev != g_scratch_dev) { g_sums = nullptr; g_in_tile = nullptr; g_tile = nullptr; g_total = nullptr; g_cap = 0; g_scratch_dev = dev; }
     if (nblocks <= g_cap) return PDE_OK;
     cudaFree(g_sums); cudaFree(g_in_tile); cudaFree(g_tile); cudaFree(g_total);
     g_sums = nullptr; g_in_tile = nullptr; g_tile = nullptr; g_total = nullptr; g_cap = 0;
@@ -611,6 +618,7 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     while ((long long)cap < 2 * n) cap <<= 1;
     // grow-only scratch table, kept across calls (allocating and freeing 400 MB per call cost 8-70 ms
     // around 1.7 ms of kernels)
+    if (current_device() != g_dedup_dev) { g_dedup_keys = nullptr; g_dedup_vals = nullptr; g_dedup_cnt = nullptr; g_dedup_cap = 0; g_dedup_dev = current_device(); }
     if (cap > g_dedup_cap) {
         cudaFree(g_dedup_keys); cudaFree(g_dedup_vals); cudaFree(g_dedup_cnt);
         g_dedup_keys = nullptr; g_dedup_vals = nullptr; g_dedup_cnt = nullptr; g_dedup_cap = 0;
