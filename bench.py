@@ -392,6 +392,28 @@ def run_ours(args):
         except Exception as e:
             kerr3 = {"error": repr(e)[:200]}
 
+    # ---- function fingerprints of the depth-4 uniques and of the survivors ----
+    fp_info = None
+    if rank == 0 and world == 1 and isinstance(depth4, dict) and "error" not in depth4:
+        try:
+            import numpy as np
+            from pde_engine_b200.fingerprint import GpuFingerprinter
+            fpr = GpuFingerprinter("force_free", P=64, device=dev)
+            fpr.fingerprint(uniq4[:256])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            f4 = fpr.fingerprint(uniq4)
+            t1 = time.perf_counter()
+            surv = np.asarray(bv4.survivor, bool)
+            ks = f4.key[surv]
+            fp_info = {"rows": len(uniq4), "points": 64, "mantissa_bits": 26, "wall_ms_host_strings_to_keys": (t1 - t0) * 1e3,
+                       "functions": int(len(np.unique(f4.key[f4.key != 0]))), "unknown": int((f4.key == 0).sum()),
+                       "survivors": int(surv.sum()), "survivor_functions": int(len(np.unique(ks[ks != 0]))),
+                       "survivor_unknown": int((ks == 0).sum()),
+                       "note": "opt-in (run_discovery share_confirmations): the CPU confirms one representative per survivor function"}
+        except Exception as e:
+            fp_info = {"error": repr(e)[:200]}
+
     # ---- stage 1 (HBM bound): depth-5 enumeration from the depth 1-4 unique sets ----
     enum_info = None
     if rank == 0 and world == 1 and isinstance(depth4, dict) and "error" not in depth4:
@@ -489,6 +511,7 @@ def run_ours(args):
             "evaluated_fraction": float((nf >= 0).float().mean().item()),
             "depth4_validation": depth4,
             "kerr_depth3_validation": kerr3,
+            "function_fingerprints_depth4": fp_info,
             "enumerator": enum_info,
         }
         if not args.no_cpu_baseline and world == 1:

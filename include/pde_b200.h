@@ -229,6 +229,28 @@ int  pde_eval_points(const pde_session *s, const pde_program *p,
                      int spill_slots,
                      double *jets_dev, double *resid_dev, double *scale_dev, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Function fingerprints: a numeric pre-bucketing for the
+ * DB-normalisation step of emit_to_db (GM:1256-1286), which runs SymPy
+ * simplify(expand(.)) on every row only to have UNIQUE(normalized) (GM:1407)
+ * drop rows that denote a function already stored.
+ *   values[n, P]   u(x_k) at the P points (device; written by the call, kept
+ *                  as evidence / for an exact re-check by the caller)
+ *   key[n]         64-bit key of the values rounded to `mantissa_bits` (8..51)
+ *                  bits: equal functions -> equal keys up to round-off at a
+ *                  rounding boundary (a split bucket costs one redundant CPU
+ *                  simplify; different functions do not merge unless they agree
+ *                  to 2^-mantissa_bits at all P points); 0 = no finite value
+ *                  (not evaluated / non-finite everywhere): leave to the CPU
+ *   n_finite[n]    points with a finite value (0 is the device analogue of
+ *                  _has_degenerate_denominator, GM:134-199: a suspect, never a verdict)
+ * ---------------------------------------------------------------------- */
+int  pde_fingerprint(const pde_session *s,
+                     const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
+                     const double *pts_dev, const double *prim_dev, int n_prim, int P,
+                     int spill_slots, int mantissa_bits,
+                     double *values_dev, uint64_t *key_dev, int32_t *n_finite_dev, void *stream);
+
 /* number of kernels launched by this library since load (bench "gpu_launches") */
 int64_t pde_launch_count(void);
 

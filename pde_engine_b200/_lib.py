@@ -75,6 +75,8 @@ _sig("pde_validate", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_i
      c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_int, c_int, P(ValidateOut), c_void_p)
 _sig("pde_eval_points", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("pde_fingerprint", c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
+     c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_fp64_peak", c_int, c_int, P(c_double), c_void_p)
 _sig("pde_fp64_peak_3op", c_int, c_int, P(c_double), c_void_p)
 
@@ -84,7 +86,7 @@ EXPORTED = [
     "pde_compile_exprs", "pde_compile_exprs_packed", "pde_exprset_free", "pde_exprset_size", "pde_exprset_export", "pde_exprset_programs",
     "pde_enumerate_count", "pde_enumerate", "pde_dedup", "pde_synth_trees",
     "pde_compile_residual", "pde_program_free", "pde_program_info", "pde_program_point_table",
-    "pde_validate", "pde_eval_points", "pde_fp64_peak", "pde_fp64_peak_3op",
+    "pde_validate", "pde_eval_points", "pde_fingerprint", "pde_fp64_peak", "pde_fp64_peak_3op",
 ]
 
 

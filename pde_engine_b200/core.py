@@ -228,6 +228,23 @@ def eval_points(session: Session, program: ResidualProgram, code, length, pts, t
     return jets, resid, scale
 
 
+def fingerprint(session: Session, code, length, pts, prim=None, *, mantissa_bits: int = 26, spill_slots: int = 4,
+                stream=None):
+    """Function fingerprints (pde_fingerprint): values [n, P] f64, key [n] int64 (bit pattern of the uint64 key;
+    0 = no finite value), n_finite [n] int32 -- CUDA tensors."""
+    import torch
+    n, L = code.shape
+    Pn = pts.shape[1]
+    dev = code.device
+    values = torch.empty((n, Pn), dtype=torch.float64, device=dev)
+    key = torch.empty(n, dtype=torch.int64, device=dev)
+    n_finite = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.pde_fingerprint(session._h, _dev_ptr(code), _dev_ptr(length), n, L, _dev_ptr(pts), _dev_ptr(prim),
+                              (0 if prim is None else int(prim.shape[0])), Pn, int(spill_slots), int(mantissa_bits),
+                              _dev_ptr(values), _dev_ptr(key), _dev_ptr(n_finite), _stream_ptr(stream)))
+    return values, key, n_finite
+
+
 def enumerate_count(exprs: ExprSet, depth_begin: Sequence[int], depth: int, prune: bool = True, stream=None) -> int:
     db = (C.c_int32 * len(depth_begin))(*[int(x) for x in depth_begin])
     n = C.c_int64()

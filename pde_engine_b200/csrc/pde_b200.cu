@@ -71,6 +71,51 @@ __global__ void __launch_bounds__(256) fp64_peak3_kernel(double* out, int iters,
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + b;
 }
 
+// ---- function fingerprints ----
+// One warp per candidate: every value u(x_k) is rounded to (52 - drop_bits) mantissa bits (round half up on the
+// magnitude; -0 -> +0), salted with its point index and summed -- an order-independent 64-bit key, so
+// candidates that denote the same function get the same key unless a value sits within round-off of a
+// rounding boundary (probability ~ 2^-drop_bits-ish per value; a split bucket only costs a redundant
+// CPU simplify, it never merges different functions).  Non-finite values hash as one NaN pattern.
+__device__ __forceinline__ unsigned long long fp_mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+fingerprint_kernel(const double* __restrict__ values, long long n, int P, int drop_bits,
+                   unsigned long long* __restrict__ key, int* __restrict__ n_finite) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long cand = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cand < n; cand += warps) {
+        unsigned long long h = 0;
+        int nf = 0;
+        for (int k = lane; k < P; k += 32) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(values[(size_t)cand * P + k]);
+            const unsigned long long mag = b & 0x7fffffffffffffffULL;
+            unsigned long long q = 0x7ff8000000000000ULL;
+            if (mag < 0x7ff0000000000000ULL) {
+                ++nf;
+                q = ((mag + (1ULL << (drop_bits - 1))) >> drop_bits) << drop_bits;
+                if (q) q |= b & 0x8000000000000000ULL;
+            }
+            h += fp_mix64(q ^ (0x9E3779B97F4A7C15ULL * (unsigned long long)(k + 1)));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            h += __shfl_xor_sync(0xffffffffu, h, off);
+            nf += __shfl_xor_sync(0xffffffffu, nf, off);
+        }
+        if (lane == 0) {
+            unsigned long long k64 = fp_mix64(h);
+            key[cand] = nf ? (k64 ? k64 : 1ULL) : 0ULL;      // 0 = no finite value: unknown, leave to the CPU
+            n_finite[cand] = nf;
+        }
+    }
+}
+
 }  // namespace pde
 
 using namespace pde;
@@ -323,6 +368,38 @@ int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* c
     vp.ns = spill_slots; vp.jets = jets; vp.resid = resid; vp.scale = scale;
     if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true>(vp, st);
     return launch_validate<PDE_PROBLEM_KERR, true>(vp, st);
+}
+
+int pde_fingerprint(const pde_session* s, const uint8_t* code, const uint8_t* len, int64_t n, int L,
+                    const double* pts, const double* prim, int n_prim, int P, int spill_slots, int mantissa_bits,
+                    double* values, uint64_t* key, int32_t* n_finite, void* stream) {
+    static const pde_program dummy{};
+    int rc = check_common(s, &dummy, code, len, n, L, pts, pts, P, spill_slots);
+    if (rc) return rc;
+    if (n == 0) return PDE_OK;
+    if (!values || !key || !n_finite) { set_error("pde_fingerprint: null output"); return PDE_E_INVALID; }
+    if (mantissa_bits < 8 || mantissa_bits > 51) { set_error("mantissa_bits must be in 8..51"); return PDE_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = upload_tables(s, st);
+    if (rc) return rc;
+    // programs that are not evaluated (empty / malformed / too many spills) leave NaN rows -> key 0
+    PDE_CUDA(cudaMemsetAsync(values, 0xff, sizeof(double) * (size_t)n * P, st));
+    ValidateParams vp{};
+    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = pts; vp.prim = prim;
+    vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
+    vp.ns = spill_slots; vp.resid = values;
+    rc = launch_validate<kProblemValue, true>(vp, st);
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    PDE_CUDA(cudaGetDevice(&dev));
+    PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = (n + 7) / 8;
+    const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    fingerprint_kernel<<<grid, 256, 0, st>>>(values, n, P, 52 - mantissa_bits,
+                                             reinterpret_cast<unsigned long long*>(key), n_finite);
+    count_launch();
+    PDE_CUDA(cudaGetLastError());
+    return PDE_OK;
 }
 
 static int fp64_peak_impl(bool three_operands, int iters, double* tflops, void* stream) {

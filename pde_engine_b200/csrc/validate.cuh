@@ -643,6 +643,19 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
     }
 };
 
+// Not a PDE: the value of u itself (order-2 jets are the cheapest instantiated interpreter).  Used by
+// pde_fingerprint to bucket candidates by the FUNCTION they denote (GM:1256-1286).
+constexpr int kProblemValue = 2;
+template <> struct Residual<kProblemValue> {
+    static constexpr int N = 2;
+    static constexpr int COLS = 1;
+    __device__ static __forceinline__ void fetch(const double*, int, int, double (&c)[1]) { c[0] = 0.0; }
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&)[1], double& R, double& S) {
+        R = u.c[0];
+        S = fabs(u.c[1]) + fabs(u.c[2]);
+    }
+};
+
 // ---------------------------------------------------------------------------------
 // Work decomposition.  Warps own candidates, lanes own collocation points.  A CTA is G groups
 // of 4 warps -- one warp of a group on each of the SM's four schedulers (warp id mod 4).  A group

@@ -64,7 +64,8 @@ CREATE TABLE IF NOT EXISTS {table} (
 def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Optional[str] = None,
                   run_id: str = "gpu_run", db_normalize: Optional[Callable[[str], str]] = None,
                   is_degenerate: Optional[Callable[[Any], bool]] = None, batch_size: int = 2000,
-                  match_known: bool = True, confirm_pool: Any = None) -> Dict[str, Any]:
+                  match_known: bool = True, confirm_pool: Any = None,
+                  share_confirmations: Any = None) -> Dict[str, Any]:
     """Enumerate to ``max_depth`` and validate every unique (GM:1251-1411 semantics).
 
     spec          ProblemSpec whose ``validator`` is a GpuBatchValidator
@@ -76,6 +77,12 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
     confirm_pool  a ``confirm.ConfirmationPool``: the survivors of each chunk are confirmed by its CPU
                   worker processes (most plausible first, wall cap per candidate) instead of inline;
                   rows that hit the cap get ``is_valid = None`` / status ``'timeout'``
+    share_confirmations  opt-in, with ``confirm_pool``: a ``fingerprint.GpuFingerprinter``.  Survivors that
+                  denote the same FUNCTION (equal device fingerprints) are confirmed once --
+                  by their shortest string -- and the verdict is copied to the others, with the
+                  representative named in ``validator_evidence``.  Every row is still stored; the reference
+                  confirms each string on its own, so this is a deviation wherever SymPy decides two forms
+                  of one function differently
     Returns {'rows': [...], 'stats': {...}}; rows carry the run-DB columns.
     """
     import sympy as sp
@@ -100,6 +107,9 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
                 known[sp.sympify(s, locals=locs)] = name
             except Exception:
                 pass
+
+    confirmed_functions: Dict[int, tuple] = {}     # fingerprint key -> (representative string, is_valid, reason, paper)
+    stats_extra = {"confirmations_shared": 0}
 
     def insert(row: dict) -> None:
         rows.append(row)
@@ -161,11 +171,44 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
             # most plausible first: smallest residual ratio, unevaluated candidates last
             todo = [k for k, r in enumerate(pending) if r["wait"]]
             todo.sort(key=lambda k: (pending[k]["evidence"].get("n_finite", 0) <= 0, pending[k]["evidence"].get("ratio_max", 0.0)))
-            verdicts = confirm_pool.confirm([pending[k]["expression"] for k in todo])
-            for k, (ok, reason, paper) in zip(todo, verdicts):
-                pending[k].update(is_valid=ok, validation_reason=reason, paper=paper,
-                                  evidence={"gpu": pending[k]["evidence"], "confirmed_by": "confirm.ConfirmationPool"})
-                gv.stats["cpu_confirmed"] += 1
+            shared_from: Dict[int, str] = {}
+            verdicts: Dict[int, tuple] = {}
+            reps: List[tuple] = []
+            ask = todo
+            if share_confirmations is not None and todo:
+                keys = share_confirmations.fingerprint([pending[k]["expression"] for k in todo]).key.tolist()
+                groups: Dict[int, List[int]] = {}
+                for k, key in zip(todo, keys):
+                    if key:
+                        groups.setdefault(key, []).append(k)
+                ask_set = {k for k, key in zip(todo, keys) if not key}                  # unknown: confirmed on their own
+                for key, members in groups.items():
+                    if key in confirmed_functions:                                      # settled earlier in this run
+                        for k in members:
+                            shared_from[k] = confirmed_functions[key][0]
+                            verdicts[k] = confirmed_functions[key][1:]
+                        continue
+                    rep = min(members, key=lambda k: len(pending[k]["expression"]))     # shortest form: cheapest for SymPy
+                    reps.append((key, rep, members))
+                    ask_set.add(rep)
+                ask = [k for k in todo if k in ask_set]                                 # keeps the most-plausible-first order
+            verdicts.update(zip(ask, confirm_pool.confirm([pending[k]["expression"] for k in ask])))
+            for key, rep, members in reps:
+                if verdicts[rep][0] is not None:                                        # a timeout is not a verdict
+                    confirmed_functions[key] = (pending[rep]["expression"],) + tuple(verdicts[rep])
+                for k in members:
+                    if k != rep:
+                        shared_from[k] = pending[rep]["expression"]
+                        verdicts[k] = verdicts[rep]
+            for k in todo:
+                ok, reason, paper = verdicts[k]
+                ev = {"gpu": pending[k]["evidence"], "confirmed_by": "confirm.ConfirmationPool"}
+                if k in shared_from:
+                    ev["same_function_as"] = shared_from[k]
+                    stats_extra["confirmations_shared"] += 1
+                else:
+                    gv.stats["cpu_confirmed"] += 1
+                pending[k].update(is_valid=ok, validation_reason=reason, paper=paper, evidence=ev)
         for r in pending:
             ok, reason = r["is_valid"], r["validation_reason"]
             status = "completed" if ok is not None else ("timeout" if str(reason).startswith("Timeout") else "error")
@@ -183,5 +226,5 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
         conn.close()
     stats = dict(gv.stats)
     stats.update(rows=len(rows), valid=sum(1 for r in rows if r["is_valid"]), wall_s=time.time() - t_start,
-                 enumeration=gen.stats)
+                 enumeration=gen.stats, **stats_extra)
     return {"rows": rows, "stats": stats, "table": table}
