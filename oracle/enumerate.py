@@ -133,6 +133,34 @@ def candidates_for_depth(
     return out
 
 
+def count_candidates(E: Dict[int, List[str]], depth: int, prune: bool = True) -> int:
+    """Number of candidates ``candidates_for_depth`` emits, by counting (LBF:139-195 rule by rule, no strings
+    built): the size check for depths where the list itself is too long to build (depth 5: 1.2e7)."""
+    prev = E[depth - 1]
+    if not prune:
+        n = len(UNARY_NAMES) * len(prev)
+        for d1 in range(1, depth):
+            n += len(BINARY_NAMES) * len(E[d1]) * len(E[depth - d1])
+        return n
+    n = sum(len(UNARY_NAMES) - (1 if e.startswith("inv(") else 0) for e in prev if has_vars(e))     # LBF:142-153
+    for d1 in range(1, depth):
+        A, B = E[d1], E[depth - d1]
+        nv_a = sum(1 for a in A if not has_vars(a))
+        nv_b = sum(1 for b in B if not has_vars(b))
+        live = len(A) * len(B) - nv_a * nv_b                        # LBF:162: at least one operand has variables
+        setb = set(B)
+        same = sum(1 for a in A if a in setb and has_vars(a))       # pairs a == b that passed the line above
+        one_a, one_b = ("1" in A), ("1" in setb)                    # '1' has no variables: its partner must have some
+        with_one_b = (len(A) - nv_a) if one_b else 0                # live pairs (a, '1')
+        with_one_a = (len(B) - nv_b) if one_a else 0                # live pairs ('1', b)
+        n += live                                                   # add
+        n += live - same                                            # sub: a != b
+        n += live - with_one_a - with_one_b                         # mul: neither is '1' (a live pair has at most one)
+        n += live - with_one_b - same                               # div: b != '1', a != b ('1' == '1' is not live)
+        n += live - with_one_b                                      # geom_sum: b != '1'
+    return n
+
+
 def signature(normalized: str) -> str:
     """LBF:55,66"""
     return hashlib.sha256(normalized.encode()).hexdigest()[:16]

@@ -110,3 +110,60 @@ def test_depth4_uniques_sign_symmetry(cuda_device, enum_ff):
     c = run(*_negated(code, length))
     # a program that needed all its spill slots may need one more frame after NEG is appended? no: NEG is in place.
     _same(a, c, "sign symmetry")
+
+
+def test_depth5_enumeration_full_size(cuda_device, enum_ff):
+    """Stage 1 at the size behind BASELINE config 5: the 11 778 899 pruned depth-5 candidates built from the real
+    depth 1-4 unique sets.  Count against the oracle's rule-by-rule counter (pinned to the reference's counts at
+    depths 2-4), windows against the full pass, structural hashes of a sample against the oracle's hash, triples
+    against the prune rules, and the dedup count against the number of distinct hashes."""
+    import torch
+    import pde_engine_b200 as pb
+    from oracle import enumerate as oe
+    E = uniques_by_depth(enum_ff)
+    flat, db = [], [0]
+    for k in range(1, 5):
+        flat += E[k]
+        db.append(len(flat))
+    sess = pb.Session.for_problem("force_free")
+    es = sess.compile(flat)
+    L = 128
+    n = pb.enumerate_count(es, db, 5, True)
+    assert n == oe.count_candidates(E, 5) == 11_778_899
+    assert pb.enumerate_count(es, db, 5, False) == oe.count_candidates(E, 5, prune=False)
+    dev = pb.enumerate_candidates(es, db, 5, True, 0, n, L)
+    first, nu = pb.dedup(dev["code"], dev["len"], dev["hash"])
+    torch.cuda.synchronize()
+    # windows (the sharding contract) at this size
+    for lo, cnt in ((0, 4097), (5_000_003, 100_001), (n - 33, 33)):
+        w = pb.enumerate_candidates(es, db, 5, True, lo, cnt, L)
+        for k in ("triple", "code", "len", "hash"):
+            assert torch.equal(w[k], dev[k][lo:lo + cnt]), (k, lo)
+    # sample rows: hash = oracle structural hash of the row's bytes; the triple obeys the prune rules and the order
+    idx = np.unique(np.concatenate([np.arange(0, n, 9973), np.arange(n - 50, n)]))
+    sel = torch.from_numpy(idx).to(cuda_device)
+    code = dev["code"][sel].cpu().numpy()
+    ln = dev["len"][sel].cpu().numpy()
+    hs = dev["hash"][sel].cpu().numpy().view(np.uint64)
+    tr = dev["triple"][sel].cpu().numpy()
+    for r in range(len(idx)):
+        if ln[r]:
+            assert int(hs[r]) == bc.structural_hash(bytes(code[r, :ln[r]])), idx[r]
+            assert not code[r, ln[r]:].any()
+        o, a, b = (int(x) for x in tr[r])
+        if b < 0:
+            assert oe.has_vars(flat[a]) and a >= db[3]                 # unary: operand from E[4], LBF:142-147
+        else:
+            assert oe.has_vars(flat[a]) or oe.has_vars(flat[b])        # LBF:162
+            da = np.searchsorted(db, a, side="right")
+            dbb = np.searchsorted(db, b, side="right")
+            assert da + dbb == 5                                       # depths add up (after the add/mul swap too)
+    # order: (op kind, operands) follow the reference's loop nest -- unary block first
+    t_all = dev["triple"][:, 2]
+    n_unary = int((t_all < 0).sum())
+    assert n_unary == sum(8 - e.startswith("inv(") for e in E[4] if oe.has_vars(e))
+    assert bool((t_all[:n_unary] < 0).all()) and bool((t_all[n_unary:] >= 0).all())
+    # dedup: first occurrences = distinct programs (64-bit hashes: no collision expected among 1.2e7 rows)
+    hv = dev["hash"][dev["len"] > 0]
+    n_empty = int((dev["len"] == 0).sum())
+    assert nu == int(first.sum()) == int(torch.unique(hv).numel()) + n_empty

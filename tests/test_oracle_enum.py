@@ -91,3 +91,16 @@ def test_depth2_run_db_fixture(enum_ff):
     assert len(E[2]) == 110 and len(rows) == 112
     sig = oe.signature
     assert sig("rho") == hashlib.sha256(b"rho").hexdigest()[:16]
+
+
+def test_closed_form_candidate_count(enum_ff, enum_kerr):
+    """oracle.enumerate.count_candidates (used where the list is too long to build) against the reference's
+    own candidate counts at every recorded depth, and against the list builder with pruning off."""
+    for g in (enum_ff, enum_kerr):
+        E = uniques_by_depth(g)
+        for d in sorted(E):
+            if d < 2:
+                continue
+            assert oe.count_candidates(E, d) == g["depths"][str(d)]["n_candidates"]
+        assert oe.count_candidates(E, 2, prune=False) == len(oe.candidates_for_depth(E, 2, prune=False))
+        assert oe.count_candidates(E, 3, prune=False) == len(oe.candidates_for_depth(E, 3, prune=False))
