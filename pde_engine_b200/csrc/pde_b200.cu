@@ -296,6 +296,9 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 #ifndef PDE_W_BIG
 #define PDE_W_BIG 20
 #endif
+#ifndef PDE_W_KERR
+#define PDE_W_KERR PDE_W_BIG   // Kerr, NP = 2, depth <= 3 uniques x 8: W = 20 (96 regs, 100 B spilled) 46.4 G evals/s; 16 (121 regs) 40.1; 24 (80 regs) 45.2
+#endif
 static int g_variant = -1;
 template <int PROBLEM, bool DUMP>
 static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
@@ -306,7 +309,8 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
         bool fits = false;
         if (g_variant != 4 && g_variant != 16 && vp.P >= 128) {
             constexpr int NPB = PROBLEM == PDE_PROBLEM_KERR ? PDE_NP_KERR : PDE_NP_BIG;
-            int rc = launch_validate_cfg<PROBLEM, DUMP, PDE_W_BIG, NPB, 1>(vp, st, &fits);
+            constexpr int WB = PROBLEM == PDE_PROBLEM_KERR ? PDE_W_KERR : PDE_W_BIG;
+            int rc = launch_validate_cfg<PROBLEM, DUMP, WB, NPB, 1>(vp, st, &fits);
             if (rc || fits) return rc;
         }
         if (g_variant != 4 && PDE_W_BIG != 16 && vp.P >= 128) {
