@@ -64,6 +64,23 @@ class Fingerprints:
         return out
 
 
+    def groups(self) -> List[dict]:
+        """Equivalence classes of the batch, largest first -- the grouping the reference's report builds with a SymPy
+        canonicalisation pipeline per row (GM:1918-2008): ``{'rep': index of the shortest member, 'members': [...]}``;
+        unknown rows are singletons."""
+        by_key: Dict[int, List[int]] = {}
+        out: List[dict] = []
+        for i, k in enumerate(self.key.tolist()):
+            if k == 0:
+                out.append({"rep": i, "members": [i]})
+            else:
+                by_key.setdefault(k, []).append(i)
+        for members in by_key.values():
+            out.append({"rep": min(members, key=lambda i: (len(self.strs[i]), i)), "members": members})
+        out.sort(key=lambda g: (-len(g["members"]), self.strs[g["rep"]]))      # GM:2010: descending size, then representative
+        return out
+
+
 class GpuFingerprinter:
     def __init__(self, problem: str = "force_free", P: int = 64, mantissa_bits: int = 26, L: int = 128,
                  spill_slots: int = 4, device=None, keep_values: bool = False):

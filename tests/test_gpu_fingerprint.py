@@ -87,6 +87,9 @@ def test_same_function_different_strings(cuda_device):
     assert k[6] == k[7] and k[9] == k[10] and k[11] == k[12] and k[13] == k[14]
     assert k[8] == 0 and f.n_finite[8] == 0                  # imaginary everywhere: unknown, left to the CPU
     assert len({int(x) for x in k if x}) == 7
+    g = f.groups()
+    assert [strs[i] for i in g[0]["members"]] == ["rho", "neg(neg(rho))", "inv(inv(rho))", "sqrt(rho**2)"] and strs[g[0]["rep"]] == "rho"
+    assert sum(len(x["members"]) for x in g) == len(strs) and len(g) == 8          # 7 functions + the unknown row
     dd = FunctionDedup(fpr)
     keep, same = dd.filter(strs)
     assert keep.tolist() == [True, False, False, True, True, False, True, False, True, True, False, True, False, True, False]
@@ -143,3 +146,14 @@ def test_run_with_shared_confirmations(cuda_device, tmp_path):
     assert sb["confirmations_shared"] > 0
     assert sb["cpu_confirmed"] + sb["confirmations_shared"] == runs[False]["stats"]["cpu_confirmed"]
     assert any('"same_function_as"' in r["validator_evidence"] for r in b)
+
+
+def test_kerr_parameters_are_generic(cuda_device):
+    """The reference's check values are M = 1, a = 1/10 (PI:283): fingerprints use generic values so that
+    expressions which only coincide there stay apart."""
+    from pde_engine_b200.fingerprint import GpuFingerprinter
+    f = GpuFingerprinter("kerr_magnetosphere").fingerprint(
+        ["r", "M*r", "r*x", "x*r", "a**2", "1/100", "-2*M*r + a**2 + r**2", "a**2 + r**2 - 2*r", "sqrt(x**2)", "x"])
+    k = f.key
+    assert (k != 0).all()
+    assert k[0] != k[1] and k[2] == k[3] and k[4] != k[5] and k[6] != k[7] and k[8] != k[9]
