@@ -409,6 +409,27 @@ __device__ __forceinline__ void jet_abs(Jet<N>& t) {
 }
 
 
+// Univariate jets.  A sub-expression that depends on ONE coordinate only has a jet whose mixed and other-axis
+// coefficients are structurally zero: coefficient (i, j) is on axis AX = 0 iff j == 0, on AX = 1 iff i == 0
+// (AX < 0: the general bivariate jet).  The bodies below take AX as a template parameter and skip every
+// output and every product that involves an off-axis coefficient -- the loops are fully unrolled, so the test is a
+// compile-time constant.  An order-4 product costs 15 multiply-adds instead of 70 on an axis.  The skipped
+// coefficients are never read and never written: they stay the zeros the leaf put there.
+template <int AX>
+__host__ __device__ constexpr bool ax_on(int i, int j) { return AX < 0 || (AX == 0 ? j == 0 : i == 0); }
+
+template <int N, int AX>
+__device__ __forceinline__ void jet_copy_ax(Jet<N>& t, const Jet<N>& u) {
+#pragma unroll
+    for (int n = 0; n <= N; ++n) {
+#pragma unroll
+        for (int j = 0; j <= n; ++j) {
+            if (!ax_on<AX>(n - j, j)) continue;
+            asm("mov.f64 %0, %1;" : "=d"(t.c[jidx(n - j, j)]) : "d"(u.c[jidx(n - j, j)]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // NP-point versions of the long bodies: the point index h is the INNERMOST loop, so the
 // NP independent dependency chains are interleaved in program order (NP-way ILP for
@@ -420,13 +441,14 @@ __device__ __forceinline__ void jet_abs(Jet<N>& t) {
 // One accumulator chain per output coefficient: the 15 outputs are independent, which is all the
 // ILP the in-order issue needs, and every extra instruction costs an issue slot (a second chain
 // per output added 14 DADDs to the 70 multiply-adds).
-template <int N, int NP>
+template <int N, int NP, int AX = -1>
 __device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP]) {
 #pragma unroll
     for (int n = N; n >= 0; --n) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP];
 #pragma unroll
             PDE_H acc[h] = t[h].c[jidx(gi, gj)] * u[h].c[0];
@@ -435,6 +457,7 @@ __device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP])
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == gi && bj == gj) continue;
+                    if (!ax_on<AX>(bi, bj)) continue;
 #pragma unroll
                     PDE_H acc[h] = fma(t[h].c[jidx(bi, bj)], u[h].c[jidx(gi - bi, gj - bj)], acc[h]);
                 }
@@ -446,7 +469,7 @@ __device__ __forceinline__ void jetv_mul(Jet<N> (&t)[NP], const Jet<N> (&u)[NP])
 }
 
 // t = t / d (in place on the numerator)
-template <int N, int NP>
+template <int N, int NP, int AX = -1>
 __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP]) {
     double r0[NP];
 #pragma unroll
@@ -456,6 +479,7 @@ __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP])
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP];
 #pragma unroll
             PDE_H acc[h] = t[h].c[jidx(gi, gj)];
@@ -464,6 +488,7 @@ __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP])
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     if (bi == 0 && bj == 0) continue;
+                    if (!ax_on<AX>(bi, bj)) continue;
 #pragma unroll
                     PDE_H acc[h] = fma(-d[h].c[jidx(bi, bj)], t[h].c[jidx(gi - bi, gj - bj)], acc[h]);
                 }
@@ -474,13 +499,14 @@ __device__ __forceinline__ void jetv_div(Jet<N> (&t)[NP], const Jet<N> (&d)[NP])
     }
 }
 
-template <int N, int NP>
+template <int N, int NP, int AX = -1>
 __device__ __forceinline__ void jetv_square(Jet<N> (&t)[NP]) {
 #pragma unroll
     for (int n = N; n >= 0; --n) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP], mid[NP];
 #pragma unroll
             PDE_H { acc[h] = 0.0; mid[h] = 0.0; }
@@ -489,6 +515,7 @@ __device__ __forceinline__ void jetv_square(Jet<N> (&t)[NP]) {
 #pragma unroll
                 for (int bj = 0; bj <= gj; ++bj) {
                     const int ib = jidx(bi, bj), ic = jidx(gi - bi, gj - bj);
+                    if (!ax_on<AX>(bi, bj)) continue;
                     if (ib < ic) {
 #pragma unroll
                         PDE_H acc[h] = fma(t[h].c[ib], t[h].c[ic], acc[h]);
@@ -504,7 +531,7 @@ __device__ __forceinline__ void jetv_square(Jet<N> (&t)[NP]) {
     }
 }
 
-template <int N, int NP>
+template <int N, int NP, int AX = -1>
 __device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
     double hh[NP];
 #pragma unroll
@@ -514,6 +541,7 @@ __device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP], mid[NP];
 #pragma unroll
             PDE_H { acc[h] = 0.0; mid[h] = 0.0; }
@@ -523,6 +551,7 @@ __device__ __forceinline__ void jetv_sqrt(Jet<N> (&t)[NP]) {
                 for (int bj = 0; bj <= gj; ++bj) {
                     const int ci = gi - bi, cj = gj - bj;
                     if ((bi == 0 && bj == 0) || (ci == 0 && cj == 0)) continue;
+                    if (!ax_on<AX>(bi, bj)) continue;
                     const int ib = jidx(bi, bj), ic = jidx(ci, cj);
                     if (ib < ic) {
 #pragma unroll
@@ -677,7 +706,7 @@ __device__ __forceinline__ void jetv_compose(Jet<N> (&t)[NP], Jet<N> (&a)[NP], c
 // scalar-times-jet parts share their scalar between consecutive multiply-adds:  23 + 8 + 35 + 14 = 80 multiply-adds
 // for N = 4 (Horner 91), about 50 of them with three different register pairs (Horner 61).  In place on t;
 // `a` holds d^2 (degrees 2..N) and, in its degree-1 slots, the degree-1 part of G.   Valid for N <= 4.
-template <int N, int NP>
+template <int N, int NP, int AX = -1>
 __device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP], const double (&f)[NP][N + 1]) {
     static_assert(N <= 4, "G = f_2 + f_3 d + f_4 d^2 covers N <= 4");
     // ---- d^2, degrees 2..N: unordered pairs once, doubled, plus the square of the middle term ----
@@ -686,6 +715,7 @@ __device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP]
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj;
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP], sq[NP];
             int cnt = 0;
             bool has_sq = false;
@@ -720,11 +750,15 @@ __device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP]
     double g2[NP][3];
     if (N >= 3) {
 #pragma unroll
-        PDE_H { a[h].c[1] = f[h][3] * t[h].c[1]; a[h].c[2] = f[h][3] * t[h].c[2]; }
+        PDE_H {
+            if (ax_on<AX>(1, 0)) a[h].c[1] = f[h][3] * t[h].c[1];
+            if (ax_on<AX>(0, 1)) a[h].c[2] = f[h][3] * t[h].c[2];
+        }
     }
     if (N >= 4) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
+            if (!ax_on<AX>(2 - k, k)) continue;
 #pragma unroll
             PDE_H g2[h][k] = fma(f[h][4], a[h].c[3 + k], f[h][3] * t[h].c[3 + k]);
         }
@@ -735,6 +769,7 @@ __device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP]
 #pragma unroll
         for (int gj = 0; gj <= n; ++gj) {
             const int gi = n - gj, g = jidx(gi, gj);
+            if (!ax_on<AX>(gi, gj)) continue;
             double acc[NP];
 #pragma unroll
             PDE_H acc[h] = fma(f[h][2], a[h].c[g], f[h][1] * t[h].c[g]);
@@ -755,7 +790,8 @@ __device__ __forceinline__ void jetv_compose_ps(Jet<N> (&t)[NP], Jet<N> (&a)[NP]
     }
 #pragma unroll
     PDE_H {
-        if (N >= 1) { t[h].c[1] *= f[h][1]; t[h].c[2] *= f[h][1]; }
+        if (N >= 1 && ax_on<AX>(1, 0)) t[h].c[1] *= f[h][1];
+        if (N >= 1 && ax_on<AX>(0, 1)) t[h].c[2] *= f[h][1];
         t[h].c[0] = f[h][0];
     }
 }

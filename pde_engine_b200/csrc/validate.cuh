@@ -23,6 +23,9 @@
 #include "residual_ff_gen.cuh"
 #include "../../include/pde_b200.h"
 
+#ifndef PDE_UNIVARIATE
+#define PDE_UNIVARIATE 1       // single-axis bodies for sub-expressions that depend on one coordinate
+#endif
 #ifndef PDE_COMPOSE_PS
 #define PDE_COMPOSE_PS 1      // 1: Paterson-Stockmeyer body (80 multiply-adds), 0: Horner body (91); measured 136.1 vs 138.3 ms
 #endif
@@ -71,6 +74,10 @@ enum UKind : uint8_t {
     U_NKINDS
 };
 constexpr unsigned F_SPILL = 1u << 16;
+// U_SQRT, U_SQUARE, U_INV, U_EXP, U_POW only (translate pass 3): T depends on ONE coordinate (or none), F_AXIS1 says
+// which; the body then runs on that axis' 5 coefficients instead of all 15
+constexpr unsigned F_UNI = 1u << 17;
+constexpr unsigned F_AXIS1 = 1u << 18;
 enum UFn : unsigned { FN_INV = 0, FN_EXP = 1, FN_EXPN = 2, FN_POW = 3 };
 
 struct ValidateParams {
@@ -283,6 +290,32 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
         }
     }
     emit(U_END, 0);
+#if PDE_UNIVARIATE
+    // ---- pass 3: which coordinates does every jet depend on?  (bit 0: coordinate 0, bit 1: coordinate 1) ----
+    // The stream is straight-line code, so one walk with a mask for T and a mask stack for the spilled jets
+    // (in `stk`, free again) is exact.  A heavy body whose result depends on at most one coordinate is replaced by
+    // its single-axis version: 15 instead of 70 multiply-adds for an order-4 product.  Constants ride on axis 0.
+    // PRIM rows are treated as bivariate.  The light bodies are correct as they are (zeros stay zeros).
+    unsigned mt = 0;
+    int msp = 0;
+    for (int k = 0; k + 1 < nu; ++k) {
+        const unsigned w = uc[k], kind = w & 0xffu, arg = (w >> 8) & 0xffu;
+        switch (kind) {
+            case U_SETV0: case U_SETV1: case U_SETC: case U_SETP: case U_FNV: case U_FNC:
+                if (w & F_SPILL) stk[msp++] = (uint8_t)mt;
+                mt = kind == U_SETV0 ? 1u : kind == U_SETV1 ? 2u : kind == U_SETP ? 3u : kind == U_FNV ? (1u << arg) : 0u;
+                break;
+            case U_ADD_S: case U_SUB_S: case U_RSUB_S: case U_MUL_S: case U_DIV_S: case U_RDIV_S: mt |= stk[--msp]; break;
+            case U_ADD_P: case U_SUB_P: case U_MUL_P: case U_DIV_P: case U_RDIV_P: mt = 3u; break;
+            case U_ADDV0: case U_SUBV0: case U_MULV0: case U_DIVV0: mt |= 1u; break;
+            case U_ADDV1: case U_SUBV1: case U_MULV1: case U_DIVV1: mt |= 2u; break;
+            case U_SQRT: case U_SQUARE: case U_INV: case U_EXP: case U_POW:
+                if (mt != 3u) uc[k] = w | F_UNI | (mt == 2u ? F_AXIS1 : 0u);
+                break;
+            default: break;
+        }
+    }
+#endif
     return 0;
 }
 
@@ -562,8 +595,14 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
 #pragma unroll
                 PDE_EACH jet_abs(T[h]);
                 break;
-            case U_SQRT: jetv_sqrt<N, NP>(T); break;
-            case U_SQUARE: jetv_square<N, NP>(T); break;
+#define PDE_BY_AXIS(FN, ...)                                                 \
+    if (ins_cur & F_UNI) {                                                      \
+        if (ins_cur & F_AXIS1) FN<N, NP, 1>(__VA_ARGS__); else FN<N, NP, 0>(__VA_ARGS__); \
+    } else {                                                                    \
+        FN<N, NP, -1>(__VA_ARGS__);                                             \
+    }
+            case U_SQRT: PDE_BY_AXIS(jetv_sqrt, T) break;
+            case U_SQUARE: PDE_BY_AXIS(jetv_square, T) break;
             // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
             // shared in-place Horner body
             case U_INV:
@@ -579,7 +618,7 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
                 PDE_EACH scalar_taylor<N>(FN_POW, arg, T[h].c[0], f[h]);
             l_compose:
 #if PDE_COMPOSE_PS
-                jetv_compose_ps<N, NP>(T, U, f);
+                PDE_BY_AXIS(jetv_compose_ps, T, U, f)
 #else
                 jetv_compose<N, NP>(T, U, f);
 #endif
@@ -587,6 +626,7 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
             default: __builtin_unreachable();
         }
     }
+#undef PDE_BY_AXIS
 #undef PDE_SPILL_IF_FLAGGED
 #undef PDE_FETCH_S
 #undef PDE_FETCH_P
