@@ -266,3 +266,43 @@ def test_full_size_properties(cuda_device, enum_ff):
         if s in strs:
             i = strs.index(s)
             assert (bits[i >> 5] >> (i & 31)) & 1, s
+
+
+UNIVARIATE = {
+    "force_free": ["sqrt(exp(rho))", "exp(-sqrt(rho))", "1/exp(rho**2)", "sqrt(rho)**(3/2)", "exp(exp(-z))", "(z**2)**(-3/2)",
+                   "sqrt(1 + z**2)", "exp(1/(1 + rho))", "(1 + exp(rho))**2", "exp(sqrt(2))", "1/sqrt(exp(1))",
+                   "sqrt(exp(rho))*exp(1/z)", "exp(exp(rho))/(1 + exp(-z))", "sqrt(exp(rho) + exp(sqrt(rho)))",
+                   "exp(sqrt(rho*rho + 1))**2", "sqrt(exp(z))/(1 + sqrt(exp(z)))"],
+    "kerr_magnetosphere": ["sqrt(exp(r))", "exp(-sqrt(r))", "exp(exp(x))", "1/exp(x**2)", "sqrt(exp(r))*exp(x)", "(1 + exp(r))**2"],
+}
+
+
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_single_axis_bodies(problem, cuda_device):
+    """Sub-expressions of one coordinate run through the single-axis sqrt / square / composition bodies
+    (translate pass 3): on-axis coefficients against the oracle, off-axis coefficients exactly zero, and products
+    of a rho-part with a z-part (general bodies fed by single-axis results) against the oracle too."""
+    import torch
+    strs = UNIVARIATE[problem]
+    pb, sess, prog, pts, pts_t, tab_t = _setup(problem, 64, cuda_device)
+    es = sess.compile(strs)
+    assert not es.flags().any()
+    code, ln = es.programs(128)
+    jets, resid, scale = pb.eval_points(sess, prog, torch.from_numpy(code).to(cuda_device), torch.from_numpy(ln).to(cuda_device),
+                                        pts_t, tab_t, None, spill_slots=8)
+    torch.cuda.synchronize()
+    jets = jets.cpu().numpy()
+    oracle = _oracle_eval(problem, strs, pts)
+    n = _compare_points(jets, resid.cpu().numpy(), scale.cpu().numpy(), oracle, strs, problem, pts)
+    assert n > 0
+    order = 4 if problem == "force_free" else 2
+    v0, v1 = sess.var_names if hasattr(sess, "var_names") else (("rho", "z") if problem == "force_free" else ("r", "x"))
+    for i, s in enumerate(strs):
+        has0, has1 = (v0 in s), (v1 in s.replace("exp", "").replace("sqrt", "")) if v1 == "x" else (v1 in s)
+        if has0 and has1:
+            continue
+        for a in range(order + 1):
+            for b in range(order + 1 - a):
+                off_axis = (b > 0) if has0 else (a > 0) if has1 else (a + b > 0)
+                if off_axis:
+                    assert (jets[i, J.idx(a, b)] == 0).all(), (s, a, b)       # structural zeros stay exact zeros
