@@ -130,7 +130,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------ clocks
@@ -518,13 +518,30 @@ def run_ours(args):
             v, dt, ns = cpu_baseline(args.cpu_sample, P, args.depth, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"first {ns} trees of the same batch x {P} points, oracle (numpy) port, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # Libraries chat on stdout (NCCL prints its version line there): everything but the result line goes to stderr.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
