@@ -65,6 +65,7 @@ enum UKind : uint8_t {
     U_MUL_S, U_MUL_P,                         // T = T * U
     U_DIV_S, U_DIV_P,                         // T = T / U  (in place on the numerator)
     U_RDIV_S, U_RDIV_P,                       // T = U / T  (in place on U, copied back)
+    U_RDIV_V0, U_RDIV_V1,                     // T = coordinate / T: the same quotient body with U = the coordinate's jet
     U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
     U_NEG, U_ABS, U_SQRT, U_SQUARE,
@@ -273,7 +274,8 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                         if (bl >= PDE_OP_CONST0) emit(U_RSUBC, bl - PDE_OP_CONST0);
                         else { emit(U_NEG, 0); bin_leaf_right(0, bl); }
                     } else if (op_is_prim(bl)) emit(U_RDIV_P, bl - PDE_OP_PRIM0);        // PRIM / T
-                    else { emit(U_INV, 0); bin_leaf_right(2, bl); }                     // x / T = (1 / T) * x (sparse)
+                    else if (bl == PDE_OP_VAR0 || bl == PDE_OP_VAR1) emit(U_RDIV_V0 + (bl - PDE_OP_VAR0), 0);   // x / T by the quotient recurrence
+                    else { emit(U_INV, 0); bin_leaf_right(2, bl); }                     // c / T = (1 / T) * c
                 } else {
                     const int second = rf ? l : r;
                     if (ns >= ns_max) return 2;                  // the second sub-tree's first leaf will spill T
@@ -307,8 +309,8 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                 break;
             case U_ADD_S: case U_SUB_S: case U_RSUB_S: case U_MUL_S: case U_DIV_S: case U_RDIV_S: mt |= stk[--msp]; break;
             case U_ADD_P: case U_SUB_P: case U_MUL_P: case U_DIV_P: case U_RDIV_P: mt = 3u; break;
-            case U_ADDV0: case U_SUBV0: case U_MULV0: case U_DIVV0: mt |= 1u; break;
-            case U_ADDV1: case U_SUBV1: case U_MULV1: case U_DIVV1: mt |= 2u; break;
+            case U_ADDV0: case U_SUBV0: case U_MULV0: case U_DIVV0: case U_RDIV_V0: mt |= 1u; break;
+            case U_ADDV1: case U_SUBV1: case U_MULV1: case U_DIVV1: case U_RDIV_V1: mt |= 2u; break;
             case U_SQRT: case U_SQUARE: case U_INV: case U_EXP: case U_POW:
                 if (mt != 3u) uc[k] = w | F_UNI | (mt == 2u ? F_AXIS1 : 0u);
                 break;
@@ -529,6 +531,16 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
             // U / T: the division runs in place on the numerator U; the copy back is opaque to the
             // register allocator (jet_copy, jet.cuh) and costs 30 moves against 76 FP64 instructions
             case U_RDIV_S: PDE_FETCH_S goto l_rdiv;
+            case U_RDIV_V0: {
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH { jet_fill(U[h], z); U[h].c[0] = cx[h].x0; U[h].c[1] = c_one; }
+            } goto l_rdiv;
+            case U_RDIV_V1: {
+                const double z = opaque_zero();
+#pragma unroll
+                PDE_EACH { jet_fill(U[h], z); U[h].c[0] = cx[h].x1; U[h].c[2] = c_one; }
+            } goto l_rdiv;
             case U_RDIV_P: PDE_FETCH_P
             l_rdiv:
                 jetv_div<N, NP>(U, T);

@@ -272,7 +272,8 @@ UNIVARIATE = {
     "force_free": ["sqrt(exp(rho))", "exp(-sqrt(rho))", "1/exp(rho**2)", "sqrt(rho)**(3/2)", "exp(exp(-z))", "(z**2)**(-3/2)",
                    "sqrt(1 + z**2)", "exp(1/(1 + rho))", "(1 + exp(rho))**2", "exp(sqrt(2))", "1/sqrt(exp(1))",
                    "sqrt(exp(rho))*exp(1/z)", "exp(exp(rho))/(1 + exp(-z))", "sqrt(exp(rho) + exp(sqrt(rho)))",
-                   "exp(sqrt(rho*rho + 1))**2", "sqrt(exp(z))/(1 + sqrt(exp(z)))"],
+                   "exp(sqrt(rho*rho + 1))**2", "sqrt(exp(z))/(1 + sqrt(exp(z)))",
+                   "z/exp(exp(z/rho))", "rho/exp(exp(z/rho))"],      # coordinate / T: quotient recurrence (relative derivatives ~1e13)
     "kerr_magnetosphere": ["sqrt(exp(r))", "exp(-sqrt(r))", "exp(exp(x))", "1/exp(x**2)", "sqrt(exp(r))*exp(x)", "(1 + exp(r))**2"],
 }
 
@@ -310,9 +311,9 @@ def test_single_axis_bodies(problem, cuda_device):
 
 def _random_expr(rng, depth, vars_, in_exp=False):
     """Random expression string over the reference's vocabulary after normalisation: + - * /,
-    rational powers, sqrt, exp, Abs, small rational constants.  No exp inside an exp: for `z/exp(exp(z/rho))` the
-    relative derivatives reach 1e13 and the device's 1/T by composition loses 8 digits against the oracle's quotient
-    recurrence (a value of 1e-51 whose residual underflows anyway)."""
+    rational powers, sqrt, exp, Abs, small rational constants.  No exp inside an exp: with relative derivatives of 1e13
+    (`2/exp(exp(z/rho))`) 1/T by composition loses 8 digits against the oracle's quotient recurrence (values of 1e-51
+    whose residual underflows anyway)."""
     if depth == 0 or rng.random() < 0.15:
         r = rng.random()
         if r < 0.4:
