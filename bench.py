@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3600, help="trees in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--confirm-points", type=int, default=256,
+                    help="points of the confirmation pass with round-off majorants (0: one pass with majorants on all points)")
     return ap.parse_args()
 
 
@@ -213,7 +215,7 @@ def run_ours(args):
     def step():
         nonlocal out
         out = pb.validate(sess, prog, trees["code"], trees["len"], pts_t, tab_t, prim_t,
-                          tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=2, out=out)
+                          tau=1e-10, min_finite=8, vote_frac=0.5, confirm_points=args.confirm_points, n_ref=3, spill_slots=2, out=out)
         if world > 1:
             gather_survivors(out["survivor_bits"], trees["hash"], n)
 
@@ -240,7 +242,7 @@ def run_ours(args):
     for s in range(args.steps):
         kern_ev[s][0].record()
         out = pb.validate(sess, prog, trees["code"], trees["len"], pts_t, tab_t, prim_t,
-                          tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=2, out=out)
+                          tau=1e-10, min_finite=8, vote_frac=0.5, confirm_points=args.confirm_points, n_ref=3, spill_slots=2, out=out)
         kern_ev[s][1].record()
         if world > 1:
             gather_survivors(out["survivor_bits"], trees["hash"], n)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 2
+#define PDE_B200_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------- */
 #define PDE_OK            0
@@ -183,22 +183,46 @@ int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][
  * Replaces the per-candidate validate() call of emit_to_db (GM:1302-1316) and
  * the validator worker pool (GM:1672-1824) as a *filter*: a candidate is
  * rejected only when its residual is numerically non-zero: n_finite >= min_finite
- * and |R| > tau * S at >= vote_frac * n_finite of the finite points (a
- * majority vote is robust against isolated ill-conditioned points near poles);
+ * and |R| > tau * S~ at >= vote_frac * n_finite of the finite points;
  * everything else survives to the CPU validator.
+ *
+ * S~ is the DECISION SCALE: the residual's majorant (sum of |monomial|, every
+ * partial of order n replaced by the sum of the |partials| of that order)
+ * evaluated at partials inflated by theta_n = 2 eps W n! / (t0^n tau), where W is
+ * the round-off majorant the interpreter carries next to every jet
+ * (|computed c_g - exact c_g| <= eps W / t0^|g|; rules and proof sketch in
+ * oracle/majorant.py).  For an exact solution |R| <= tau S~ under
+ * ANY float64 evaluation order, so a point can only vote when its residual is
+ * non-zero beyond the propagated rounding error of u's own jet; t0 (0 < t0 <= 1,
+ * default 1/8) is the radius the majorant series are evaluated at: points
+ * closer than t0 to a pole of a sub-expression do not vote.
+ *
+ * Two passes (confirm_points > 0, a multiple of 128; default 256): carrying the
+ * majorants costs about a fifth of the kernel's throughput, and a rejection is
+ * sound as soon as the majorant rule votes it on ANY sufficiently large set of
+ * points.  Pass 1 therefore sweeps all P points WITHOUT majorants (theta = 0)
+ * and only PROPOSES rejections; pass 2 re-evaluates the proposed rejections on
+ * the first confirm_points points of the same grid WITH the majorants and a
+ * rejection stands only if that pass votes it too (n_finite >= min_finite and
+ * votes >= vote_frac * n_finite there); every other candidate gets its survivor
+ * bit back.  ratio_max / resid_max / scale_at / n_finite / n_votes report pass
+ * 1 (whole grid, theta = 0), `confirm` reports pass 2, ref_rs holds (R, S~) of
+ * pass 2 for re-examined candidates.  confirm_points = 0: one pass over all P
+ * points with the majorants carried (what the parity tests compare against).
  *
  *   code[n, L], len[n]   postfix programs (len 0 = skip: survivor, n_finite 0)
  *   pts[2][P]            collocation grid, SoA, P a multiple of 64
  *   table[cols][P]       pde_program_point_table
  *   prim[n_prim][P/32][16][32]  jets of PRIM(p) leaves in 32-point stripe blocks: coefficient g of
- *                            point q at [p][q / 32][g][q % 32] (rows n_coef..15 are padding), so a
+ *                            point q at [p][q / 32][g][q % 32]; row 15 holds the leaf's majorant pair
+ *                            (D, W) as two float32 (rows n_coef..14 are padding), so a
  *                            warp reads a leaf with coalesced loads at immediate offsets; may be
  *                            NULL (n_prim = 0) if no program uses PRIM; a program that uses PRIM(p) with
  *                            p >= n_prim is reported as malformed (n_finite = -2), never dereferenced
  * outputs (per candidate):
- *   ratio_max   max |R|/S over finite points        resid_max  max |R|
- *   scale_at    S at the arg-max of the ratio       n_finite, n_votes
- *   ref_rs[n, n_ref, 2]  (R, S) at the first n_ref points (the reference's own
+ *   ratio_max   max |R|/S~ over finite points       resid_max  max |R|
+ *   scale_at    S~ at the arg-max of the ratio      n_finite, n_votes
+ *   ref_rs[n, n_ref, 2]  (R, S~) at the first n_ref points (the reference's own
  *                        test points, FFV:296-297 / KV:168-172); n_ref <= 4
  *   survivor_bits[(n+31)/32]  bit c = 1 iff candidate c is NOT rejected
  *   n_finite < 0: not evaluated (-1 empty program, -2 malformed, -3 needs more
@@ -212,22 +236,28 @@ typedef struct pde_validate_out {
     int32_t  *n_votes;       /* [n] */
     double   *ref_rs;        /* [n, n_ref, 2] or NULL */
     uint32_t *survivor_bits; /* [(n+31)/32] */
+    int32_t  *confirm;       /* [n, 2] or NULL: (n_finite, n_votes) of the confirmation pass; -1 = not re-examined */
+    int32_t  *scratch;       /* [n + 2]: work space of the two-pass mode (may be NULL when confirm_points = 0) */
 } pde_validate_out;
 
 int  pde_validate(const pde_session *s, const pde_program *p,
                   const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
                   const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
-                  double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
+                  double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
                   const pde_validate_out *out, void *stream);
 
-/* parity / tooling entry: full per-point output for SMALL batches.
- *   jets[n, n_coef, P] normalised Taylor coefficients of u (may be NULL)
- *   resid[n, P], scale[n, P] (may be NULL) */
+/* parity / tooling entry: full per-point output for SMALL batches (each may be NULL).
+ *   jets[n, n_coef, P]   normalised Taylor coefficients of u
+ *   resid[n, P]          R
+ *   scale[n, P]          S  = sum of |monomial| of R (the scale per-point parity is quoted against)
+ *   scale_maj[n, P]      S~ = the decision scale of pde_validate
+ *   maj[n, 3, P] float32 (V, D, W): the majorants of the finished jet */
 int  pde_eval_points(const pde_session *s, const pde_program *p,
                      const uint8_t *code_dev, const uint8_t *len_dev, int64_t n, int L,
                      const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
-                     int spill_slots,
-                     double *jets_dev, double *resid_dev, double *scale_dev, void *stream);
+                     double tau, double t0, int spill_slots,
+                     double *jets_dev, double *resid_dev, double *scale_dev, double *scale_maj_dev, float *maj_dev,
+                     void *stream);
 
 /* ------------------------------------------------------------------------
  * Function fingerprints: a numeric pre-bucketing for the

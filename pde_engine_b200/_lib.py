@@ -37,6 +37,7 @@ class ValidateOut(C.Structure):
     _fields_ = [
         ("ratio_max", c_void_p), ("resid_max", c_void_p), ("scale_at", c_void_p),
         ("n_finite", c_void_p), ("n_votes", c_void_p), ("ref_rs", c_void_p), ("survivor_bits", c_void_p),
+        ("confirm", c_void_p), ("scratch", c_void_p),
     ]
 
 
@@ -72,9 +73,9 @@ _sig("pde_program_free", None, c_void_p)
 _sig("pde_program_info", c_int, c_void_p, P(c_int), P(c_int), P(c_int))
 _sig("pde_program_point_table", c_int, c_void_p, c_void_p, c_int, c_void_p)
 _sig("pde_validate", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-     c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_int, c_int, P(ValidateOut), c_void_p)
+     c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_double, c_int, c_int, c_int, P(ValidateOut), c_void_p)
 _sig("pde_eval_points", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-     c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
+     c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_fingerprint", c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_fp64_peak", c_int, c_int, P(c_double), c_void_p)

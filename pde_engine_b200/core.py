@@ -18,6 +18,13 @@ PROBLEM_FORCE_FREE = 0
 PROBLEM_KERR = 1
 
 N_CONST, N_POW = 128, 64
+# radius the round-off majorant series are evaluated at (include/pde_b200.h, oracle/majorant.py): measured on the
+# reference verdicts of depth <= 3 (tests/offline/majorant_study.py): 1/16 keeps 310 of 311 old rejects, 1/8 297 of 300,
+# 1/4 295 of 312, 1/32 308 of 311 -- smaller radii lose fewer points next to poles but inflate high-order partials more
+T0_DEFAULT = 0.0625
+# points of the confirmation pass (include/pde_b200.h): carrying the majorants costs ~1/5 of the kernel's throughput, so the
+# whole grid is swept without them and only the proposed rejections are re-examined with them on a sub-grid
+CONFIRM_POINTS_DEFAULT = 256
 
 
 def _np_ptr(a: np.ndarray):
@@ -185,10 +192,13 @@ class ResidualProgram:
 # ---------------------------------------------------------------------------
 
 def validate(session: Session, program: ResidualProgram, code, length, pts, table, prim=None, *,
-             tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, n_ref: int = 3,
+             tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, t0: float = T0_DEFAULT,
+             confirm_points: int = CONFIRM_POINTS_DEFAULT, n_ref: int = 3,
              spill_slots: int = 4, stream=None, out: Optional[dict] = None) -> dict:
     """Stage 2 (pde_validate).  code [n, L] uint8, length [n] uint8, pts [2, P] f64,
-    table [cols, P] f64, prim [n_prim, P/32, 16, 32] f64 (synthetic.pack_primitive_table) or None -- all CUDA tensors."""
+    table [cols, P] f64, prim [n_prim, P/32, 16, 32] f64 (synthetic.pack_primitive_table) or None -- all CUDA tensors.
+    confirm_points > 0: two passes (proposals on all P points, confirmation with round-off majorants on the first
+    confirm_points points); 0: one pass with the majorants on all points (include/pde_b200.h)."""
     import torch
     n, L = code.shape
     Pn = pts.shape[1]
@@ -202,19 +212,25 @@ def validate(session: Session, program: ResidualProgram, code, length, pts, tabl
             "n_votes": torch.empty(n, dtype=torch.int32, device=dev),
             "ref_rs": torch.empty((n, n_ref, 2), dtype=torch.float64, device=dev) if n_ref else None,
             "survivor_bits": torch.empty((n + 31) // 32, dtype=torch.int32, device=dev),
+            "confirm": torch.empty((n, 2), dtype=torch.int32, device=dev),
         }
-    vo = _lib.ValidateOut(*[_dev_ptr(out[k]) for k in
-                            ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "survivor_bits")])
+    confirm_points = min(int(confirm_points), Pn) // 128 * 128
+    if confirm_points > 0 and out.get("scratch") is None:
+        out["scratch"] = torch.empty(n + 2, dtype=torch.int32, device=dev)
+    vo = _lib.ValidateOut(*[_dev_ptr(out.get(k)) for k in
+                            ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "survivor_bits", "confirm", "scratch")])
     check(lib.pde_validate(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
                            _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
-                           float(tau), int(min_finite), float(vote_frac), int(n_ref), int(spill_slots),
+                           float(tau), int(min_finite), float(vote_frac), float(t0), int(confirm_points), int(n_ref), int(spill_slots),
                            C.byref(vo), _stream_ptr(stream)))
     return out
 
 
 def eval_points(session: Session, program: ResidualProgram, code, length, pts, table, prim=None, *,
-                spill_slots: int = 4, want_jets: bool = True, want_resid: bool = True, stream=None):
-    """Parity / tooling entry (pde_eval_points): full per-point jets [n, NC, P], R [n, P], S [n, P]."""
+                spill_slots: int = 4, want_jets: bool = True, want_resid: bool = True, want_maj: bool = False,
+                tau: float = 1e-10, t0: float = T0_DEFAULT, stream=None):
+    """Parity / tooling entry (pde_eval_points): full per-point jets [n, NC, P], R [n, P], S [n, P]; with
+    want_maj also the decision scale S~ [n, P] and the majorants (V, D, W) [n, 3, P] float32."""
     import torch
     n, L = code.shape
     Pn = pts.shape[1]
@@ -222,9 +238,14 @@ def eval_points(session: Session, program: ResidualProgram, code, length, pts, t
     jets = torch.full((n, program.n_coef, Pn), float("nan"), dtype=torch.float64, device=dev) if want_jets else None
     resid = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
     scale = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_resid else None
+    scale_maj = torch.full((n, Pn), float("nan"), dtype=torch.float64, device=dev) if want_maj else None
+    maj = torch.full((n, 3, Pn), float("nan"), dtype=torch.float32, device=dev) if want_maj else None
     check(lib.pde_eval_points(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
-                              _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn, int(spill_slots),
-                              _dev_ptr(jets), _dev_ptr(resid), _dev_ptr(scale), _stream_ptr(stream)))
+                              _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
+                              float(tau), float(t0), int(spill_slots),
+                              _dev_ptr(jets), _dev_ptr(resid), _dev_ptr(scale), _dev_ptr(scale_maj), _dev_ptr(maj), _stream_ptr(stream)))
+    if want_maj:
+        return jets, resid, scale, scale_maj, maj
     return jets, resid, scale
 
 

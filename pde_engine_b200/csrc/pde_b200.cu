@@ -116,6 +116,21 @@ fingerprint_kernel(const double* __restrict__ values, long long n, int P, int dr
     }
 }
 
+// Proposed rejections of the first pass (cleared survivor bits) -> index list for the confirmation pass.
+// Order is whatever the atomics give: every output of the confirmation pass is addressed by candidate.
+__global__ void __launch_bounds__(256)
+compact_rejects_kernel(const unsigned* __restrict__ bits, long long n, int* __restrict__ index, unsigned long long* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool rej = i < n && !((bits[i >> 5] >> (i & 31)) & 1u);
+    const unsigned b = __ballot_sync(0xffffffffu, rej);
+    if (!b) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (rej) index[base + __popc(b & ((1u << lane) - 1u))] = (int)i;
+}
+
 }  // namespace pde
 
 using namespace pde;
@@ -238,7 +253,7 @@ int pde_program_point_table(const pde_program* p, const double* pts, int P, doub
 }  // extern "C"
 
 // ------------------------------------------------------------- stage 2
-static int upload_tables(const pde_session* s, cudaStream_t st) {
+static int upload_tables(const pde_session* s, double tau, double t0, cudaStream_t st) {
     double cv[PDE_N_CONST], pv[PDE_N_POW];
     pde_session_tables(s, cv, nullptr, pv, nullptr);
     double rv[PDE_N_CONST];
@@ -252,14 +267,40 @@ static int upload_tables(const pde_session* s, cudaStream_t st) {
         for (int j = 0; j < 4; ++j) fr[sl][j] = (pv[sl] - j) / (j + 1);
     }
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_frow, fr, sizeof(fr), 0, cudaMemcpyHostToDevice, st));
+    // x**n, n = 0, 1, 2, ... <= 64: binomial coefficients C(n, 0..4) (the division-free Taylor coefficients)
+    int pi[kNRows];
+    double fb[kNRows][5];
+    for (int sl = 0; sl < kNRows; ++sl) {
+        const double k = pv[sl];
+        pi[sl] = (k >= 0.0 && k <= 64.0 && k == floor(k)) ? (int)k : -1;
+        fb[sl][0] = 1.0;
+        for (int j = 0; j < 4; ++j) fb[sl][j + 1] = fb[sl][j] * (k - j) / (j + 1);
+    }
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow_int, pi, sizeof(pi), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_fbin, fb, sizeof(fb), 0, cudaMemcpyHostToDevice, st));
+    // round-off majorants: theta_n / W = 2 eps n! / (t0^n tau) (+ 0.2 % for the float32 arithmetic of the majorants)
+    const float t0f = (float)t0;
+    double th[4], fact = 1.0, tp = 1.0;
+    for (int n = 1; n <= 4; ++n) {
+        fact *= n; tp *= (double)t0f;
+        th[n - 1] = 2.0 * 2.220446049250313e-16 * fact / (tp * tau) * 1.002;
+    }
+    float cf[PDE_N_CONST], rf[PDE_N_CONST], pf[PDE_N_POW];
+    for (int i = 0; i < PDE_N_CONST; ++i) { cf[i] = fmaxf((float)fabs(cv[i]), 1e-18f); rf[i] = fmaxf((float)fabs(rv[i]), 1e-18f); }
+    for (int i = 0; i < PDE_N_POW; ++i) pf[i] = (float)pv[i];
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_constf, cf, sizeof(cf), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconstf, rf, sizeof(rf), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_powf, pf, sizeof(pf), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_t0, &t0f, sizeof(t0f), 0, cudaMemcpyHostToDevice, st));
+    PDE_CUDA(cudaMemcpyToSymbolAsync(c_theta, th, sizeof(th), 0, cudaMemcpyHostToDevice, st));
     return PDE_OK;
 }
 
-template <int PROBLEM, bool DUMP, int W, int NP, int MINB>
+template <int PROBLEM, bool DUMP, int W, int NP, int MINB, bool MAJ>
 static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* fits) {
     constexpr int N = Residual<PROBLEM>::N;
     const size_t smem = cta_smem_bytes<N, NP>(vp.L, vp.ns, W);
-    auto kern = validate_kernel<PROBLEM, DUMP, W, NP, MINB>;
+    auto kern = validate_kernel<PROBLEM, DUMP, W, NP, MINB, MAJ>;
     int dev = 0, sms = 0, occ = 0, max_smem = 0;
     PDE_CUDA(cudaGetDevice(&dev));
     PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -300,24 +341,26 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 #define PDE_W_KERR PDE_W_BIG   // Kerr, NP = 2, depth <= 3 uniques x 8: W = 20 (96 regs, 100 B spilled) 46.4 G evals/s; 16 (121 regs) 40.1; 24 (80 regs) 45.2
 #endif
 static int g_variant = -1;
-template <int PROBLEM, bool DUMP>
+template <int PROBLEM, bool DUMP, bool MAJ>
 static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
     if (g_variant < 0) { const char* e = getenv("PDE_B200_VARIANT"); g_variant = e ? atoi(e) : 0; }
     if constexpr (DUMP) {
-        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4>(vp, st, nullptr);
+        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4, MAJ>(vp, st, nullptr);
     } else {
         bool fits = false;
-        if (g_variant != 4 && g_variant != 16 && vp.P >= 128) {
+        if (g_variant != 4 && g_variant != 16 && vp.P_eval >= 128) {
             constexpr int NPB = PROBLEM == PDE_PROBLEM_KERR ? PDE_NP_KERR : PDE_NP_BIG;
             constexpr int WB = PROBLEM == PDE_PROBLEM_KERR ? PDE_W_KERR : PDE_W_BIG;
-            int rc = launch_validate_cfg<PROBLEM, DUMP, WB, NPB, 1>(vp, st, &fits);
+            if (vp.P_eval % (128 * NPB) == 0 || vp.P_eval == vp.P) {
+                int rc = launch_validate_cfg<PROBLEM, DUMP, WB, NPB, 1, MAJ>(vp, st, &fits);
+                if (rc || fits) return rc;
+            }
+        }
+        if (g_variant != 4 && PDE_W_BIG != 16 && vp.P_eval >= 128) {
+            int rc = launch_validate_cfg<PROBLEM, DUMP, 16, 1, 1, MAJ>(vp, st, &fits);
             if (rc || fits) return rc;
         }
-        if (g_variant != 4 && PDE_W_BIG != 16 && vp.P >= 128) {
-            int rc = launch_validate_cfg<PROBLEM, DUMP, 16, 1, 1>(vp, st, &fits);
-            if (rc || fits) return rc;
-        }
-        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4>(vp, st, nullptr);
+        return launch_validate_cfg<PROBLEM, DUMP, 4, 1, 4, MAJ>(vp, st, nullptr);
     }
 }
 
@@ -331,47 +374,80 @@ static int check_common(const pde_session* s, const pde_program* p, const void* 
     return PDE_OK;
 }
 
+static int check_tau_t0(double tau, double t0) {
+    if (!(tau > 0.0 && tau <= 1.0)) { set_error("tau must be in (0, 1]"); return PDE_E_INVALID; }
+    if (!(t0 >= 1e-6 && t0 <= 1.0)) { set_error("t0 (majorant radius) must be in [1e-6, 1]"); return PDE_E_INVALID; }
+    return PDE_OK;
+}
+
 extern "C" {
 
 int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
                  int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
-                 double tau, int min_finite, double vote_frac, int n_ref, int spill_slots,
+                 double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
                  const pde_validate_out* out, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
+    if (rc) return rc;
+    rc = check_tau_t0(tau, t0);
     if (rc) return rc;
     if (n == 0) return PDE_OK;              // an empty batch is a no-op (its buffers may be null)
     if (!out || !out->ratio_max || !out->resid_max || !out->scale_at || !out->n_finite || !out->n_votes || !out->survivor_bits) {
         set_error("pde_validate: null output"); return PDE_E_INVALID;
     }
     if (n_ref < 0 || n_ref > 4) { set_error("n_ref must be in 0..4"); return PDE_E_INVALID; }
-    if (n == 0) return PDE_OK;
+    if (n >= 0x7fffffffLL) { set_error("pde_validate: n too large for one call"); return PDE_E_OVERFLOW; }
+    if (confirm_points < 0 || confirm_points > P || (confirm_points % 128) != 0) {
+        set_error("confirm_points must be 0 (one pass with majorants) or a multiple of 128 <= P"); return PDE_E_INVALID;
+    }
+    if (confirm_points > 0 && !out->scratch) { set_error("pde_validate: the two-pass mode needs out->scratch [n + 2] int32"); return PDE_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    rc = upload_tables(s, st);
+    rc = upload_tables(s, tau, t0, st);
     if (rc) return rc;
     PDE_CUDA(cudaMemsetAsync(out->survivor_bits, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
     ValidateParams vp{};
     vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
-    vp.ns = spill_slots; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
+    vp.P_eval = P;
+    vp.ns = spill_slots; vp.t0 = (float)t0; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
     vp.ratio_max = out->ratio_max; vp.resid_max = out->resid_max; vp.scale_at = out->scale_at;
     vp.n_finite = out->n_finite; vp.n_votes = out->n_votes; vp.ref_rs = out->ref_rs; vp.survivor_bits = out->survivor_bits;
-    if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, false>(vp, st);
-    return launch_validate<PDE_PROBLEM_KERR, false>(vp, st);
+    const bool ff = p->problem == PDE_PROBLEM_FORCE_FREE;
+    if (confirm_points == 0) {
+        // one pass over the whole grid with the majorants carried
+        return ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, true>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, true>(vp, st);
+    }
+    // pass 1: all P points, no majorants -- proposes rejections
+    rc = ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, false>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, false>(vp, st);
+    if (rc) return rc;
+    // pass 2: the proposed rejections again on the first confirm_points points WITH the majorants; a rejection
+    // stands only if this pass votes it too (include/pde_b200.h)
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(out->scratch);
+    int* index = out->scratch + 2;
+    PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    if (out->confirm) PDE_CUDA(cudaMemsetAsync(out->confirm, 0xff, sizeof(int32_t) * 2 * (size_t)n, st));   // -1: not re-examined
+    compact_rejects_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out->survivor_bits, n, index, cnt);
+    count_launch();
+    PDE_CUDA(cudaGetLastError());
+    vp.index = index; vp.n_index = cnt; vp.confirm = out->confirm; vp.P_eval = confirm_points;
+    return ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, true>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, true>(vp, st);
 }
 
 int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
                     int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
-                    int spill_slots, double* jets, double* resid, double* scale, void* stream) {
+                    double tau, double t0, int spill_slots, double* jets, double* resid, double* scale, double* scale_maj,
+                    float* maj, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
+    if (rc) return rc;
+    rc = check_tau_t0(tau, t0);
     if (rc) return rc;
     if (n == 0) return PDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = upload_tables(s, st);
+    rc = upload_tables(s, tau, t0, st);
     if (rc) return rc;
     ValidateParams vp{};
     vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
-    vp.ns = spill_slots; vp.jets = jets; vp.resid = resid; vp.scale = scale;
-    if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true>(vp, st);
-    return launch_validate<PDE_PROBLEM_KERR, true>(vp, st);
+    vp.P_eval = P; vp.ns = spill_slots; vp.t0 = (float)t0; vp.tau = tau; vp.jets = jets; vp.resid = resid; vp.scale = scale; vp.scale_maj = scale_maj; vp.maj = maj;
+    if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true, true>(vp, st);
+    return launch_validate<PDE_PROBLEM_KERR, true, true>(vp, st);
 }
 
 int pde_fingerprint(const pde_session* s, const uint8_t* code, const uint8_t* len, int64_t n, int L,
@@ -384,15 +460,15 @@ int pde_fingerprint(const pde_session* s, const uint8_t* code, const uint8_t* le
     if (!values || !key || !n_finite) { set_error("pde_fingerprint: null output"); return PDE_E_INVALID; }
     if (mantissa_bits < 8 || mantissa_bits > 51) { set_error("mantissa_bits must be in 8..51"); return PDE_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    rc = upload_tables(s, st);
+    rc = upload_tables(s, 1e-10, 0.0625, st);
     if (rc) return rc;
     // programs that are not evaluated (empty / malformed / too many spills) leave NaN rows -> key 0
     PDE_CUDA(cudaMemsetAsync(values, 0xff, sizeof(double) * (size_t)n * P, st));
     ValidateParams vp{};
     vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = pts; vp.prim = prim;
     vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
-    vp.ns = spill_slots; vp.resid = values;
-    rc = launch_validate<kProblemValue, true>(vp, st);
+    vp.P_eval = P; vp.ns = spill_slots; vp.t0 = 0.0625f; vp.tau = 1e-10; vp.resid = values;
+    rc = launch_validate<kProblemValue, true, false>(vp, st);
     if (rc) return rc;
     int dev = 0, sms = 0;
     PDE_CUDA(cudaGetDevice(&dev));

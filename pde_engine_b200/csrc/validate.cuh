@@ -26,9 +26,6 @@
 #ifndef PDE_UNIVARIATE
 #define PDE_UNIVARIATE 1       // single-axis bodies for sub-expressions that depend on one coordinate
 #endif
-#ifndef PDE_COMPOSE_PS
-#define PDE_COMPOSE_PS 1      // 1: Paterson-Stockmeyer body (80 multiply-adds), 0: Horner body (91); measured 136.1 vs 138.3 ms
-#endif
 
 namespace pde {
 
@@ -41,6 +38,16 @@ __constant__ double c_pow[PDE_N_POW];
 // Taylor-ratio rows of x**k (U_POW): f_{j+1} = f_j * row[j] / x_0, row[j] = (k - j)/(j + 1)
 constexpr int kNRows = PDE_N_POW;
 __constant__ double c_frow[kNRows][4];
+// x**n with n = 0, 1, 2, ...: c_pow_int[slot] = n (else -1) and the binomial coefficients C(n, j), j = 0..4, so that
+// the Taylor coefficients C(n, j) x^(n-j) need no division and stay finite at x = 0
+__constant__ int c_pow_int[kNRows];
+__constant__ double c_fbin[kNRows][5];
+// round-off majorants (oracle/majorant.py): expansion radius t0 and theta_n / W = 2 eps n! / (t0^n tau), n = 1..4
+__constant__ float c_t0;
+__constant__ float c_constf[PDE_N_CONST];    // |c_const| and |c_rconst| as float (clamped like maj_abs), c_pow as float
+__constant__ float c_rconstf[PDE_N_CONST];
+__constant__ float c_powf[kNRows];
+__constant__ double c_theta[4];
 __constant__ double c_one = 1.0;                       // constant-bank operand: no register, no per-dispatch move
 __constant__ double c_sign[2] = {1.0, -1.0};
 __constant__ double c_rfact[4] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4};   // 1/(j + 1)
@@ -65,17 +72,16 @@ enum UKind : uint8_t {
     U_MUL_S, U_MUL_P,                         // T = T * U
     U_DIV_S, U_DIV_P,                         // T = T / U  (in place on the numerator)
     U_RDIV_S, U_RDIV_P,                       // T = U / T  (in place on U, copied back)
-    U_RDIV_V0, U_RDIV_V1,                     // T = coordinate / T: the same quotient body with U = the coordinate's jet
+    U_RDIV_V0, U_RDIV_V1, U_RDIV_C,           // T = coordinate / T, constant / T (1 / T, inv(T)): the same quotient body with U = the leaf's jet
     U_ADDC, U_SUBC, U_RSUBC, U_MULC, U_MULRC, // sparse leaf fast paths (arg = const slot; MULRC: reciprocal)
     U_ADDV0, U_ADDV1, U_SUBV0, U_SUBV1, U_MULV0, U_MULV1, U_DIVV0, U_DIVV1,
     U_NEG, U_ABS, U_SQRT, U_SQUARE,
-    U_INV,                                    // T = 1 / T            } one shared Horner body
-    U_EXP,                                    // exp(+-T), arg = sign } (jetv_compose), in place
-    U_POW,                                    // arg = exponent slot  }
+    U_EXP,                                    // exp(+-T), arg = sign } one shared composition body
+    U_POW,                                    // arg = exponent slot  } (jetv_compose_ps), in place
     U_NKINDS
 };
 constexpr unsigned F_SPILL = 1u << 16;
-// U_SQRT, U_SQUARE, U_INV, U_EXP, U_POW only (translate pass 3): T depends on ONE coordinate (or none), F_AXIS1 says
+// U_SQRT, U_SQUARE, U_EXP, U_POW only (translate pass 3): T depends on ONE coordinate (or none), F_AXIS1 says
 // which; the body then runs on that axis' 5 coefficients instead of all 15
 constexpr unsigned F_UNI = 1u << 17;
 constexpr unsigned F_AXIS1 = 1u << 18;
@@ -91,7 +97,13 @@ struct ValidateParams {
     const double* prim;   // [n_prim][P/32][16][32]: per 32-point stripe, coefficient-major, lanes contiguous
     int n_prim;           // PRIM(p) with p >= n_prim is malformed input
     int P;
+    int P_eval;           // points evaluated (the first P_eval of the grid; a multiple of 128 * NP or == P)
+    // confirmation pass: candidate i of this launch is index[i], i < *n_index (both on the device)
+    const int* index;
+    const unsigned long long* n_index;
+    int* confirm;         // [n, 2] (n_finite, n_votes) of the confirmation pass, or null
     int ns;               // spill slots per lane
+    float t0;             // expansion radius of the round-off majorants
     double tau;
     int min_finite;
     double vote_frac;
@@ -107,7 +119,9 @@ struct ValidateParams {
     // dump-mode outputs
     double* jets;
     double* resid;
-    double* scale;
+    double* scale;        // S: sum of |monomial| of the residual (the scale parity is quoted against)
+    double* scale_maj;    // S~: the decision scale (isotropic majorant at the round-off-inflated partials)
+    float* maj;           // [n, 3, P]: (V, D, W) of the finished jet
 };
 
 __device__ __forceinline__ bool op_is_prim(unsigned b) { return b >= PDE_OP_PRIM0 && b < PDE_OP_PRIM0 + PDE_N_PRIM; }
@@ -206,7 +220,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             case PDE_OP_FN_SQUARE: kind = U_SQUARE; break;
             case PDE_OP_EXP: kind = U_EXP; arg = 0; fn = FN_EXP; break;
             case PDE_OP_FN_EXPNEG: kind = U_EXP; arg = 1; fn = FN_EXPN; break;
-            case PDE_OP_FN_INV: kind = U_INV; fn = FN_INV; break;
+            case PDE_OP_FN_INV: kind = U_RDIV_C; arg = 0; fn = FN_INV; break;          // inv(T) = CONST(0) / T, CONST(0) = 1
             case PDE_OP_FN_POW32: kind = U_POW; arg = 0; fn = FN_POW; slot = 0; break;
             case PDE_OP_FN_POWN32: kind = U_POW; arg = 1; fn = FN_POW; slot = 1; break;
             default: {
@@ -214,7 +228,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                 const double k = c_pow[slot];
                 if (k == 2.0) kind = U_SQUARE;
                 else if (k == 0.5) kind = U_SQRT;
-                else if (k == -1.0) { kind = U_INV; fn = FN_INV; }
+                else if (k == -1.0) { kind = U_RDIV_C; arg = 0; fn = FN_INV; }
                 else { kind = U_POW; arg = slot; fn = FN_POW; }
             }
         }
@@ -275,7 +289,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
                         else { emit(U_NEG, 0); bin_leaf_right(0, bl); }
                     } else if (op_is_prim(bl)) emit(U_RDIV_P, bl - PDE_OP_PRIM0);        // PRIM / T
                     else if (bl == PDE_OP_VAR0 || bl == PDE_OP_VAR1) emit(U_RDIV_V0 + (bl - PDE_OP_VAR0), 0);   // x / T by the quotient recurrence
-                    else { emit(U_INV, 0); bin_leaf_right(2, bl); }                     // c / T = (1 / T) * c
+                    else emit(U_RDIV_C, bl - PDE_OP_CONST0);                            // c / T by the quotient recurrence
                 } else {
                     const int second = rf ? l : r;
                     if (ns >= ns_max) return 2;                  // the second sub-tree's first leaf will spill T
@@ -311,7 +325,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
             case U_ADD_P: case U_SUB_P: case U_MUL_P: case U_DIV_P: case U_RDIV_P: mt = 3u; break;
             case U_ADDV0: case U_SUBV0: case U_MULV0: case U_DIVV0: case U_RDIV_V0: mt |= 1u; break;
             case U_ADDV1: case U_SUBV1: case U_MULV1: case U_DIVV1: case U_RDIV_V1: mt |= 2u; break;
-            case U_SQRT: case U_SQUARE: case U_INV: case U_EXP: case U_POW:
+            case U_SQRT: case U_SQUARE: case U_EXP: case U_POW:
                 if (mt != 3u) uc[k] = w | F_UNI | (mt == 2u ? F_AXIS1 : 0u);
                 break;
             default: break;
@@ -324,6 +338,7 @@ __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc
 template <int N>
 struct PointCtx {
     double x0, x1;
+    float ax0, ax1;       // |x0|, |x1| as float (maj_abs): the V of a coordinate leaf
     const double* prim;   // this point's slot in PRIM(0)'s stripe block: coefficient g at [g * 32]
 };
 
@@ -371,19 +386,43 @@ template <int OFF>
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
     asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v) : "memory");
 }
-// slot element k = coef * NP + point lives at byte offset k * TPB * 8: an immediate of the LDS/STS
-template <int N, int NP, int TPB, int K = 0>
-__device__ __forceinline__ void spill_store(unsigned addr, const Jet<N> (&T)[NP]) {
+template <int OFF>
+__device__ __forceinline__ void lds_f32x2(unsigned addr, float& a, float& b) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(a), "=f"(b) : "r"(addr), "n"(OFF));
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f32x2(unsigned addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "f"(a), "f"(b) : "memory");
+}
+// A spill slot holds NC * NP jet coefficients + 2 NP majorant elements; element k lives at byte offset k * TPB * 8
+// (an immediate of the LDS/STS): coefficient g of point h at k = g * NP + h, the majorants of point h at
+// NC * NP + 2 h (V, D) and NC * NP + 2 h + 1 (W).
+struct Maj;
+template <int N, int NP>
+__host__ __device__ constexpr int spill_slot_elems() { return (Jet<N>::NC + 2) * NP; }
+template <int N, int NP, int TPB, bool MAJ, int K = 0, class M>
+__device__ __forceinline__ void spill_store(unsigned addr, const Jet<N> (&T)[NP], const M (&mj)[NP]) {
     if constexpr (K < Jet<N>::NC * NP) {
         sts_f64<K * TPB * 8>(addr, T[K % NP].c[K / NP]);
-        spill_store<N, NP, TPB, K + 1>(addr, T);
+        spill_store<N, NP, TPB, MAJ, K + 1>(addr, T, mj);
+    } else if constexpr (MAJ && K < spill_slot_elems<N, NP>()) {
+        constexpr int h = (K - Jet<N>::NC * NP) / 2;
+        if constexpr (((K - Jet<N>::NC * NP) & 1) == 0) sts_f32x2<K * TPB * 8>(addr, mj[h].V, mj[h].D);
+        else sts_f32x2<K * TPB * 8>(addr, mj[h].W, 0.0f);
+        spill_store<N, NP, TPB, MAJ, K + 1>(addr, T, mj);
     }
 }
-template <int N, int NP, int TPB, int K = 0>
-__device__ __forceinline__ void spill_load(unsigned addr, Jet<N> (&U)[NP]) {
+template <int N, int NP, int TPB, bool MAJ, int K = 0, class M>
+__device__ __forceinline__ void spill_load(unsigned addr, Jet<N> (&U)[NP], M (&mj)[NP]) {
     if constexpr (K < Jet<N>::NC * NP) {
         U[K % NP].c[K / NP] = lds_f64<K * TPB * 8>(addr);
-        spill_load<N, NP, TPB, K + 1>(addr, U);
+        spill_load<N, NP, TPB, MAJ, K + 1>(addr, U, mj);
+    } else if constexpr (MAJ && K < spill_slot_elems<N, NP>()) {
+        constexpr int h = (K - Jet<N>::NC * NP) / 2;
+        float pad;
+        if constexpr (((K - Jet<N>::NC * NP) & 1) == 0) lds_f32x2<K * TPB * 8>(addr, mj[h].V, mj[h].D);
+        else lds_f32x2<K * TPB * 8>(addr, mj[h].W, pad);
+        spill_load<N, NP, TPB, MAJ, K + 1>(addr, U, mj);
     }
 }
 
@@ -395,11 +434,27 @@ __device__ __forceinline__ void scalar_taylor(unsigned fn, unsigned slot, double
         f[0] = r;
 #pragma unroll
         for (int j = 0; j < N; ++j) f[j + 1] = -f[j] * r;
-    } else if (fn == FN_POW) {           // f_{j+1} = f_j (k - j)/(j + 1) / x
-        const double r = fast_rcp(x);
-        f[0] = pow0(x, c_pow[slot]);
+    } else if (fn == FN_POW) {
+        const int n = c_pow_int[slot];
+        if (n >= 0) {
+            // x**n, n = 0, 1, 2, ...: f_j = C(n, j) x^(n-j) by products only -- exact structure, finite at x = 0
+            // (the ratio recurrence below divides by x: `(2*z - 1)**3` at the reference point z = 1/2 was NaN)
+            int ex = n > N ? n - N : 0;
+            double pw = 1.0, base = x;
+#pragma unroll 1
+            for (int e = ex; e; e >>= 1) { if (e & 1) pw *= base; base *= base; }
 #pragma unroll
-        for (int j = 0; j < N; ++j) f[j + 1] = f[j] * (r * c_frow[slot][j]);
+            for (int j = N; j >= 0; --j) {
+                const int want = n > j ? n - j : 0;
+                if (want > ex) { pw *= x; ex = want; }
+                f[j] = c_fbin[slot][j] * pw;
+            }
+        } else {                         // f_{j+1} = f_j (k - j)/(j + 1) / x
+            const double r = fast_rcp(x);
+            f[0] = pow0(x, c_pow[slot]);
+#pragma unroll
+            for (int j = 0; j < N; ++j) f[j + 1] = f[j] * (r * c_frow[slot][j]);
+        }
     } else {                             // exp(+-x): (+-1)^j exp(+-x) / j!
         const double sg = c_sign[fn == FN_EXPN];
         f[0] = fast_exp(sg * x);
@@ -408,33 +463,138 @@ __device__ __forceinline__ void scalar_taylor(unsigned fn, unsigned slot, double
     }
 }
 
-// Interpret the micro-ops for NP points per lane at once: results in T[0..NP).
+// ---------------------------------------------------------------------------------
+// Round-off majorants (the calculus and its proof sketch: oracle/majorant.py).  Next to every jet the
+// interpreter carries three float32 numbers:  V >= |c_0| (the value, summed WITHOUT cancellation),
+// D >= sum_{n>=1} [C]_n t0^n (the non-constant part of a one-variable majorant series of the jet, evaluated at the
+// radius t0) and W, the same for the accumulated rounding error in units of 2^-52, so that
+// |computed c_g - exact c_g| <= 2^-52 W / t0^|g|.  The residual's decision scale is evaluated at partials inflated by
+// that bound (Residual<>::eval): a point votes "non-zero" only if no float64 evaluation order of an exact solution
+// could have produced its |R|.  float32 because magnitudes need no precision and the FP64 pipe is the bottleneck:
+// the rules run on the FMA / MUFU pipes (approximate reciprocal, log2, exp2: a 1e-4 safety factor covers them);
+// only quotients and compositions convert the ACTUAL value of their operand (one F2F each: the pole distance
+// |d_0| - D needs it).  Overflow gives inf / NaN (the point does not vote).
+// ---------------------------------------------------------------------------------
+struct Maj { float V, D, W; };
+__device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float kMajSlop = 1.0001f;      // MUFU approximations (2^-22 absolute in lg2 / ex2 arguments, 1 ulp in rcp)
+// |x| of a jet's actual value as float, clamped from below so that products of magnitudes cannot flush to zero
+__device__ __forceinline__ float maj_abs(double x) { return fmaxf(__double2float_rn(fabs(x)), 1e-18f); }
+__device__ __forceinline__ Maj maj_leaf(float v, float d, float w) { Maj m; m.V = v; m.D = d; m.W = w; return m; }
+// a +- b
+__device__ __forceinline__ void maj_add(Maj& a, const Maj& b) {
+    a.W = (a.W + b.W) + ((a.V + a.D) + (b.V + b.D));
+    a.V += b.V;
+    a.D += b.D;
+}
+// a * b
+__device__ __forceinline__ void maj_mul(Maj& a, const Maj& b) {
+    const float Ma = a.V + a.D, Mb = b.V + b.D;
+    a.W = fmaf(a.W, Mb, fmaf(Ma, b.W, 16.0f * Ma * Mb));
+    a.D = fmaf(a.V, b.D, a.D * Mb);
+    a.V *= b.V;
+}
+// q = a / d; d0 = |actual value of d|
+__device__ __forceinline__ Maj maj_div(const Maj& a, const Maj& d, float d0) {
+    const float den = d0 - d.D;                               // distance to the pole, in majorant terms
+    const float r = den > 0.0f ? f_rcp(den) * kMajSlop : __int_as_float(0x7f800000);
+    Maj q;
+    q.V = a.V * f_rcp(d0) * kMajSlop;
+    q.D = fmaf(q.V, d.D, a.D) * r;
+    const float Mq = q.V + q.D;
+    q.W = (fmaf(Mq, d.W, a.W) + 16.0f * fmaf(d.D, Mq, a.V + a.D)) * r;
+    return q;
+}
+// F(x): G >= sum |F_j| D^j, G1 >= dG/dD  ->  V = G, D = G1 D, W = G1 W + cF G
+__device__ __forceinline__ void maj_apply(Maj& x, float G, float G1, float cF) {
+    x.W = fmaf(G1, x.W, cF * G);
+    x.D = G1 * x.D;
+    x.V = G;
+}
+// x ** n, n = 0, 1, 2, ... (all binomial coefficients positive: no actual value needed)
+__device__ __forceinline__ void maj_ipow(Maj& x, float n) {
+    const float M = x.V + x.D;
+    const float G = f_ex2(n * f_lg2(M)) * kMajSlop;
+    maj_apply(x, G, n * G * f_rcp(M) * kMajSlop, 16.0f * n);
+}
+__device__ __forceinline__ void maj_square(Maj& x) {
+    const float M = x.V + x.D;
+    maj_apply(x, M * M, 2.0f * M, 32.0f);
+}
+// x ** k for any other constant k; a = |actual value|.  |binom(k, j)| <= binom(|k| + j - 1, j): G = a^k (1 - D/a)^-|k|
+__device__ __forceinline__ void maj_pow(Maj& x, float k, float a) {
+    const float ak = fabsf(k), r = a - x.D;                   // r <= 0: outside the radius -> NaN, the point does not vote
+    const float G = f_ex2(fmaf(k, f_lg2(a), -ak * f_lg2(r * f_rcp(a)))) * kMajSlop;
+    maj_apply(x, G, G * ak * f_rcp(r) * kMajSlop, 64.0f);
+}
+__device__ __forceinline__ void maj_sqrt(Maj& x, float a) {   // k = 1/2: G = a / sqrt(a - D)
+    const float r = a - x.D;
+    const float G = a * f_rsqrt(r) * kMajSlop;
+    maj_apply(x, G, 0.5f * G * f_rcp(r) * kMajSlop, 64.0f);
+}
+// exp(sg * x); x0 = the actual (signed) value
+__device__ __forceinline__ void maj_exp(Maj& x, float sg, float x0) {
+    const float G = f_ex2(fmaf(sg, x0, x.D) * 1.4426950408889634f) * kMajSlop;
+    maj_apply(x, G, G, 64.0f);
+}
+// the scalar-function kinds of U_FNV / U_FNC (fn, slot) applied to a leaf (x0 = its actual value)
+__device__ __forceinline__ void maj_fn(unsigned fn, unsigned slot, float x0, Maj& x) {
+    const float a = fmaxf(fabsf(x0), 1e-18f);
+    if (fn == FN_INV) {
+        x = maj_div(maj_leaf(1.0f, 0.0f, 1.0f), x, a);
+    } else if (fn == FN_POW) {
+        if (c_pow_int[slot] >= 0) maj_ipow(x, c_powf[slot]); else maj_pow(x, c_powf[slot], a);
+    } else {
+        maj_exp(x, fn == FN_EXPN ? -1.0f : 1.0f, x0);
+    }
+}
+
+// Interpret the micro-ops for NP points per lane at once: results in T[0..NP), majorants of the result in MT.
 // uc: shared address of the micro-op words; sp_addr: shared address of this thread's spill column
-// (layout [(slot * NC + coef) * NP + point][thread], conflict free), moved up and down by one slot.
-template <int N, int NP, int TPB>
+// (layout [slot][element][thread], conflict free), moved up and down by one slot.
+// MAJ = false: the majorants are not carried (their arithmetic has no side effects and is dead-code eliminated; the
+// spill / table traffic is compiled out explicitly) -- the fast first pass of pde_validate.
+template <int N, int NP, int TPB, bool MAJ>
 __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
-                                            size_t prim_stride, const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP]) {
+                                            size_t prim_stride, const PointCtx<N> (&cx)[NP], Jet<N> (&T)[NP], Maj (&MT)[NP]) {
     constexpr int NC = Jet<N>::NC;
-    constexpr unsigned kSlotBytes = NC * NP * TPB * 8;
+    constexpr unsigned kSlotBytes = spill_slot_elems<N, NP>() * TPB * 8;
     Jet<N> U[NP];
+    Maj MU[NP];
     double f[NP][N + 1];
+    const float t0 = c_t0;
 #define PDE_EACH for (int h = 0; h < NP; ++h)
 #define PDE_SPILL_IF_FLAGGED                                                                 \
     if (ins_cur & F_SPILL) {                                                                 \
-        spill_store<N, NP, TPB>(sp_addr, T);                                                 \
+        spill_store<N, NP, TPB, MAJ>(sp_addr, T, MT);                                             \
         sp_addr += kSlotBytes;                                                               \
     }
 #define PDE_FETCH_S                                                                          \
     {                                                                                        \
         sp_addr -= kSlotBytes;                                                               \
-        spill_load<N, NP, TPB>(sp_addr, U);                                                  \
+        spill_load<N, NP, TPB, MAJ>(sp_addr, U, MU);                                              \
     }
-#define PDE_FETCH_P                                                                          \
+// PRIM(p): jet rows 0..NC-1 and the (D, W) pair in row 15 of the stripe block; V from the value itself
+#define PDE_LOAD_P(J, M)                                                                     \
     {                                                                                        \
         _Pragma("unroll") PDE_EACH {                                                         \
             const double* from = cx[h].prim + (size_t)arg * prim_stride;                     \
-            _Pragma("unroll") for (int g = 0; g < NC; ++g) U[h].c[g] = __ldg(from + g * 32); \
+            _Pragma("unroll") for (int g = 0; g < NC; ++g) J[h].c[g] = __ldg(from + g * 32); \
+            if (MAJ) {                                                                       \
+                const float2 mj = __ldg(reinterpret_cast<const float2*>(from + 15 * 32));    \
+                M[h] = maj_leaf(maj_abs(J[h].c[0]), mj.x, mj.y);                             \
+            }                                                                                \
         }                                                                                    \
+    }
+#define PDE_FETCH_P PDE_LOAD_P(U, MU)
+// the operand jet of U_RDIV_V*: a coordinate
+#define PDE_U_VAR(X, AX, GSLOT)                                                              \
+    {                                                                                        \
+        const double z = opaque_zero();                                                      \
+        _Pragma("unroll") PDE_EACH { jet_fill(U[h], z); U[h].c[0] = cx[h].X; U[h].c[GSLOT] = c_one; MU[h] = maj_leaf(cx[h].AX, t0, 0.0f); } \
     }
 #pragma unroll 1
     for (;;) {
@@ -451,28 +611,23 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
                 PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x0; T[h].c[1] = c_one; }
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x0; T[h].c[1] = c_one; MT[h] = maj_leaf(cx[h].ax0, t0, 0.0f); }
             } break;
             case U_SETV1: {
                 PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x1; T[h].c[2] = c_one; }
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = cx[h].x1; T[h].c[2] = c_one; MT[h] = maj_leaf(cx[h].ax1, t0, 0.0f); }
             } break;
             case U_SETC: {
                 PDE_SPILL_IF_FLAGGED
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = c_const[arg]; }
+                PDE_EACH { jet_fill(T[h], z); T[h].c[0] = c_const[arg]; MT[h] = maj_leaf(c_constf[arg], 0.0f, c_constf[arg]); }
             } break;
             case U_SETP: {
                 PDE_SPILL_IF_FLAGGED
-#pragma unroll
-                PDE_EACH {
-                    const double* from = cx[h].prim + (size_t)arg * prim_stride;
-#pragma unroll
-                    for (int g = 0; g < NC; ++g) T[h].c[g] = __ldg(from + g * 32);
-                }
+                PDE_LOAD_P(T, MT)
             } break;
             // F(coordinate): the jet of F(x_k + dx_k) is F's Taylor expansion along dx_k
             case U_FNV: {
@@ -480,7 +635,10 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
                 const double z = opaque_zero();
 #pragma unroll
                 PDE_EACH {
-                    scalar_taylor<N>((ins_cur >> 17) & 3u, ins_cur >> 19, arg ? cx[h].x1 : cx[h].x0, f[h]);
+                    const double x = arg ? cx[h].x1 : cx[h].x0;
+                    scalar_taylor<N>((ins_cur >> 17) & 3u, ins_cur >> 19, x, f[h]);
+                    MT[h] = maj_leaf(arg ? cx[h].ax1 : cx[h].ax0, t0, 0.0f);
+                    maj_fn((ins_cur >> 17) & 3u, ins_cur >> 19, __double2float_rn(x), MT[h]);
                     jet_fill(T[h], z);
                     T[h].c[0] = f[h][0];
                     if (arg) {
@@ -498,6 +656,8 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
 #pragma unroll
                 PDE_EACH {
                     scalar_taylor<N>((ins_cur >> 17) & 3u, ins_cur >> 19, c_const[arg], f[h]);
+                    MT[h] = maj_leaf(c_constf[arg], 0.0f, c_constf[arg]);
+                    maj_fn((ins_cur >> 17) & 3u, ins_cur >> 19, __double2float_rn(c_const[arg]), MT[h]);
                     jet_fill(T[h], z);
                     T[h].c[0] = f[h][0];
                 }
@@ -506,98 +666,102 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
             case U_ADD_P: PDE_FETCH_P
             l_add:
 #pragma unroll
-                PDE_EACH jet_add(T[h], U[h]);
+                PDE_EACH { maj_add(MT[h], MU[h]); jet_add(T[h], U[h]); }
                 break;
             case U_SUB_S: PDE_FETCH_S goto l_sub;
             case U_SUB_P: PDE_FETCH_P
             l_sub:
 #pragma unroll
-                PDE_EACH jet_sub(T[h], U[h]);
+                PDE_EACH { maj_add(MT[h], MU[h]); jet_sub(T[h], U[h]); }
                 break;
             case U_RSUB_S: PDE_FETCH_S
 #pragma unroll
-                PDE_EACH jet_rsub(T[h], U[h]);
+                PDE_EACH { maj_add(MT[h], MU[h]); jet_rsub(T[h], U[h]); }
                 break;
             case U_MUL_S: PDE_FETCH_S goto l_mul;
             case U_MUL_P: PDE_FETCH_P
             l_mul:
+#pragma unroll
+                PDE_EACH maj_mul(MT[h], MU[h]);
                 jetv_mul<N, NP>(T, U);
                 break;
             case U_DIV_S: PDE_FETCH_S goto l_div;
             case U_DIV_P: PDE_FETCH_P
             l_div:
+#pragma unroll
+                PDE_EACH MT[h] = maj_div(MT[h], MU[h], maj_abs(U[h].c[0]));
                 jetv_div<N, NP>(T, U);
                 break;
             // U / T: the division runs in place on the numerator U; the copy back is opaque to the
             // register allocator (jet_copy, jet.cuh) and costs 30 moves against 76 FP64 instructions
             case U_RDIV_S: PDE_FETCH_S goto l_rdiv;
-            case U_RDIV_V0: {
+            case U_RDIV_V0: PDE_U_VAR(x0, ax0, 1) goto l_rdiv;
+            case U_RDIV_V1: PDE_U_VAR(x1, ax1, 2) goto l_rdiv;
+            case U_RDIV_C: {
                 const double z = opaque_zero();
 #pragma unroll
-                PDE_EACH { jet_fill(U[h], z); U[h].c[0] = cx[h].x0; U[h].c[1] = c_one; }
-            } goto l_rdiv;
-            case U_RDIV_V1: {
-                const double z = opaque_zero();
-#pragma unroll
-                PDE_EACH { jet_fill(U[h], z); U[h].c[0] = cx[h].x1; U[h].c[2] = c_one; }
+                PDE_EACH { jet_fill(U[h], z); U[h].c[0] = c_const[arg]; MU[h] = maj_leaf(c_constf[arg], 0.0f, c_constf[arg]); }
             } goto l_rdiv;
             case U_RDIV_P: PDE_FETCH_P
             l_rdiv:
+#pragma unroll
+                PDE_EACH MT[h] = maj_div(MU[h], MT[h], maj_abs(T[h].c[0]));
                 jetv_div<N, NP>(U, T);
 #pragma unroll
                 PDE_EACH jet_copy(T[h], U[h]);
                 break;
             case U_ADDC:
 #pragma unroll
-                PDE_EACH T[h].c[0] += c_const[arg];
+                PDE_EACH { maj_add(MT[h], maj_leaf(c_constf[arg], 0.0f, c_constf[arg])); T[h].c[0] += c_const[arg]; }
                 break;
             case U_SUBC:
 #pragma unroll
-                PDE_EACH T[h].c[0] -= c_const[arg];
+                PDE_EACH { maj_add(MT[h], maj_leaf(c_constf[arg], 0.0f, c_constf[arg])); T[h].c[0] -= c_const[arg]; }
                 break;
             case U_RSUBC:
 #pragma unroll
-                PDE_EACH { jet_neg(T[h]); T[h].c[0] += c_const[arg]; }
+                PDE_EACH { maj_add(MT[h], maj_leaf(c_constf[arg], 0.0f, c_constf[arg])); jet_neg(T[h]); T[h].c[0] += c_const[arg]; }
                 break;
+            // T * c and T / c (multiplication by the reciprocal): V' = |c| V, D' = |c| D, W' = |c| (W + 17 M) in both rules
             case U_MULC:
 #pragma unroll
-                PDE_EACH jet_scale(T[h], c_const[arg]);
+                PDE_EACH { const float c = c_constf[arg]; MT[h].W = c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W); MT[h].V *= c; MT[h].D *= c; jet_scale(T[h], c_const[arg]); }
                 break;
             case U_MULRC:
 #pragma unroll
-                PDE_EACH jet_scale(T[h], c_rconst[arg]);
+                PDE_EACH { const float c = c_rconstf[arg]; MT[h].W = c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W); MT[h].V *= c; MT[h].D *= c; jet_scale(T[h], c_rconst[arg]); }
                 break;
             case U_ADDV0:
 #pragma unroll
-                PDE_EACH { T[h].c[0] += cx[h].x0; T[h].c[1] += c_one; }
+                PDE_EACH { maj_add(MT[h], maj_leaf(cx[h].ax0, t0, 0.0f)); T[h].c[0] += cx[h].x0; T[h].c[1] += c_one; }
                 break;
             case U_ADDV1:
 #pragma unroll
-                PDE_EACH { T[h].c[0] += cx[h].x1; T[h].c[2] += c_one; }
+                PDE_EACH { maj_add(MT[h], maj_leaf(cx[h].ax1, t0, 0.0f)); T[h].c[0] += cx[h].x1; T[h].c[2] += c_one; }
                 break;
             case U_SUBV0:
 #pragma unroll
-                PDE_EACH { T[h].c[0] -= cx[h].x0; T[h].c[1] -= c_one; }
+                PDE_EACH { maj_add(MT[h], maj_leaf(cx[h].ax0, t0, 0.0f)); T[h].c[0] -= cx[h].x0; T[h].c[1] -= c_one; }
                 break;
             case U_SUBV1:
 #pragma unroll
-                PDE_EACH { T[h].c[0] -= cx[h].x1; T[h].c[2] -= c_one; }
+                PDE_EACH { maj_add(MT[h], maj_leaf(cx[h].ax1, t0, 0.0f)); T[h].c[0] -= cx[h].x1; T[h].c[2] -= c_one; }
                 break;
             case U_MULV0:
 #pragma unroll
-                PDE_EACH jet_mul_var(T[h], 0, cx[h].x0);
+                PDE_EACH { maj_mul(MT[h], maj_leaf(cx[h].ax0, t0, 0.0f)); jet_mul_var(T[h], 0, cx[h].x0); }
                 break;
             case U_MULV1:
 #pragma unroll
-                PDE_EACH jet_mul_var(T[h], 1, cx[h].x1);
+                PDE_EACH { maj_mul(MT[h], maj_leaf(cx[h].ax1, t0, 0.0f)); jet_mul_var(T[h], 1, cx[h].x1); }
                 break;
             case U_DIVV0:
 #pragma unroll
-                PDE_EACH jet_div_var(T[h], 0, lazy_rcp(cx[h].x0));
+                PDE_EACH { MT[h] = maj_div(MT[h], maj_leaf(cx[h].ax0, t0, 0.0f), cx[h].ax0); jet_div_var(T[h], 0, lazy_rcp(cx[h].x0)); }
                 break;
             case U_DIVV1:
 #pragma unroll
-                PDE_EACH jet_div_var(T[h], 1, lazy_rcp(cx[h].x1));
+                PDE_EACH { MT[h] = maj_div(MT[h], maj_leaf(cx[h].ax1, t0, 0.0f), cx[h].ax1); jet_div_var(T[h], 1, lazy_rcp(cx[h].x1)); }
                 break;
             case U_NEG:
 #pragma unroll
@@ -613,27 +777,33 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
     } else {                                                                    \
         FN<N, NP, -1>(__VA_ARGS__);                                             \
     }
-            case U_SQRT: PDE_BY_AXIS(jetv_sqrt, T) break;
-            case U_SQUARE: PDE_BY_AXIS(jetv_square, T) break;
-            // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
-            // shared in-place Horner body
-            case U_INV:
+            case U_SQRT:
 #pragma unroll
-                PDE_EACH scalar_taylor<N>(FN_INV, 0, T[h].c[0], f[h]);
-                goto l_compose;
+                PDE_EACH maj_sqrt(MT[h], maj_abs(T[h].c[0]));
+                PDE_BY_AXIS(jetv_sqrt, T)
+                break;
+            case U_SQUARE:
+#pragma unroll
+                PDE_EACH maj_square(MT[h]);
+                PDE_BY_AXIS(jetv_square, T)
+                break;
+            // scalar functions: Taylor coefficients of F at T_0 by one ratio recurrence, then the
+            // shared in-place composition body
             case U_EXP:
 #pragma unroll
-                PDE_EACH scalar_taylor<N>(FN_EXP + arg, 0, T[h].c[0], f[h]);
+                PDE_EACH {
+                    scalar_taylor<N>(FN_EXP + arg, 0, T[h].c[0], f[h]);
+                    maj_exp(MT[h], arg ? -1.0f : 1.0f, __double2float_rn(T[h].c[0]));
+                }
                 goto l_compose;
             case U_POW:
 #pragma unroll
-                PDE_EACH scalar_taylor<N>(FN_POW, arg, T[h].c[0], f[h]);
+                PDE_EACH {
+                    scalar_taylor<N>(FN_POW, arg, T[h].c[0], f[h]);
+                    if (c_pow_int[arg] >= 0) maj_ipow(MT[h], c_powf[arg]); else maj_pow(MT[h], c_powf[arg], maj_abs(T[h].c[0]));
+                }
             l_compose:
-#if PDE_COMPOSE_PS
                 PDE_BY_AXIS(jetv_compose_ps, T, U, f)
-#else
-                jetv_compose<N, NP>(T, U, f);
-#endif
                 break;
             default: __builtin_unreachable();
         }
@@ -642,6 +812,8 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
 #undef PDE_SPILL_IF_FLAGGED
 #undef PDE_FETCH_S
 #undef PDE_FETCH_P
+#undef PDE_LOAD_P
+#undef PDE_U_VAR
 #undef PDE_EACH
 }
 
@@ -653,15 +825,25 @@ __device__ __forceinline__ double ldg_early(const double* p) {
     return v;
 }
 
-// Residual operators: R and its round-off scale S from the finished jet.
+// Residual operators: R, the decision scale S~ and (SHARP: parity / tooling mode) the plain scale S from the finished
+// jet.  S = sum of |monomial| bounds the round-off of evaluating R from the partials; S~ >= S also covers the round-off
+// INSIDE the partials: it is the residual's majorant at partials inflated by theta_n = W c_theta[n-1] (oracle/majorant.py
+// "Decision scale"), so |R| <= tau S~ for every float64 evaluation of an exact solution.
 template <int PROBLEM> struct Residual;
+
+// W of a finished jet as the double the thetas are built from.  W = 0 is exact only for a bare coordinate leaf;
+// anywhere else a vanishing W is an underflow of tiny magnitudes: give up (inf: the point does not vote).
+__device__ __forceinline__ double maj_final(float W, bool single_leaf) {
+    return (W < 1e-30f && !single_leaf) ? __longlong_as_double(0x7ff0000000000000LL) : (double)W;
+}
 
 template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
     static constexpr int N = 4;
     static constexpr int COLS = 1;
     // FFV:305-347; entries expanded by tools/gen_residual.py
     __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[1]) { c[0] = ldg_early(tab + pt); }
-    __device__ static __forceinline__ void eval(const Jet<4>& u, const double (&c)[1], double& R, double& S) {
+    template <bool SHARP>
+    __device__ static __forceinline__ void eval(const Jet<4>& u, const double (&c)[1], double Wd, double& R, double& St, double& S) {
         double d[15];
 #pragma unroll
         for (int n = 0; n <= 4; ++n) {
@@ -672,7 +854,20 @@ template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
         double p[4], a[4];
         ff_residual_entries(d, w, p, a);
         R = p[0] * p[3] - p[1] * p[2];       // det M, FFV:347
-        S = a[0] * a[3] + a[1] * a[2];
+        if (SHARP) S = a[0] * a[3] + a[1] * a[2];
+        // isotropic majorant (oracle/majorant.py: iso_tables): every partial of order n replaced by
+        // m_n = sum_{|g| = n} |d_g| + theta_n; one polynomial in m_1..m_4 and |w| instead of 48 monomials
+        const double m1 = fma(Wd, c_theta[0], fabs(d[1]) + fabs(d[2]));
+        const double m2 = fma(Wd, c_theta[1], (fabs(d[3]) + fabs(d[4])) + fabs(d[5]));
+        const double m3 = fma(Wd, c_theta[2], (fabs(d[6]) + fabs(d[7])) + (fabs(d[8]) + fabs(d[9])));
+        const double m4 = fma(Wd, c_theta[3], ((fabs(d[10]) + fabs(d[11])) + (fabs(d[12]) + fabs(d[13]))) + fabs(d[14]));
+        const double aw = fabs(w), m1w = m1 * aw;
+        const double b0 = m1 * fma(4.0, m3, aw * fma(2.0, m2, m1w));                                         // LT_A
+        const double b1 = 8.0 * (m1 * m1) * m2;                                                               // LT_B
+        const double b2 = m1 * fma(m2, fma(8.0, m3, 2.0 * (m2 * aw)),
+                                   m1 * fma(8.0, m4, aw * fma(4.0, m3, aw * fma(4.0, m2, 2.0 * m1w))));       // L2T_A
+        const double b3 = 8.0 * (m1 * m1) * fma(3.0 * m2, m2, 2.0 * (m1 * m3));                               // L2T_B
+        St = fma(b0, b3, b1 * b2);
     }
 };
 
@@ -684,14 +879,18 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
         c[0] = ldg_early(tab + pt); c[1] = ldg_early(tab + P + pt);
         c[2] = ldg_early(tab + 2 * (size_t)P + pt); c[3] = ldg_early(tab + 3 * (size_t)P + pt);
     }
-    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&c)[4], double& R, double& S) {
+    template <bool SHARP>
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&c)[4], double Wd, double& R, double& St, double& S) {
         const double c1 = c[0], c1r = c[1], c2 = c[2], c2x = c[3];
         const double t0 = c1r * u.c[1];
         const double t1 = c1 * (2.0 * u.c[3]);
         const double t2 = c2x * u.c[2];
         const double t3 = c2 * (2.0 * u.c[5]);
         R = (t0 + t1) + (t2 + t3);
-        S = (fabs(t0) + fabs(t1)) + (fabs(t2) + fabs(t3));
+        const double s = (fabs(t0) + fabs(t1)) + (fabs(t2) + fabs(t3));
+        if (SHARP) S = s;
+        const double th1 = Wd * c_theta[0], th2 = Wd * c_theta[1];
+        St = fma(fabs(c1r) + fabs(c2x), th1, fma(fabs(c1) + fabs(c2), th2, s));
     }
 };
 
@@ -702,9 +901,10 @@ template <> struct Residual<kProblemValue> {
     static constexpr int N = 2;
     static constexpr int COLS = 1;
     __device__ static __forceinline__ void fetch(const double*, int, int, double (&c)[1]) { c[0] = 0.0; }
-    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&)[1], double& R, double& S) {
+    template <bool SHARP>
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&)[1], double, double& R, double& St, double& S) {
         R = u.c[0];
-        S = fabs(u.c[1]) + fabs(u.c[2]);
+        St = S = fabs(u.c[1]) + fabs(u.c[2]);
     }
 };
 
@@ -728,17 +928,21 @@ struct WarpPartial {
 template <int N, int NP>
 __host__ __device__ constexpr size_t cta_smem_bytes(int L, int ns, int W) {
     // per warp: code[L] | start[L] | need[L] | frames[2L] | ucode[2L+6] u32 ; then partials[W][4] ; status[W] ;
-    // then spill[ns][NC][NP][32 W] f64   (16-byte aligned pieces)
+    // then spill[ns][(NC + 2) NP][32 W] 8-byte elements   (16-byte aligned pieces)
     return ((size_t)((L + 15) / 16 * 16) * 5 + (size_t)(kUcodeMax(L) * 4 + 15) / 16 * 16) * W +
            (size_t)W * 4 * sizeof(WarpPartial) + 16 * W +
-           (size_t)ns * Jet<N>::NC * NP * 32 * W * 8;
+           (size_t)ns * spill_slot_elems<N, NP>() * 32 * W * 8;
 }
 
 __device__ __forceinline__ void group_barrier(int g) {
     asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 }
 
-template <int PROBLEM, bool DUMP, int W, int NP, int MINB>
+// MAJ = false: first pass, all P points, no round-off majorants (S~ = the residual's isotropic majorant at the
+// computed partials): fast, but its rejections are only PROPOSALS.  MAJ = true with p.index: confirmation pass over the
+// proposed rejections on the first P_eval points with the majorants carried; a rejection stands only if this pass
+// votes it too, everything else gets its survivor bit back.  MAJ = true without p.index: one-pass mode / DUMP.
+template <int PROBLEM, bool DUMP, int W, int NP, int MINB, bool MAJ>
 __global__ void __launch_bounds__(W * 32, MINB)
 validate_kernel(const ValidateParams p) {
     using Res = Residual<PROBLEM>;
@@ -761,14 +965,17 @@ validate_kernel(const ValidateParams p) {
     double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
 
     const unsigned spill_addr = keep_in_register(smem_addr(s_spill));
-    const long long n_chunks = (p.n + 3) / 4;
+    const bool indexed = MAJ && p.index != nullptr;
+    const long long n_items = indexed ? (long long)*p.n_index : p.n;
+    const long long n_chunks = (n_items + 3) / 4;
     for (long long chunk = (long long)blockIdx.x * G + grp; chunk < n_chunks; chunk += (long long)gridDim.x * G) {
         const long long cand0 = chunk * 4;
         // ---- phase 1: every warp of the group stages + translates its own candidate ----
         {
-            const long long cand = cand0 + wg;
+            const long long item = cand0 + wg;
+            const long long cand = (indexed && item < n_items) ? (long long)p.index[item] : item;
             int status = -1;
-            if (cand < p.n) {
+            if (item < n_items) {
                 int len = p.len[cand];
                 if (len > p.L) len = p.L + 1;          // a length beyond the row is malformed input (never read past the row)
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code + (size_t)cand * p.L);
@@ -786,15 +993,17 @@ validate_kernel(const ValidateParams p) {
         group_barrier(grp);
         // ---- phase 2: the group's 4 warps sweep the chunk's candidates together ----
         for (int c = 0; c < 4; ++c) {
-            const long long cand = cand0 + c;
             const int status = s_status[c];
             if (status != 0) continue;
+            const long long cand = indexed ? (long long)p.index[cand0 + c] : cand0 + c;
             const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 5 * Lp));
+            // a bare coordinate / constant / PRIM leaf: the only programs whose round-off majorant W may be exactly 0
+            const bool single_leaf = MAJ && (lds_u32(uc + 4) & 0xffu) == U_END;
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
             const size_t prim_stride = (size_t)p.P * 16;
 #pragma unroll 1
-            for (int stripe = wg * 32 * NP; stripe < p.P; stripe += 128 * NP) {
+            for (int stripe = wg * 32 * NP; stripe < p.P_eval; stripe += 128 * NP) {
                 PointCtx<N> cx[NP];
                 if (NP == 2) {
                     // one 128-bit load per coordinate: two consecutive points per lane
@@ -805,6 +1014,10 @@ validate_kernel(const ValidateParams p) {
                     cx[0].x0 = __ldg(p.pts + stripe + lane);
                     cx[0].x1 = __ldg(p.pts + p.P + stripe + lane);
                 }
+                if (MAJ) {
+#pragma unroll
+                    for (int h = 0; h < NP; ++h) { cx[h].ax0 = maj_abs(cx[h].x0); cx[h].ax1 = maj_abs(cx[h].x1); }
+                }
                 double coef[NP][Res::COLS];
                 int pt[NP];
 #pragma unroll
@@ -814,11 +1027,12 @@ validate_kernel(const ValidateParams p) {
                     Res::fetch(p.tab, p.P, pt[h], coef[h]);      // issued early: latency hides behind the program
                 }
                 Jet<N> T[NP];
-                run_program<N, NP, TPB>(uc, spill_addr, prim_stride, cx, T);
+                Maj MT[NP];
+                run_program<N, NP, TPB, MAJ>(uc, spill_addr, prim_stride, cx, T, MT);
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
-                    double R, S;
-                    Res::eval(T[h], coef[h], R, S);
+                    double R, S, St;
+                    Res::template eval<DUMP>(T[h], coef[h], MAJ ? maj_final(MT[h].W, single_leaf) : 0.0, R, St, S);
                     if (DUMP) {
                         if (p.jets) {
 #pragma unroll
@@ -826,19 +1040,25 @@ validate_kernel(const ValidateParams p) {
                         }
                         if (p.resid) p.resid[(size_t)cand * p.P + pt[h]] = R;
                         if (p.scale) p.scale[(size_t)cand * p.P + pt[h]] = S;
+                        if (p.scale_maj) p.scale_maj[(size_t)cand * p.P + pt[h]] = St;
+                        if (p.maj) {
+                            p.maj[((size_t)cand * 3 + 0) * p.P + pt[h]] = MT[h].V;
+                            p.maj[((size_t)cand * 3 + 1) * p.P + pt[h]] = MT[h].D;
+                            p.maj[((size_t)cand * 3 + 2) * p.P + pt[h]] = MT[h].W;
+                        }
                     } else {
                         const double aR = fabs(R);
-                        const bool fin = (aR <= 1.79769313486231570e308) && (S <= 1.79769313486231570e308) && (S > 0.0);
+                        const bool fin = (aR <= 1.79769313486231570e308) && (St <= 1.79769313486231570e308) && (St > 0.0);
                         if (fin) {
                             ++n_fin;
-                            const double ratio = aR * fast_rcp(S);
-                            n_vote += (aR > p.tau * S) ? 1 : 0;
-                            if (ratio > best_ratio) { best_ratio = ratio; best_S = S; }
+                            const double ratio = aR * fast_rcp(St);
+                            n_vote += (aR > p.tau * St) ? 1 : 0;
+                            if (ratio > best_ratio) { best_ratio = ratio; best_S = St; }
                             max_R = fmax(max_R, aR);
                         }
                         if (p.ref_rs && pt[h] < p.n_ref) {
                             p.ref_rs[((size_t)cand * p.n_ref + pt[h]) * 2 + 0] = R;
-                            p.ref_rs[((size_t)cand * p.n_ref + pt[h]) * 2 + 1] = S;
+                            p.ref_rs[((size_t)cand * p.n_ref + pt[h]) * 2 + 1] = St;
                         }
                     }
                 }
@@ -866,31 +1086,37 @@ validate_kernel(const ValidateParams p) {
         // ---- phase 3: every warp writes the row of the candidate it translated ----
         if (!DUMP && lane == 0) {
             const int c = wg;
-            const long long cand = cand0 + c;
+            const long long item = cand0 + c;
             const int status = s_status[c];
-            if (cand < p.n) {
-                if (status != 0) {
-                    p.ratio_max[cand] = 0.0; p.resid_max[cand] = 0.0; p.scale_at[cand] = 0.0;
-                    p.n_finite[cand] = (status < 0) ? -1 : -1 - status;   // -1 empty, -2 malformed, -3 spill overflow
-                    p.n_votes[cand] = 0;
-                    if (p.ref_rs) for (int k = 0; k < 2 * p.n_ref; ++k) p.ref_rs[(size_t)cand * 2 * p.n_ref + k] = __longlong_as_double(0x7ff8000000000000LL);
-                    atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
-                } else {
-                    WarpPartial t = s_part[c * 4];
+            if (item < n_items) {
+                const long long cand = indexed ? (long long)p.index[item] : item;
+                WarpPartial t = s_part[c * 4];
+                if (status == 0) {
                     for (int w = 1; w < 4; ++w) {
                         const WarpPartial o = s_part[c * 4 + w];
                         t.n_fin += o.n_fin; t.n_vote += o.n_vote;
                         if (o.best_ratio > t.best_ratio) { t.best_ratio = o.best_ratio; t.best_S = o.best_S; }
                         t.max_R = fmax(t.max_R, o.max_R);
                     }
+                }
+                const bool reject = status == 0 && (t.n_fin >= p.min_finite) && (t.n_vote > 0) && ((double)t.n_vote >= p.vote_frac * (double)t.n_fin);
+                if (indexed) {
+                    // confirmation pass: only the verdict (and its evidence) is written; the per-candidate maxima stay those
+                    // of the first pass over the whole grid
+                    if (p.confirm) { p.confirm[2 * cand] = status == 0 ? t.n_fin : -1 - status; p.confirm[2 * cand + 1] = status == 0 ? t.n_vote : 0; }
+                } else if (status != 0) {
+                    p.ratio_max[cand] = 0.0; p.resid_max[cand] = 0.0; p.scale_at[cand] = 0.0;
+                    p.n_finite[cand] = (status < 0) ? -1 : -1 - status;   // -1 empty, -2 malformed, -3 spill overflow
+                    p.n_votes[cand] = 0;
+                    if (p.ref_rs) for (int k = 0; k < 2 * p.n_ref; ++k) p.ref_rs[(size_t)cand * 2 * p.n_ref + k] = __longlong_as_double(0x7ff8000000000000LL);
+                } else {
                     p.ratio_max[cand] = t.best_ratio;
                     p.resid_max[cand] = t.max_R;
                     p.scale_at[cand] = t.best_S;
                     p.n_finite[cand] = t.n_fin;
                     p.n_votes[cand] = t.n_vote;
-                    const bool reject = (t.n_fin >= p.min_finite) && (t.n_vote > 0) && ((double)t.n_vote >= p.vote_frac * (double)t.n_fin);
-                    if (!reject) atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
                 }
+                if (!reject) atomicOr(p.survivor_bits + (cand >> 5), 1u << (cand & 31));
             }
         }
         // no barrier here: a warp only overwrites its OWN status/ucode slot in the next phase 1, and the

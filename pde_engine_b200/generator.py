@@ -127,7 +127,7 @@ class GpuExpressionGenerator:
                 dev = enum.pop("device")
                 enum.pop("device_first", None)
                 out = core.validate(self.session, filt.program, dev["code"], dev["len"], filt.pts, filt.table, None,
-                                    tau=filt.tau, min_finite=filt.min_finite, vote_frac=filt.vote_frac, n_ref=0,
+                                    tau=filt.tau, min_finite=filt.min_finite, vote_frac=filt.vote_frac, t0=filt.t0, confirm_points=filt.confirm_points, n_ref=0,
                                     spill_slots=filt.spill_slots)
                 bits = out["survivor_bits"].cpu().numpy().view(np.uint32)
                 k = np.arange(n)

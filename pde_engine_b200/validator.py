@@ -41,6 +41,7 @@ class BatchVerdict:
         self.n_finite = out["n_finite"]
         self.n_votes = out["n_votes"]
         self.ref_rs = out["ref_rs"]
+        self.confirm = out.get("confirm")          # [n, 2] (n_finite, n_votes) of the confirmation pass, -1 = not re-examined
         bits = out["survivor_bits"].view(np.uint32)
         n = len(self.strs)
         self.survivor = ((bits[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
@@ -55,6 +56,7 @@ class BatchVerdict:
             "n_finite": int(self.n_finite[i]), "n_votes": int(self.n_votes[i]),
             "ratio_max": float(self.ratio_max[i]), "resid_max": float(self.resid_max[i]),
             "scale_at_max": float(self.scale_at[i]),
+            "confirm_pass": None if self.confirm is None else [int(v) for v in self.confirm[i]],
             "ref_points_R_S": None if self.ref_rs is None else [[float(v) for v in row] for row in self.ref_rs[i]],
         }
 
@@ -62,14 +64,15 @@ class BatchVerdict:
 class GpuBatchValidator:
     def __init__(self, cpu_validator: Any = None, problem: str = "force_free", P: int = 4096,
                  tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, L: int = 128,
-                 spill_slots: int = 2, sympify_locals: Optional[dict] = None, device=None):
+                 spill_slots: int = 2, sympify_locals: Optional[dict] = None, device=None, t0: float = core.T0_DEFAULT,
+                 confirm_points: int = core.CONFIRM_POINTS_DEFAULT):
         import torch
         self.cpu_validator = cpu_validator
         self.problem = canonical_slug(problem)
         self.session = core.Session.for_problem(self.problem)
         self.program = core.ResidualProgram.for_problem(self.problem)
         self.P, self.tau, self.min_finite, self.vote_frac = P, tau, min_finite, vote_frac
-        self.L, self.spill_slots = L, spill_slots
+        self.L, self.spill_slots, self.t0, self.confirm_points = L, spill_slots, t0, confirm_points
         self.sympify_locals = sympify_locals
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         pts = collocation_grid(self.problem, P)
@@ -109,6 +112,7 @@ class GpuBatchValidator:
             "n_votes": torch.empty(n, dtype=torch.int32, device=dev),
             "ref_rs": torch.empty((n, 3, 2), dtype=torch.float64, device=dev),
             "survivor_bits": torch.empty((n + 31) // 32, dtype=torch.int32, device=dev),
+            "confirm": torch.empty((n, 2), dtype=torch.int32, device=dev),
         }
         flags = np.zeros(n, np.uint8)
         n_uncompiled = 0
@@ -144,8 +148,8 @@ class GpuBatchValidator:
             copied.record()
             part = {k: (v[lo // 32:(hi + 31) // 32] if k == "survivor_bits" else v[lo:hi]) for k, v in out.items()}
             core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
-                          tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac,
-                          n_ref=3, spill_slots=self.spill_slots, out=part)
+                          tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac, t0=self.t0,
+                          confirm_points=self.confirm_points, n_ref=3, spill_slots=self.spill_slots, out=part)
         host = {}
         for k, v in out.items():
             h = self._pin["host"][k][:v.shape[0]]

@@ -9,8 +9,12 @@ TypeError fallback to the 2-kwarg form), one candidate per task, fresh caches,
 hard per-candidate wall cap (the symbolic zero test takes 0.01 s - >20 min,
 SURVEY 0.5): candidates that hit the cap are recorded as {"timeout": true}.
 
-Usage: python tests/golden/make_golden_verdicts.py force_free 3 15 120
+Usage: python tests/golden/make_golden_verdicts.py force_free 3 15 120 [workers]
        (problem, depth, take every k-th unique, cap seconds)
+
+Resumable: every finished record is appended to $PDE_REF_WORK/verdicts_<problem>_d<depth>.jsonl and
+records already present there (or in the committed fixture, when it was made with the same cap) are
+not recomputed -- the full depth-3 force-free set is ~30 CPU-hours.
 """
 from __future__ import annotations
 
@@ -77,19 +81,36 @@ def _one(s):
 
 def main():
     problem, depth, step, cap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    workers = int(sys.argv[5]) if len(sys.argv) > 5 else min(8, os.cpu_count() or 1)
     enum_file = {"force_free": "enum_force_free_d4", "kerr_magnetosphere": "enum_kerr_magnetosphere_d3"}[problem]
     g = json.load(gzip.open(os.path.join(REPO, "tests", "golden", enum_file + ".json.gz"), "rt"))
     exprs = g["depths"][str(depth)]["uniques"][::step]
     print(len(exprs), "expressions", flush=True)
-    t0 = time.time()
-    with mp.Pool(min(8, os.cpu_count() or 1), initializer=_init, initargs=(problem, cap), maxtasksperchild=20) as pool:
-        recs = []
-        for r in pool.imap(_one, exprs, chunksize=1):
-            recs.append(r)
-            if len(recs) % 20 == 0:
-                print(len(recs), round(time.time() - t0), flush=True)
-    out = {"problem": problem, "depth": depth, "step": step, "cap_seconds": cap, "records": recs}
     path = os.path.join(REPO, "tests", "golden", f"verdicts_{problem}_d{depth}.json")
+    log_path = os.path.join(WORK, f"verdicts_{problem}_d{depth}.jsonl")
+    done = {}
+    if os.path.exists(path):
+        old = json.load(open(path))
+        if old.get("cap_seconds") == cap:
+            done.update({r["s"]: r for r in old["records"]})
+    if os.path.exists(log_path):
+        for line in open(log_path):
+            r = json.loads(line)
+            done[r["s"]] = r
+    todo = [s for s in exprs if s not in done]
+    print(len(done), "already done,", len(todo), "to do,", workers, "workers", flush=True)
+    t0 = time.time()
+    with mp.Pool(workers, initializer=_init, initargs=(problem, cap), maxtasksperchild=20) as pool, open(log_path, "a") as log:
+        k = 0
+        for r in pool.imap_unordered(_one, todo, chunksize=1):
+            done[r["s"]] = r
+            log.write(json.dumps(r) + "\n")
+            log.flush()
+            k += 1
+            if k % 50 == 0:
+                print(k, round(time.time() - t0), flush=True)
+    recs = [done[s] for s in exprs]
+    out = {"problem": problem, "depth": depth, "step": step, "cap_seconds": cap, "records": recs}
     json.dump(out, open(path, "w"), indent=0)
     nv = sum(1 for r in recs if r.get("is_valid"))
     print("wrote", path, "valid", nv, "invalid", sum(1 for r in recs if r.get("is_valid") is False),
