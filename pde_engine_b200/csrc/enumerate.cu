@@ -587,12 +587,13 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
                   int64_t first, int64_t count, int L,
                   int32_t* triple, uint8_t* code, uint8_t* len, uint64_t* hash, void* stream) {
     if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
-    if (!triple || !code || !len || !hash || first < 0 || count < 0) { set_error("pde_enumerate: bad argument"); return PDE_E_INVALID; }
+    if (first < 0 || count < 0) { set_error("pde_enumerate: bad argument"); return PDE_E_INVALID; }
     if (L < 16 || L > kMaxRow || (L % 16) != 0) { set_error("L must be a multiple of 16 in [16, %d]", kMaxRow); return PDE_E_INVALID; }
     EnumParams p;
     int rc = fill_params(e, depth_begin, depth, prune, p);
     if (rc) return rc;
-    if (count == 0) return PDE_OK;
+    if (count == 0) return PDE_OK;           // an empty window is a no-op (its buffers may be null: the reference just moves on, LBF:139-195)
+    if (!triple || !code || !len || !hash) { set_error("pde_enumerate: null output"); return PDE_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     rc = run_count(p, st, nullptr);
     if (rc) return rc;
@@ -612,7 +613,7 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
     if (n == 0) { if (n_unique) *n_unique = 0; return PDE_OK; }      // an empty batch is a no-op (its buffers may be null)
     if (!code || !len || !hash || !first_occurrence || n < 0 || (L % 16) != 0) { set_error("pde_dedup: bad argument"); return PDE_E_INVALID; }
-    if (n >= 0xffffffffLL) { set_error("pde_dedup: n too large"); return PDE_E_OVERFLOW; }
+    if (n > (1LL << 30)) { set_error("pde_dedup: n too large (the 32-bit table index covers 2^30 candidates per call)"); return PDE_E_OVERFLOW; }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned cap = 1024;
     while ((long long)cap < 2 * n) cap <<= 1;

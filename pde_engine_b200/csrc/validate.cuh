@@ -490,26 +490,31 @@ __device__ __forceinline__ void maj_add(Maj& a, const Maj& b) {
     a.V += b.V;
     a.D += b.D;
 }
+// Every rule that rounds clamps its V and W from below: float32 products of small magnitudes would flush to zero
+// and a zero W means "exact" (a coordinate under -x / |x|).  A clamped majorant is merely larger than necessary.
+constexpr float kMajFloor = 1e-30f;
+__device__ __forceinline__ float maj_floor(float x) { return x < kMajFloor ? kMajFloor : x; }    // NaN (outside a radius) stays NaN
 // a * b
 __device__ __forceinline__ void maj_mul(Maj& a, const Maj& b) {
     const float Ma = a.V + a.D, Mb = b.V + b.D;
-    a.W = fmaf(a.W, Mb, fmaf(Ma, b.W, 16.0f * Ma * Mb));
+    a.W = maj_floor(fmaf(a.W, Mb, fmaf(Ma, b.W, 16.0f * Ma * Mb)));
     a.D = fmaf(a.V, b.D, a.D * Mb);
-    a.V *= b.V;
+    a.V = maj_floor(a.V * b.V);
 }
 // q = a / d; d0 = |actual value of d|
 __device__ __forceinline__ Maj maj_div(const Maj& a, const Maj& d, float d0) {
     const float den = d0 - d.D;                               // distance to the pole, in majorant terms
     const float r = den > 0.0f ? f_rcp(den) * kMajSlop : __int_as_float(0x7f800000);
     Maj q;
-    q.V = a.V * f_rcp(d0) * kMajSlop;
+    q.V = maj_floor(a.V * f_rcp(d0) * kMajSlop);
     q.D = fmaf(q.V, d.D, a.D) * r;
     const float Mq = q.V + q.D;
-    q.W = (fmaf(Mq, d.W, a.W) + 16.0f * fmaf(d.D, Mq, a.V + a.D)) * r;
+    q.W = maj_floor((fmaf(Mq, d.W, a.W) + 16.0f * fmaf(d.D, Mq, a.V + a.D)) * r);
     return q;
 }
 // F(x): G >= sum |F_j| D^j, G1 >= dG/dD  ->  V = G, D = G1 D, W = G1 W + cF G
 __device__ __forceinline__ void maj_apply(Maj& x, float G, float G1, float cF) {
+    G = maj_floor(G);
     x.W = fmaf(G1, x.W, cF * G);
     x.D = G1 * x.D;
     x.V = G;
@@ -725,11 +730,11 @@ __device__ __forceinline__ void run_program(unsigned uc, unsigned sp_addr,
             // T * c and T / c (multiplication by the reciprocal): V' = |c| V, D' = |c| D, W' = |c| (W + 17 M) in both rules
             case U_MULC:
 #pragma unroll
-                PDE_EACH { const float c = c_constf[arg]; MT[h].W = c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W); MT[h].V *= c; MT[h].D *= c; jet_scale(T[h], c_const[arg]); }
+                PDE_EACH { const float c = c_constf[arg]; MT[h].W = maj_floor(c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W)); MT[h].V = maj_floor(MT[h].V * c); MT[h].D *= c; jet_scale(T[h], c_const[arg]); }
                 break;
             case U_MULRC:
 #pragma unroll
-                PDE_EACH { const float c = c_rconstf[arg]; MT[h].W = c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W); MT[h].V *= c; MT[h].D *= c; jet_scale(T[h], c_rconst[arg]); }
+                PDE_EACH { const float c = c_rconstf[arg]; MT[h].W = maj_floor(c * fmaf(17.0f, MT[h].V + MT[h].D, MT[h].W)); MT[h].V = maj_floor(MT[h].V * c); MT[h].D *= c; jet_scale(T[h], c_rconst[arg]); }
                 break;
             case U_ADDV0:
 #pragma unroll
@@ -831,11 +836,9 @@ __device__ __forceinline__ double ldg_early(const double* p) {
 // "Decision scale"), so |R| <= tau S~ for every float64 evaluation of an exact solution.
 template <int PROBLEM> struct Residual;
 
-// W of a finished jet as the double the thetas are built from.  W = 0 is exact only for a bare coordinate leaf;
-// anywhere else a vanishing W is an underflow of tiny magnitudes: give up (inf: the point does not vote).
-__device__ __forceinline__ double maj_final(float W, bool single_leaf) {
-    return (W < 1e-30f && !single_leaf) ? __longlong_as_double(0x7ff0000000000000LL) : (double)W;
-}
+// W of a finished jet as the double the thetas are built from (0 = exact: a coordinate under -x / |x|; every
+// rounding rule clamps at kMajFloor, so an underflow cannot pose as exactness)
+__device__ __forceinline__ double maj_final(float W) { return (double)W; }
 
 template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
     static constexpr int N = 4;
@@ -997,8 +1000,6 @@ validate_kernel(const ValidateParams p) {
             if (status != 0) continue;
             const long long cand = indexed ? (long long)p.index[cand0 + c] : cand0 + c;
             const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 5 * Lp));
-            // a bare coordinate / constant / PRIM leaf: the only programs whose round-off majorant W may be exactly 0
-            const bool single_leaf = MAJ && (lds_u32(uc + 4) & 0xffu) == U_END;
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
             const size_t prim_stride = (size_t)p.P * 16;
@@ -1032,7 +1033,7 @@ validate_kernel(const ValidateParams p) {
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
                     double R, S, St;
-                    Res::template eval<DUMP>(T[h], coef[h], MAJ ? maj_final(MT[h].W, single_leaf) : 0.0, R, St, S);
+                    Res::template eval<DUMP>(T[h], coef[h], MAJ ? maj_final(MT[h].W) : 0.0, R, St, S);
                     if (DUMP) {
                         if (p.jets) {
 #pragma unroll

@@ -37,17 +37,29 @@ def _worker(rank, world, port, n_total, q):
     rng = np.random.default_rng(1234)
     surv_all = rng.random(n_total) < 0.3
     hash_all = rng.integers(1, 2 ** 62, size=n_total, dtype=np.int64)
-    hash_all[n_total - 5] = hash_all[3]            # a cross-shard exact duplicate
-    surv_all[3] = surv_all[n_total - 5] = True
+    len_all = rng.integers(1, 40, size=n_total).astype(np.uint8)
+    prog_all = [bytes(rng.integers(1, 255, size=int(k)).astype(np.uint8)) for k in len_all]
+    dup, col, un = n_total - 5, n_total - 9, (7, n_total - 11, n_total - 13)
+    hash_all[dup] = hash_all[3]; len_all[dup] = len_all[3]; prog_all[dup] = prog_all[3]       # a cross-shard exact duplicate
+    hash_all[col] = hash_all[5]; len_all[col] = len_all[5]                                    # a 64-bit COLLISION: same hash and length, other bytes
+    prog_all[col] = bytes((b ^ 1) or 2 for b in prog_all[5])
+    for u in un:                                                                              # not compiled on the device: constant hash, len 0
+        hash_all[u] = 0x1234; len_all[u] = 0; prog_all[u] = b""
+    for i in (3, 5, dup, col) + un:
+        surv_all[i] = True
     surv = surv_all[first:first + count]
     words = np.zeros((count + 31) // 32, dtype=np.uint32)
     for i in np.nonzero(surv)[0]:
         words[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
-    g = gather_survivors(torch.from_numpy(words.view(np.int32)), torch.from_numpy(hash_all[first:first + count].copy()), count)
+    g = gather_survivors(torch.from_numpy(words.view(np.int32)), torch.from_numpy(hash_all[first:first + count].copy()), count,
+                         lens=torch.from_numpy(len_all[first:first + count].copy()))
     if rank == 0:
-        idx, hs = merge_survivors(g)
-        want = [i for i in np.nonzero(surv_all)[0] if i != n_total - 5]   # duplicate keeps the lowest index
-        q.put((idx == [int(i) for i in want], [int(h) for h in hs] == [int(hash_all[i]) for i in want]))
+        idx, hs = merge_survivors(g, fetch_programs=lambda ids: [prog_all[i] for i in ids])
+        want = [i for i in np.nonzero(surv_all)[0] if i != dup]   # only the byte-identical duplicate goes (lowest index stays)
+        idx_nofetch, _ = merge_survivors(g)                      # without programs nothing is merged
+        q.put((idx == [int(i) for i in want] and all(u in idx for u in un) and col in idx and
+               idx_nofetch == [int(i) for i in np.nonzero(surv_all)[0]],
+               [int(h) for h in hs] == [int(hash_all[i]) for i in want]))
     else:
         assert g is None
     dist.barrier()
@@ -80,3 +92,61 @@ def test_grids_match_oracle():
         assert np.array_equal(a.T, b)
     with pytest.raises(ValueError):
         collocation_grid("nope", 64)
+
+
+def _fake_local(self, strs, compile_threads=None):
+    """Stand-in for the device filter (no GPU in the CPU suite): a deterministic verdict row per string."""
+    from pde_engine_b200.validator import BatchVerdict
+    n = len(strs)
+    h = np.array([sum(s.encode()) for s in strs], dtype=np.int64).reshape(n)
+    surv = (h % 3) != 0
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    for i in np.flatnonzero(surv):
+        bits[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    out = {"ratio_max": h * 0.5, "resid_max": h * 0.25, "scale_at": h * 2.0, "n_finite": (h % 97).astype(np.int32),
+           "n_votes": (h % 13).astype(np.int32), "ref_rs": np.repeat(h.astype(np.float64), 6).reshape(n, 3, 2),
+           "confirm": np.stack([h % 5, h % 7], axis=1).astype(np.int32), "survivor_bits": bits.view(np.int32)}
+    return BatchVerdict(strs, (h % 2).astype(np.uint8), out)
+
+
+def _serve_worker(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pde_engine_b200.validator import GpuBatchValidator
+    GpuBatchValidator._prefilter_local = _fake_local
+    gv = object.__new__(GpuBatchValidator)          # the protocol only: no device behind it
+    gv.group, gv.device = "auto", torch.device("cpu")
+    strs = [f"rho**{k} + z*{k % 17}" for k in range(5003)]
+    if rank == 0:
+        bv = gv.prefilter(strs)                      # dealt out to both ranks
+        small = gv.prefilter(strs[:100])             # below SHARD_MIN: stays on rank 0, no collective
+        gv.shutdown()
+        want = _fake_local(gv, strs)
+        same = all(np.array_equal(getattr(bv, k), getattr(want, k)) for k in
+                   ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "confirm", "survivor", "flags"))
+        q.put((same, bv.strs == strs, len(small.strs) == 100))
+    else:
+        served = gv.serve()
+        assert served == 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_prefilter_protocol_gloo_world2():
+    """GpuBatchValidator.prefilter under torch.distributed: rank 0 deals contiguous shards, rank 1 sits in serve(), the
+    gathered verdict rows equal the single-process result, shutdown() releases the worker."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_serve_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok == (True, True, True)

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import pde_engine_b200 as pb
-from pde_engine_b200.distributed import gather_survivors, merge_survivors, shard_range
+from pde_engine_b200.distributed import enumerated_program_fetcher, gather_survivors, merge_survivors, shard_range
 from pde_engine_b200.grids import collocation_grid
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -44,19 +44,22 @@ def run(first, count):
 
 first, count = shard_range(n, rank, world)
 cand, out = run(first, count)
-g = gather_survivors(out["survivor_bits"], cand["hash"], count)
+g = gather_survivors(out["survivor_bits"], cand["hash"], count, lens=cand["len"])
 if rank == 0:
-    idx, hs = merge_survivors(g)
+    idx, hs = merge_survivors(g, fetch_programs=enumerated_program_fetcher(es, db, 4, True, 128))
     cand_all, out_all = run(0, n)
     bits = out_all["survivor_bits"].cpu().numpy().view(np.uint32)
     k = np.arange(n)
     surv = ((bits[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool)
     h = cand_all["hash"].cpu().numpy()
-    # single-GPU reference of merge_survivors: survivors in order, first occurrence of every hash
+    # single-GPU reference of merge_survivors: survivors in order, first occurrence of every PROGRAM (pde_dedup's
+    # byte-confirmed first-occurrence flags restricted to the survivors; uncompiled candidates are never merged)
+    code_all, len_all = cand_all["code"].cpu().numpy(), cand_all["len"].cpu().numpy()
     seen, want_idx = set(), []
     for i in np.nonzero(surv)[0]:
-        if int(h[i]) not in seen:
-            seen.add(int(h[i]))
+        key = bytes(code_all[i, :len_all[i]])
+        if len_all[i] == 0 or key not in seen:
+            seen.add(key)
             want_idx.append(int(i))
     assert idx == want_idx, (len(idx), len(want_idx))
     assert hs == [int(h[i]) for i in want_idx]
