@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3600, help="trees in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--confirm-points", type=int, default=256,
+    ap.add_argument("--confirm-points", type=int, default=128,
                     help="points of the confirmation pass with round-off majorants (0: one pass with majorants on all points)")
     return ap.parse_args()
 

@@ -197,7 +197,7 @@ int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][
  * default 1/8) is the radius the majorant series are evaluated at: points
  * closer than t0 to a pole of a sub-expression do not vote.
  *
- * Two passes (confirm_points > 0, a multiple of 128; default 256): carrying the
+ * Two passes (confirm_points > 0, a multiple of 128; default 128): carrying the
  * majorants costs about a fifth of the kernel's throughput, and a rejection is
  * sound as soon as the majorant rule votes it on ANY sufficiently large set of
  * points.  Pass 1 therefore sweeps all P points WITHOUT majorants (theta = 0)

@@ -24,7 +24,7 @@ N_CONST, N_POW = 128, 64
 T0_DEFAULT = 0.0625
 # points of the confirmation pass (include/pde_b200.h): carrying the majorants costs ~1/5 of the kernel's throughput, so the
 # whole grid is swept without them and only the proposed rejections are re-examined with them on a sub-grid
-CONFIRM_POINTS_DEFAULT = 256
+CONFIRM_POINTS_DEFAULT = 128
 
 
 def _np_ptr(a: np.ndarray):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib.pde_abi_version() == 2
+    assert _lib.lib.pde_abi_version() == 3
 
 
 def test_opcode_tables_agree():
@@ -55,7 +55,7 @@ def test_no_cpu_fallback_without_device():
     sess = pb.Session.for_problem("force_free")
     prog = pb.ResidualProgram.for_problem("force_free")
     out = _lib.ValidateOut()
-    rc = _lib.lib.pde_validate(sess._h, prog._h, None, None, 0, 48, None, None, None, 0, 64, 1e-10, 8, 0.5, 3, 4,
+    rc = _lib.lib.pde_validate(sess._h, prog._h, None, None, 0, 48, None, None, None, 0, 64, 1e-10, 8, 0.5, 0.0625, 0, 3, 4,
                                ctypes.byref(out), None)
     assert rc == _lib.PDE_E_NODEVICE
     assert b"no CPU fallback" in _lib.lib.pde_last_error()

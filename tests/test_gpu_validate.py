@@ -90,6 +90,7 @@ def _compare_points(dev, oracle, strs, order, fin_agree=0.995, report=None):
     deg = np.array([i + j for i, j in J.multi_indices(order)])
     t0 = Mj.T0_DEFAULT
     n_R = n_J = n_J_tight = 0
+    w_ratio = []
     worst = dict(R_over_S=0.0, R_over_St=0.0, J_over_mag=0.0, J_over_bound=0.0)
     for i, o in enumerate(oracle):
         if o is None:
@@ -132,14 +133,22 @@ def _compare_points(dev, oracle, strs, order, fin_agree=0.995, report=None):
             # the device's majorants are the oracle's rules in float32: never materially below them, rarely far above
             fw = ok & np.isfinite(W) & (W > 1e-25) & (W < 1e30)
             if fw.any():
-                assert np.all(gW[fw] >= 0.98 * W[fw]), strs[i]
-                assert np.median(np.abs(gW[fw] / W[fw] - 1.0)) < 2e-2, strs[i]      # 1e-4 safety factor per rule + MUFU approximations
+                # float32 rules: a pole distance `a - D` computed next to the radius of convergence cancels, so single points
+                # may sit a few per cent off the float64 rules in either direction (they carry a huge W and do not vote);
+                # the tightness statement is therefore global (below), the per-string one only excludes a gross underestimate
+                assert np.all(gW[fw] >= 0.9 * W[fw]), strs[i]
+                w_ratio.append(gW[fw] / W[fw])
             fs = fw & np.isfinite(St) & np.isfinite(gSt) & (St > 0)
             if fs.any():                      # the decision scale: the same polynomial of the same inflated partials; S~ is of
                 # degree <= 6 in theta, so the device's safety factors (0.2 % on theta, 1e-4 per majorant rule) show 6-fold:
                 # never materially below the oracle's, and close to it
                 assert np.all(gSt[fs] >= 0.9 * St[fs]) and np.median(gSt[fs] / St[fs]) < 1.5, strs[i]
     assert n_J_tight >= 0.999 * n_J, (n_J_tight, n_J)
+    if w_ratio:
+        wr = np.concatenate(w_ratio)
+        # 1e-4 safety factor per rule + MUFU approximations: the device's W is the oracle's to ~1 % on the bulk of the points
+        assert np.median(np.abs(wr - 1.0)) < 2e-2 and np.mean(wr < 0.98) < 1e-3 and np.mean(wr > 1.5) < 1e-2, \
+            (float(np.median(np.abs(wr - 1.0))), float(np.mean(wr < 0.98)), float(np.mean(wr > 1.5)))
     if report is not None:
         report.update(worst, n_R=n_R, n_J=n_J, n_J_tight=n_J_tight)
     print(f"parity: {n_R} residual points, worst |dR|/S {worst['R_over_S']:.2e}, |dR|/S~ {worst['R_over_St']:.2e}; "
