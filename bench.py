@@ -30,6 +30,9 @@ if REPO not in sys.path:
 METRIC = "candidate_x_point_fp64_jet_evals_per_sec"
 UNIT = "evals/s"
 NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+# validate_kernel's DRAM traffic from the committed ncu --set full capture (read + written bytes / trees of that launch)
+TRAFFIC_BYTES_PER_TREE = 55.2
+TRAFFIC_SOURCE = "profiles/r1b_validate_full_metrics.csv (ncu --set full, 200 000 trees: dram__bytes_read.sum 11.03 MB, dram__bytes_write.sum 0)"
 
 
 def parse_args():
@@ -45,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3600, help="trees in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-wall", type=float, default=45.0,
+                    help="seconds given to the reference's own validator pool (cpu_baseline_reference; 0 = skip)")
     ap.add_argument("--confirm-points", type=int, default=128,
                     help="points of the confirmation pass with round-off majorants (0: one pass with majorants on all points)")
     return ap.parse_args()
@@ -132,7 +137,24 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.ref_wall > 0:
+        line["cpu_baseline_reference"] = cpu_baseline_reference(args.ref_wall)
     _emit(line)
+
+
+def cpu_baseline_reference(wall_s):
+    """The reference's OWN validator pool (SymPy) on this box: `--validators os.cpu_count()` from a copy of
+    baseline/_ref with the one-line worker import repair, bounded to wall_s seconds (tools/ref_cpu_baseline.py)."""
+    try:
+        from tools import ref_cpu_baseline as rb
+        if not rb.available():
+            return {"unavailable": "baseline/_ref (the reference's code, made by tools/refcopy.py) is not in this snapshot"}
+        r = rb.run_reference_validators("force_free", 3, os.cpu_count() or 1, wall_s)
+        r["sample"] = (f"{r['rows_validated']} rows of the reference's own depth <= 3 force-free run validated by its "
+                       f"{r['validators']} validator processes in {r['wall_s']} s (1 test point per row, FFV:296-297)")
+        return r
+    except Exception as e:
+        return {"error": repr(e)[:300]}
 
 
 # ------------------------------------------------------------------ clocks
@@ -295,6 +317,33 @@ def run_ours(args):
                "h2d_bytes_per_step": int(code_h.numel() + len_h.numel()),
                "d2h_bytes_per_step": int(bits_h.numel() * 4 + nfin_h.numel() * 4 + ratio_h.numel() * 8)}
 
+    # ---- strong scaling of the same metric: the headline batch size IN TOTAL, 1/N of it per GPU ----
+    strong = None
+    if world > 1:
+        ns_ = (n // world) // 32 * 32
+        code_s, len_s, hash_s = trees["code"][:ns_], trees["len"][:ns_], trees["hash"][:ns_]
+        out_s = None
+
+        def strong_step():
+            nonlocal out_s
+            out_s = pb.validate(sess, prog, code_s, len_s, pts_t, tab_t, prim_t, tau=1e-10, min_finite=8, vote_frac=0.5,
+                                confirm_points=args.confirm_points, n_ref=3, spill_slots=2, out=out_s)
+            gather_survivors(out_s["survivor_bits"], hash_s, ns_)
+
+        strong_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            strong_step()
+        b.record()
+        barrier()
+        sms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "total_trees": ns_ * world, "trees_per_gpu": ns_, "ms_per_step": float(sms.item()) / args.steps,
+                  "value": world * ns_ * P * args.steps / (float(sms.item()) * 1e-3), "unit": UNIT,
+                  "note": "same kernel, same grid, the headline batch size in total: every rank validates the first 1/N of its resident trees and the step ends with the same survivor gather"}
+
     # ---- second BASELINE metric: depth-4 validation wall time ----
     import gzip
     depth4 = None
@@ -314,18 +363,23 @@ def run_ours(args):
             gather_survivors(torch.zeros((cnt4 + 31) // 32, dtype=torch.int32, device=dev),
                              torch.zeros(cnt4, dtype=torch.int64, device=dev), cnt4)
         barrier()
-        # (1) the public API path: GpuBatchValidator.prefilter = host compile pipelined with the device (chunks)
+        # (1) the public API path: GpuBatchValidator.prefilter = host compile pipelined with the device (chunks).
+        # At N > 1 it is driven exactly as the engine would drive it: rank 0 holds ALL the strings and calls
+        # prefilter(), ranks > 0 sit in serve(); the strings travel as one byte blob, every rank compiles and
+        # validates its contiguous shard, the verdict rows are gathered on rank 0 (the only exchange).
         from pde_engine_b200.validator import GpuBatchValidator
         gv4 = GpuBatchValidator(None, "force_free", P=P, device=dev)
-        gv4.prefilter(mine)          # warm-up at full size: the validator's pinned staging buffers are grown once and reused
+        tp0 = tp1 = 0.0
+        if rank == 0:
+            gv4.prefilter(uniq4)          # warm-up at full size: the validator's pinned staging buffers are grown once and reused
+            gv4.prefilter(uniq4)
+            tp0 = time.perf_counter()
+            bv4 = gv4.prefilter(uniq4)
+            tp1 = time.perf_counter()     # rank 0 returns after the gather: the wall of the whole job
+            gv4.shutdown()
+        else:
+            gv4.serve()
         barrier()
-        tp0 = time.perf_counter()
-        bv4 = gv4.prefilter(mine)
-        if world > 1:
-            gather_survivors(torch.zeros((cnt4 + 31) // 32, dtype=torch.int32, device=dev),
-                             torch.zeros(cnt4, dtype=torch.int64, device=dev), cnt4)
-        barrier()
-        tp1 = time.perf_counter()
         # (2) the same work step by step, for the breakdown
         t0 = time.perf_counter()
         es4 = sess.compile(mine)                                    # host compiler: strings -> bytecode
@@ -345,16 +399,17 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         nsurv = int(sum(bin(int(x) & 0xffffffff).count("1") for x in bits4.tolist()))
-        assert nsurv == int(bv4.survivor.sum()), "pipelined and one-shot filters disagree"
         tot = torch.tensor([nsurv, int((nf4 < 0).sum())], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
+        if rank == 0:
+            assert int(tot[0]) == int(bv4.survivor.sum()), "the API path (sharded, pipelined) and the one-shot shards disagree"
         depth4 = {"input": "143461 force-free depth-4 unique strings (tests/golden/enum_force_free_d4.json.gz)",
                   "n": len(uniq4), "points": P, "wall_ms_host_strings_to_survivor_bits": float(w[0]),
                   "unpipelined_wall_ms": float(w[3]), "host_compile_ms": float(w[1]), "kernel_ms": float(w[2]),
                   "survivors_for_cpu_confirmation": int(tot[0]), "not_device_evaluable": int(tot[1]),
                   "host_threads": min(os.cpu_count() or 1, 16),
-                  "note": "span A = GpuBatchValidator.prefilter (the public batch entry): host compile (multi-threaded C++ parser), H2D, kernel, D2H of all per-candidate outputs (+ the survivor gather at N > 1), max over ranks; every rank compiles and validates its own contiguous shard of the strings; host_compile_ms / kernel_ms / unpipelined_wall_ms are the same work done step by step"}
+                  "note": "span A = GpuBatchValidator.prefilter on rank 0 (the public batch entry, all strings on rank 0's host): at N > 1 the strings go to the ranks in serve() as one byte blob, every rank compiles (multi-threaded C++ parser, cores / N threads) and validates its contiguous shard (H2D, kernel, D2H of all per-candidate outputs), the verdict rows are gathered on rank 0; host_compile_ms / kernel_ms / unpipelined_wall_ms are the same work done step by step on each rank's shard, max over ranks"}
     except Exception as e:   # the fixture is optional for the headline metric
         depth4 = {"error": repr(e)[:200]}
 
@@ -498,9 +553,11 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
-                         # DRAM bytes per launch: 55.2 B per tree from the ncu --set full capture
-                         # (profiles/r1b_validate_full_metrics.csv: 11.03 MB read / 0 written per 200 k trees)
-                         "traffic": 55.2 * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
+                         # DRAM bytes per launch, from the ncu --set full capture of this kernel (not measured in this
+                         # run: a profiler cannot run inside the bench): dram__bytes_read.sum + dram__bytes_write.sum per
+                         # 200 k trees, scaled per tree
+                         "traffic": TRAFFIC_BYTES_PER_TREE * n, "traffic_unit": "bytes per launch (HBM idle: kernel is FP64-pipe bound)",
+                         "traffic_source": TRAFFIC_SOURCE,
                          "peak_source": "measured: pde_fp64_peak register-resident DFMA chains on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
                          # context: a DFMA that reads three different register pairs (acc += a_i * b_j, the operand
@@ -511,6 +568,10 @@ def run_ours(args):
             "survivor_fraction": float((out["survivor_bits"].view(torch.uint8).cpu().numpy().view("uint8")
                                         .reshape(-1, 1) >> np.arange(8) & 1).sum() / n),
             "evaluated_fraction": float((nf >= 0).float().mean().item()),
+            "survivor_note": "about half of the random depth-5 trees 'survive': they are NaN on most of the grid or depend on one "
+                             "coordinate only (every monomial of the determinant vanishes), i.e. undecidable for a numerical filter; "
+                             "the kernel has no early exit, every tree is evaluated at every point (evaluated_fraction)",
+            "strong_scaling": strong,
             "depth4_validation": depth4,
             "kerr_depth3_validation": kerr3,
             "function_fingerprints_depth4": fp_info,
@@ -520,6 +581,8 @@ def run_ours(args):
             v, dt, ns = cpu_baseline(args.cpu_sample, P, args.depth, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"first {ns} trees of the same batch x {P} points, oracle (numpy) port, {dt:.1f} s"}
+            if args.ref_wall > 0:
+                line["cpu_baseline_reference"] = cpu_baseline_reference(args.ref_wall)
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

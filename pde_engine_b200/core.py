@@ -95,23 +95,35 @@ class Session:
     def compile(self, strs: Sequence[str]) -> "ExprSet":
         return ExprSet(self, strs)
 
+    def compile_blob(self, blob: bytes, n: int) -> "ExprSet":
+        return ExprSet(self, None, blob, n)
+
+
+def pack_strings(strs: Sequence[str]) -> Tuple[bytes, int]:
+    """(blob of NUL-terminated strings, count): the input format of pde_compile_exprs_packed."""
+    n = len(strs)
+    return (("\0".join(strs) + "\0").encode() if n else b""), n
+
 
 class ExprSet:
     """Term-structured postfix bytecode of a list of expression strings."""
 
-    def __init__(self, session: Session, strs: Sequence[str]):
+    def __init__(self, session: Session, strs: Optional[Sequence[str]], blob: Optional[bytes] = None, n: Optional[int] = None):
+        """`strs`, or (strs=None) a ready blob of n NUL-terminated strings (`pack_strings`): what travels between
+        ranks in the sharded prefilter, so a worker never builds Python string objects."""
         self.session = session
-        self.n = len(strs)
+        if blob is None:
+            blob, n = pack_strings(strs)
+        self.n = int(n)
         # one NUL-separated blob + the offsets of the strings in it (found with two vectorised numpy passes):
         # building a ctypes array of 10^5 char pointers costs more than compiling the strings
-        blob = ("\0".join(strs) + "\0").encode() if self.n else b"\0"
         ends = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0) if self.n else np.zeros(0, np.int64)
         if len(ends) != self.n:
             raise ValueError("expression strings must not contain NUL")
         off = np.zeros(self.n + 1, dtype=np.uint32)
         off[1:] = ends + 1
         h = C.c_void_p()
-        check(lib.pde_compile_exprs_packed(session._h, blob, _np_ptr(off), self.n, C.byref(h)))
+        check(lib.pde_compile_exprs_packed(session._h, bytes(blob) if not isinstance(blob, bytes) else blob, _np_ptr(off), self.n, C.byref(h)))
         self._h = h
 
     def __del__(self):

@@ -39,8 +39,8 @@ from .grids import canonical_slug, collocation_grid
 class BatchVerdict:
     """Host copy of one pde_validate call."""
 
-    def __init__(self, strs: Sequence[str], flags: np.ndarray, out: Dict[str, np.ndarray]):
-        self.strs = list(strs)
+    def __init__(self, strs: Optional[Sequence[str]], flags: np.ndarray, out: Dict[str, np.ndarray], n: Optional[int] = None):
+        self.strs = list(strs) if strs is not None else None       # None: a worker's shard (rank 0 holds the strings)
         self.flags = flags
         self.ratio_max = out["ratio_max"]
         self.resid_max = out["resid_max"]
@@ -50,7 +50,7 @@ class BatchVerdict:
         self.ref_rs = out["ref_rs"]
         self.confirm = out.get("confirm")          # [n, 2] (n_finite, n_votes) of the confirmation pass, -1 = not re-examined
         bits = out["survivor_bits"].view(np.uint32)
-        n = len(self.strs)
+        n = len(self.strs) if self.strs is not None else int(n)
         self.survivor = ((bits[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
 
     @property
@@ -127,10 +127,8 @@ class GpuBatchValidator:
         d = self._dist()
         if d is None or len(strs) < self.SHARD_MIN:
             return self._prefilter_local(strs)
-        dist, grp, rank, world = d
-        if rank != 0:
+        if d[2] != 0:
             raise RuntimeError("GpuBatchValidator.prefilter is driven from rank 0; ranks > 0 call serve()")
-        dist.broadcast_object_list([("prefilter", strs)], src=0, group=grp)
         return self._sharded_prefilter(strs, d)
 
     def serve(self) -> int:
@@ -139,31 +137,56 @@ class GpuBatchValidator:
         d = self._dist()
         if d is None or d[2] == 0:
             return 0
-        dist, grp, rank, world = d
         served = 0
-        while True:
-            box = [None]
-            dist.broadcast_object_list(box, src=0, group=grp)
-            cmd, payload = box[0]
-            if cmd == "stop":
-                return served
-            if cmd == "prefilter":
-                self._sharded_prefilter(payload, d)
-                served += 1
+        while self._sharded_prefilter(None, d) is not False:
+            served += 1
+        return served
 
     def shutdown(self) -> None:
         """Rank 0: release the workers from `serve()`."""
         d = self._dist()
         if d is not None and d[2] == 0:
-            d[0].broadcast_object_list([("stop", None)], src=0, group=d[1])
+            import torch
+            dist, grp, rank, world = d
+            hdr = torch.zeros(world + 2, dtype=torch.int64, device=self._comm_device(dist, grp))
+            dist.broadcast(hdr, src=0, group=grp)
 
-    def _sharded_prefilter(self, strs: List[str], d) -> Optional[BatchVerdict]:
+    def _comm_device(self, dist, grp):
+        import torch
+        return self.device if dist.get_backend(grp) == "nccl" else torch.device("cpu")
+
+    def _sharded_prefilter(self, strs: Optional[List[str]], d):
+        """One sharded batch.  Rank 0 passes the strings; workers pass None and get them from rank 0 as ONE byte blob
+        (NUL-terminated strings, the compiler's own input format): header [cmd, n, bytes of shard 0..world-1], then the
+        payload.  Pickling the string list instead cost 44 + 25 ms for the 143 461 depth-4 uniques -- more than
+        compiling and validating them.  Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
         import torch
         from .distributed import shard_range
         dist, grp, rank, world = d
-        n = len(strs)
+        cdev = self._comm_device(dist, grp)
+        hdr = torch.zeros(world + 2, dtype=torch.int64, device=cdev)
+        blobs = None
+        if rank == 0:
+            n = len(strs)
+            blobs = [core.pack_strings(strs[f:f + c])[0] for f, c in (shard_range(n, r, world) for r in range(world))]
+            hdr = torch.tensor([1, n] + [len(b) for b in blobs], dtype=torch.int64).to(cdev)
+        dist.broadcast(hdr, src=0, group=grp)
+        h = hdr.cpu().tolist()
+        if h[0] == 0:
+            return False
+        n, sizes_b = int(h[1]), [int(x) for x in h[2:]]
+        if rank == 0:
+            payload = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(cdev)
+        else:
+            payload = torch.empty(sum(sizes_b), dtype=torch.uint8, device=cdev)
+        dist.broadcast(payload, src=0, group=grp)
         first, count = shard_range(n, rank, world)
-        bv = self._prefilter_local(strs[first:first + count], compile_threads=max(1, (os.cpu_count() or 1) // world))
+        if rank == 0:
+            bv = self._prefilter_local(strs[first:first + count], compile_threads=max(1, (os.cpu_count() or 1) // world), blob=blobs[0])
+        else:
+            lo = sum(sizes_b[:rank])
+            mine = payload[lo:lo + sizes_b[rank]].cpu().numpy().tobytes()
+            bv = self._prefilter_local(None, compile_threads=max(1, (os.cpu_count() or 1) // world), blob=mine, n=count)
         # one float64 row per candidate: 5 scalars + ref_rs (6) + confirm (2) + survivor + flags
         rows = np.zeros((count, 15))
         for k, name in enumerate(self._COLS):
@@ -174,9 +197,8 @@ class GpuBatchValidator:
         rows[:, 14] = bv.flags
         sizes = [shard_range(n, r, world)[1] for r in range(world)]
         nmax = max(sizes)
-        dev = self.device if dist.get_backend(grp) == "nccl" else torch.device("cpu")
-        pad = torch.zeros((nmax, 15), dtype=torch.float64, device=dev)
-        pad[:count] = torch.from_numpy(rows).to(dev)
+        pad = torch.zeros((nmax, 15), dtype=torch.float64, device=cdev)
+        pad[:count] = torch.from_numpy(rows).to(cdev)
         got = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
         dist.gather(pad, got, dst=0, group=grp)
         if rank != 0:
@@ -193,7 +215,8 @@ class GpuBatchValidator:
         out["survivor_bits"] = bits.view(np.int32)
         return BatchVerdict(strs, allr[:, 14].astype(np.uint8), out)
 
-    def _prefilter_local(self, expr_strs: Sequence[str], compile_threads: Optional[int] = None) -> BatchVerdict:
+    def _prefilter_local(self, expr_strs: Optional[Sequence[str]], compile_threads: Optional[int] = None,
+                         blob: Optional[bytes] = None, n: Optional[int] = None) -> BatchVerdict:
         """This device's filter for a batch of expression strings (normalised uniques).
 
         Very large batches go in chunks: the host compiler (multi-threaded C++, the GIL is released) works on
@@ -202,8 +225,8 @@ class GpuBatchValidator:
         Few, large parts: 32 k chunks were slower than one shot (smaller chunks parse on fewer threads and fill the
         device less evenly)."""
         import torch
-        strs = list(expr_strs)
-        n = len(strs)
+        strs = list(expr_strs) if expr_strs is not None else None      # None: a worker's shard, known only as `blob`
+        n = len(strs) if strs is not None else int(n)
         dev = self.device
         if compile_threads is not None:      # N ranks share the host's cores: cap the parser's thread pool (read per call by the library)
             os.environ["PDE_B200_COMPILE_THREADS"] = str(compile_threads)
@@ -229,6 +252,7 @@ class GpuBatchValidator:
         else:
             step = max(n, 1)
         copied = None                      # event: the previous chunk's H2D copies have left the staging buffers
+        ends = None
         # pinned staging buffers, grown on demand and reused: pageable copies of the 18 MB of programs and the
         # 12 MB of results cost several milliseconds each way
         cap = min(step, max(n, 1))
@@ -238,7 +262,15 @@ class GpuBatchValidator:
                          "host": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}, "out_n": n}
         for lo in range(0, n, step):
             hi = min(lo + step, n)
-            exprs = self.session.compile(strs[lo:hi])
+            if blob is None:
+                exprs = self.session.compile(strs[lo:hi])
+            else:                              # byte range of strings lo..hi-1 in the blob
+                if ends is None:
+                    ends = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0) + 1 if n else np.zeros(0, np.int64)
+                    if len(ends) != n:
+                        raise ValueError("blob does not hold n NUL-terminated strings")
+                b0 = int(ends[lo - 1]) if lo else 0
+                exprs = self.session.compile_blob(blob[b0:int(ends[hi - 1])] if (lo or hi < n) else blob, hi - lo)
             code_h, len_h = self._pin["code"][:hi - lo], self._pin["len"][:hi - lo]
             if copied is not None:
                 copied.synchronize()       # (not the kernel: only the copies out of the staging buffers)
@@ -260,7 +292,7 @@ class GpuBatchValidator:
             host[k] = h
         torch.cuda.current_stream().synchronize()
         host = {k: v.numpy().copy() for k, v in host.items()}      # the staging buffers are reused by the next call
-        bv = BatchVerdict(strs, flags, host)
+        bv = BatchVerdict(strs, flags, host, n=n)
         self.stats["gpu_evaluated"] += n
         self.stats["gpu_rejected"] += int(bv.rejected.sum())
         self.stats["not_compilable"] += n_uncompiled

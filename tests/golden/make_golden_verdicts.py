@@ -9,8 +9,11 @@ TypeError fallback to the 2-kwarg form), one candidate per task, fresh caches,
 hard per-candidate wall cap (the symbolic zero test takes 0.01 s - >20 min,
 SURVEY 0.5): candidates that hit the cap are recorded as {"timeout": true}.
 
-Usage: python tests/golden/make_golden_verdicts.py force_free 3 15 120 [workers]
+Usage: python tests/golden/make_golden_verdicts.py force_free 3 15 120 [workers] [wall budget in seconds]
        (problem, depth, take every k-th unique, cap seconds)
+
+With a wall budget the run stops scheduling when it is spent and writes what is finished; the fixture always holds
+EVERY record made so far with this cap (union over all strides used, in enumeration order).
 
 Resumable: every finished record is appended to $PDE_REF_WORK/verdicts_<problem>_d<depth>.jsonl and
 records already present there (or in the committed fixture, when it was made with the same cap) are
@@ -82,9 +85,11 @@ def _one(s):
 def main():
     problem, depth, step, cap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     workers = int(sys.argv[5]) if len(sys.argv) > 5 else min(8, os.cpu_count() or 1)
+    budget = float(sys.argv[6]) if len(sys.argv) > 6 else float("inf")
     enum_file = {"force_free": "enum_force_free_d4", "kerr_magnetosphere": "enum_kerr_magnetosphere_d3"}[problem]
     g = json.load(gzip.open(os.path.join(REPO, "tests", "golden", enum_file + ".json.gz"), "rt"))
-    exprs = g["depths"][str(depth)]["uniques"][::step]
+    uniques = g["depths"][str(depth)]["uniques"]
+    exprs = uniques[::step]
     print(len(exprs), "expressions", flush=True)
     path = os.path.join(REPO, "tests", "golden", f"verdicts_{problem}_d{depth}.json")
     log_path = os.path.join(WORK, f"verdicts_{problem}_d{depth}.jsonl")
@@ -109,8 +114,14 @@ def main():
             k += 1
             if k % 50 == 0:
                 print(k, round(time.time() - t0), flush=True)
-    recs = [done[s] for s in exprs]
-    out = {"problem": problem, "depth": depth, "step": step, "cap_seconds": cap, "records": recs}
+            if time.time() - t0 > budget:
+                print("wall budget spent after", k, "records", flush=True)
+                pool.terminate()
+                break
+    recs = [done[s] for s in uniques if s in done]
+    strides = sorted(set([step] + [int(x) for x in str(old.get("step", "")).split("+") if x.isdigit()])) if os.path.exists(path) else [step]
+    out = {"problem": problem, "depth": depth, "step": "+".join(str(x) for x in strides), "cap_seconds": cap,
+           "n_uniques": len(uniques), "records": recs}
     json.dump(out, open(path, "w"), indent=0)
     nv = sum(1 for r in recs if r.get("is_valid"))
     print("wrote", path, "valid", nv, "invalid", sum(1 for r in recs if r.get("is_valid") is False),

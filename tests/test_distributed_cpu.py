@@ -94,9 +94,15 @@ def test_grids_match_oracle():
         collocation_grid("nope", 64)
 
 
-def _fake_local(self, strs, compile_threads=None):
-    """Stand-in for the device filter (no GPU in the CPU suite): a deterministic verdict row per string."""
+def _fake_local(self, strs, compile_threads=None, blob=None, n=None):
+    """Stand-in for the device filter (no GPU in the CPU suite): a deterministic verdict row per string.  A worker
+    rank gets its shard as the byte blob rank 0 broadcast (strs is None), rank 0 gets both."""
     from pde_engine_b200.validator import BatchVerdict
+    if blob is not None:
+        from_blob = blob.decode().split("\0")[:-1]
+        assert strs is None or list(strs) == from_blob
+        assert n is None or n == len(from_blob)
+        strs = from_blob
     n = len(strs)
     h = np.array([sum(s.encode()) for s in strs], dtype=np.int64).reshape(n)
     surv = (h % 3) != 0

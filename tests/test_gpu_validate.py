@@ -91,6 +91,8 @@ def _compare_points(dev, oracle, strs, order, fin_agree=0.995, report=None):
     t0 = Mj.T0_DEFAULT
     n_R = n_J = n_J_tight = 0
     w_ratio = []
+    st_ratio = []
+    n_fin_pts = n_fin_diff = 0
     worst = dict(R_over_S=0.0, R_over_St=0.0, J_over_mag=0.0, J_over_bound=0.0)
     for i, o in enumerate(oracle):
         if o is None:
@@ -100,8 +102,13 @@ def _compare_points(dev, oracle, strs, order, fin_agree=0.995, report=None):
         with np.errstate(all="ignore"):
             fin_o = np.isfinite(u).all(axis=0)
             fin_g = np.isfinite(gj).all(axis=0)
-            # same finiteness pattern (the domain policy: NaN where SymPy goes complex)
-            assert (fin_o == fin_g).mean() > fin_agree, strs[i]
+            # same finiteness pattern (the domain policy: NaN where SymPy goes complex).  The two arithmetics overflow
+            # in different INTERMEDIATES (the device forms F's scalar Taylor coefficients x0**(k - j) before the
+            # composition, the oracle runs the quotient recurrence on the jet: `exp(big)**(-3/2)` is inf * 0 = NaN on
+            # the device and 0 in numpy), so single points of a string may differ; globally they are rare (below)
+            assert (fin_o == fin_g).mean() > min(fin_agree, 0.9), strs[i]
+            n_fin_pts += fin_o.size
+            n_fin_diff += int((fin_o != fin_g).sum())
             ok = fin_o & fin_g & np.isfinite(gW)
             if not ok.any():
                 continue
@@ -140,15 +147,21 @@ def _compare_points(dev, oracle, strs, order, fin_agree=0.995, report=None):
                 w_ratio.append(gW[fw] / W[fw])
             fs = fw & np.isfinite(St) & np.isfinite(gSt) & (St > 0)
             if fs.any():                      # the decision scale: the same polynomial of the same inflated partials; S~ is of
-                # degree <= 6 in theta, so the device's safety factors (0.2 % on theta, 1e-4 per majorant rule) show 6-fold:
-                # never materially below the oracle's, and close to it
-                assert np.all(gSt[fs] >= 0.9 * St[fs]) and np.median(gSt[fs] / St[fs]) < 1.5, strs[i]
+                # degree <= 6 in theta, so the device's safety factors (0.2 % on theta, 1e-4 per majorant rule) and the float32
+                # cancellation next to a radius of convergence show 6-fold: never materially below the oracle's (per string),
+                # close to it on the bulk of the points (global, below)
+                assert np.all(gSt[fs] >= 0.9 * St[fs]), strs[i]
+                st_ratio.append(gSt[fs] / St[fs])
     assert n_J_tight >= 0.999 * n_J, (n_J_tight, n_J)
+    assert n_fin_diff <= (1.0 - fin_agree) * 0.1 * n_fin_pts, (n_fin_diff, n_fin_pts)      # e.g. <= 0.05 % of the points at fin_agree = 0.995
     if w_ratio:
         wr = np.concatenate(w_ratio)
         # 1e-4 safety factor per rule + MUFU approximations: the device's W is the oracle's to ~1 % on the bulk of the points
         assert np.median(np.abs(wr - 1.0)) < 2e-2 and np.mean(wr < 0.98) < 1e-3 and np.mean(wr > 1.5) < 1e-2, \
             (float(np.median(np.abs(wr - 1.0))), float(np.mean(wr < 0.98)), float(np.mean(wr > 1.5)))
+    if st_ratio:
+        sr = np.concatenate(st_ratio)
+        assert np.median(sr) < 1.1 and np.mean(sr > 2.0) < 2e-2, (float(np.median(sr)), float(np.mean(sr > 2.0)))
     if report is not None:
         report.update(worst, n_R=n_R, n_J=n_J, n_J_tight=n_J_tight)
     print(f"parity: {n_R} residual points, worst |dR|/S {worst['R_over_S']:.2e}, |dR|/S~ {worst['R_over_St']:.2e}; "
