@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 3
+#define PDE_B200_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------- */
 #define PDE_OK            0
@@ -177,6 +177,48 @@ int  pde_program_info(const pde_program *p, int *jet_order, int *n_coef, int *n_
  * Kerr [P,4] = G/(1-x^2), d_r(G/(1-x^2)), G/Delta, d_x(G/Delta)  (column major [cols][P]) */
 int  pde_program_point_table(const pde_program *p, const double *pts_host /*[2][P]*/, int P,
                              double *table_host /*[cols][P]*/);
+
+/* ------------------------------------------------------------------------
+ * Run-time residual programs (BASELINE north_star item 3: "each problem's PDE
+ * residual operator is compiled once into device bytecode").  The reference's
+ * plugin seam is ProblemSpec.validator (problems/__init__.py:34-63); a plugin
+ * states its PDE as a SymPy formula over a generic u (KerrMagnetosphereValidator._lhs,
+ * problems/kerr_magnetosphere/validator.py:77-91; det M, problems/force_free/validator.py:305-347).
+ * pde_engine_b200/residual_compiler.py turns such a formula -- a polynomial in
+ * the partial derivatives of u whose coefficients depend only on the point --
+ * into a straight-line scalar program; this entry takes the program, and
+ * pde_validate / pde_eval_points interpret it after the candidate's jet.  A new
+ * plugin therefore needs no CUDA and no rebuild (PDE_PROBLEM_FORCE_FREE / _KERR
+ * remain as build-time specialisations of the same two residuals).
+ *
+ * Machine (csrc/validate.cuh): a file F of float64 per lane + one accumulator.
+ *   F[0 .. n_coef)              d_g = the partial derivatives of u, g = jidx(i, j) = (i+j)(i+j+1)/2 + j
+ *                               for d^(i+j) u / d x0^i d x1^j  (n_coef = 6 for order 2, 15 for order 4)
+ *   F[n_coef .. + n_cols)       the point's row of the coefficient table (caller-computed, [n_cols][P])
+ *   F[.. + n_consts)            consts
+ *   F[.. n_file)                temporaries
+ * Word = op | a << 4 | b << 12 | dst << 20 | neg << 28   (neg: the a operand is negated)
+ *   MUL   F[dst] = F[a] * F[b]          ACC0  acc = F[a] * F[b]        ACC   acc = fma(F[a], F[b], acc)
+ *   LDA   acc = F[a]                    ADDA  acc = acc + F[a]         STA   F[dst] = acc
+ *   OUT   R = acc (last word)
+ * The same program run on magnitudes (|d_g| + theta_|g|, |column|, |const|, no
+ * signs) gives the decision scale S~ (see pde_validate); with theta = 0 the
+ * plain scale S = sum of |monomial|.  Compile-time checks: every operand is an
+ * input or a temporary written earlier, dst is a temporary, the program ends
+ * with OUT, n_file <= PDE_R_MAX_FILE.  jet_order is 2 or 4.
+ * ---------------------------------------------------------------------- */
+enum pde_residual_op {
+    PDE_R_END = 0, PDE_R_MUL = 1, PDE_R_ACC0 = 2, PDE_R_ACC = 3, PDE_R_LDA = 4, PDE_R_STA = 5, PDE_R_ADDA = 6, PDE_R_OUT = 7
+};
+#define PDE_R_WORD(op, a, b, dst, neg) \
+    ((uint32_t)(op) | ((uint32_t)(a) << 4) | ((uint32_t)(b) << 12) | ((uint32_t)(dst) << 20) | ((uint32_t)((neg) ? 1 : 0) << 28))
+#define PDE_R_MAX_WORDS  2048
+#define PDE_R_MAX_CONSTS 16
+#define PDE_R_MAX_COLS   8
+#define PDE_R_MAX_FILE   51      /* order 4: three spill slots of 17 elements at 16 warps per CTA */
+#define PDE_PROBLEM_PROGRAM 3    /* pde_program_info reports it for programs made by the entry below */
+int  pde_compile_residual_program(int jet_order, int n_cols, const double *consts, int n_consts,
+                                  const uint32_t *words, int n_words, pde_program **out);
 
 /* ------------------------------------------------------------------------
  * Stage 2: the batched validator.

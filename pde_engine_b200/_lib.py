@@ -69,6 +69,7 @@ _sig("pde_enumerate", c_int, c_void_p, P(C.c_int32), c_int, c_int, c_int64, c_in
 _sig("pde_dedup", c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, P(c_int64), c_void_p)
 _sig("pde_synth_trees", c_int, C.c_uint64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_compile_residual", c_int, c_int, P(c_double), c_int, P(c_void_p))
+_sig("pde_compile_residual_program", c_int, c_int, c_int, P(c_double), c_int, P(C.c_uint32), c_int, P(c_void_p))
 _sig("pde_program_free", None, c_void_p)
 _sig("pde_program_info", c_int, c_void_p, P(c_int), P(c_int), P(c_int))
 _sig("pde_program_point_table", c_int, c_void_p, c_void_p, c_int, c_void_p)
@@ -86,7 +87,7 @@ EXPORTED = [
     "pde_session_create", "pde_session_free", "pde_session_tables", "pde_session_const_key", "pde_session_pow_key",
     "pde_compile_exprs", "pde_compile_exprs_packed", "pde_exprset_free", "pde_exprset_size", "pde_exprset_export", "pde_exprset_programs",
     "pde_enumerate_count", "pde_enumerate", "pde_dedup", "pde_synth_trees",
-    "pde_compile_residual", "pde_program_free", "pde_program_info", "pde_program_point_table",
+    "pde_compile_residual", "pde_compile_residual_program", "pde_program_free", "pde_program_info", "pde_program_point_table",
     "pde_validate", "pde_eval_points", "pde_fingerprint", "pde_fp64_peak", "pde_fp64_peak_3op",
 ]
 

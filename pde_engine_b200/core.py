@@ -15,6 +15,7 @@ from ._lib import lib, check
 
 # problem ids (include/pde_b200.h)
 PROBLEM_FORCE_FREE = 0
+PROBLEM_PROGRAM = 3          # run-time residual program (pde_compile_residual_program)
 PROBLEM_KERR = 1
 
 N_CONST, N_POW = 128, 64
@@ -167,12 +168,16 @@ class ExprSet:
 class ResidualProgram:
     """A problem's PDE residual operator, compiled once (FFV:305-347 / KV:77-91)."""
 
-    def __init__(self, problem_id: int, consts: Sequence[float] = ()):
-        arr = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
-        h = C.c_void_p()
-        check(lib.pde_compile_residual(problem_id, arr, len(consts), C.byref(h)))
+    def __init__(self, problem_id: int, consts: Sequence[float] = (), _handle=None, table_fn=None):
+        if _handle is None:
+            arr = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
+            h = C.c_void_p()
+            check(lib.pde_compile_residual(problem_id, arr, len(consts), C.byref(h)))
+        else:
+            h = _handle
         self._h = h
         self.problem_id = problem_id
+        self._table_fn = table_fn          # run-time programs: the front end computes the coefficient table
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         check(lib.pde_program_info(h, C.byref(a), C.byref(b), C.byref(c)))
         self.order, self.n_coef, self.cols = a.value, b.value, c.value
@@ -185,6 +190,27 @@ class ResidualProgram:
             return ResidualProgram(PROBLEM_KERR, (1.0, 0.1))
         raise ValueError(f"Unknown problem '{slug}'")
 
+    @staticmethod
+    def from_words(order: int, n_cols: int, consts: Sequence[float], words: Sequence[int], table_fn=None) -> "ResidualProgram":
+        """A run-time residual program (pde_compile_residual_program; residual_compiler.py makes the words)."""
+        ca = (C.c_double * max(1, len(consts)))(*[float(c) for c in consts])
+        wa = (C.c_uint32 * max(1, len(words)))(*[int(w) for w in words])
+        h = C.c_void_p()
+        check(lib.pde_compile_residual_program(int(order), int(n_cols), ca, len(consts), wa, len(words), C.byref(h)))
+        return ResidualProgram(PROBLEM_PROGRAM, (), _handle=h, table_fn=table_fn)
+
+    @staticmethod
+    def builtin_as_program(slug: str) -> "ResidualProgram":
+        """The force-free / Kerr residual as a run-time program in the schedule of its CUDA specialisation
+        (residual_programs.py, generated by tools/gen_residual.py); the coefficient table is the built-in's."""
+        from . import residual_programs as rp
+        ff = slug in ("force_free", "forcefree", "foliation", "foliations")
+        d = rp.FORCE_FREE if ff else rp.KERR
+        builtin = ResidualProgram.for_problem(slug)
+        prog = ResidualProgram.from_words(d["order"], d["n_cols"], d["consts"], d["words"], table_fn=builtin.point_table)
+        prog._keep = builtin
+        return prog
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
@@ -192,6 +218,8 @@ class ResidualProgram:
 
     def point_table(self, pts: np.ndarray) -> np.ndarray:
         """pts [2, P] float64 (SoA) -> [cols, P]"""
+        if self._table_fn is not None:
+            return np.ascontiguousarray(self._table_fn(pts), dtype=np.float64)
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         assert pts.ndim == 2 and pts.shape[0] == 2
         tab = np.zeros((self.cols, pts.shape[1]))

@@ -7,8 +7,9 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 OUT=../libpde_b200.so
 # --jump-table-density: the interpreter's dense micro-op switch becomes one indexed branch (brx.idx)
 $NVCC $FLAGS --jump-table-density=${PDE_JTD:-25} ${PDE_PTXAS_V:+-Xptxas -v} -c pde_b200.cu -o pde_b200.o &
+$NVCC $FLAGS --jump-table-density=${PDE_JTD:-25} ${PDE_PTXAS_V:+-Xptxas -v} -c program.cu -o program.o &
 $NVCC $FLAGS ${PDE_PTXAS_V:+-Xptxas -v} -c enumerate.cu -o enumerate.o &
 $NVCC $FLAGS -x cu -c compiler.cpp -o compiler.o &
 wait
-$NVCC -shared -o $OUT pde_b200.o enumerate.o compiler.o -lcudart
+$NVCC -shared -o $OUT pde_b200.o program.o enumerate.o compiler.o -lcudart
 echo "built $(realpath $OUT)"

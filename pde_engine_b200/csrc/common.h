@@ -72,4 +72,17 @@ struct pde_program {
     int n_coef = 0;
     int cols = 0;
     double consts[4] = {0, 0, 0, 0};
+    // PDE_PROBLEM_PROGRAM: the run-time residual program (pde_compile_residual_program)
+    std::vector<uint32_t> words;
+    std::vector<double> prog_consts;
+    int n_file = 0;
 };
+
+// program.cu: stage 2 with a run-time residual program (its own instantiations of the kernel and its own tables)
+struct pde_validate_out;
+namespace pde {
+struct ValidateParams;
+int program_validate(const pde_session* s, const pde_program* p, const ValidateParams& vp, const pde_validate_out* out,
+                     int confirm_points, double tau, double t0, void* stream);
+int program_eval_points(const pde_session* s, const pde_program* p, const ValidateParams& vp, double tau, double t0, void* stream);
+}

@@ -57,7 +57,7 @@ __device__ __forceinline__ double fast_sqrt(double x, double& half_rsqrt) {
 // n = rint(x log2 e) by the 2^52+2^51 trick, r = x - n ln2 (two-term Cody-Waite), Taylor to degree 13
 // on |r| <= ln2/2 (remainder 4e-18 relative), scaled by 2^n in two halves so that overflow gives inf
 // and underflow is gradual.  NaN propagates; |x| > 750 is clamped first (exp is 0 / inf there).
-__constant__ double c_expc[16] = {
+static __constant__ double c_expc[16] = {
     1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
     6.93147180369123816490e-01, 1.90821492927058770002e-10};     // ln2 hi / lo

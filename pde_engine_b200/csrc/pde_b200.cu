@@ -6,9 +6,11 @@
 #include <stdlib.h>
 #include <atomic>
 #include <cmath>
+#include <vector>
 
 #include "common.h"
 #include "validate.cuh"
+#include "launch.cuh"
 
 namespace pde {
 
@@ -116,21 +118,6 @@ fingerprint_kernel(const double* __restrict__ values, long long n, int P, int dr
     }
 }
 
-// Proposed rejections of the first pass (cleared survivor bits) -> index list for the confirmation pass.
-// Order is whatever the atomics give: every output of the confirmation pass is addressed by candidate.
-__global__ void __launch_bounds__(256)
-compact_rejects_kernel(const unsigned* __restrict__ bits, long long n, int* __restrict__ index, unsigned long long* __restrict__ count) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool rej = i < n && !((bits[i >> 5] >> (i & 31)) & 1u);
-    const unsigned b = __ballot_sync(0xffffffffu, rej);
-    if (!b) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (rej) index[base + __popc(b & ((1u << lane) - 1u))] = (int)i;
-}
-
 }  // namespace pde
 
 using namespace pde;
@@ -216,6 +203,49 @@ int pde_compile_residual(int problem_id, const double* consts, int n_consts, pde
     return PDE_OK;
 }
 
+int pde_compile_residual_program(int jet_order, int n_cols, const double* consts, int n_consts,
+                                 const uint32_t* words, int n_words, pde_program** out) {
+    if (!out || !words || n_words < 1 || (n_consts > 0 && !consts)) { set_error("pde_compile_residual_program: bad argument"); return PDE_E_INVALID; }
+    if (jet_order != 2 && jet_order != 4) { set_error("jet_order must be 2 or 4 (the instantiated jet algebras)"); return PDE_E_INVALID; }
+    if (n_cols < 0 || n_cols > PDE_R_MAX_COLS || n_consts < 0 || n_consts > PDE_R_MAX_CONSTS || n_words > PDE_R_MAX_WORDS) {
+        set_error("residual program exceeds the limits (cols %d/%d, consts %d/%d, words %d/%d)", n_cols, PDE_R_MAX_COLS, n_consts, PDE_R_MAX_CONSTS, n_words, PDE_R_MAX_WORDS);
+        return PDE_E_OVERFLOW;
+    }
+    const int nc = (jet_order + 1) * (jet_order + 2) / 2, first_tmp = nc + n_cols + n_consts;
+    // abstract run: operands are inputs or temporaries written earlier; dst is a temporary; the program ends with OUT
+    std::vector<char> defined(256, 0);
+    for (int k = 0; k < first_tmp; ++k) defined[k] = 1;
+    int n_file = first_tmp;
+    bool acc_set = false, ended = false;
+    for (int i = 0; i < n_words; ++i) {
+        const uint32_t w = words[i];
+        const unsigned op = w & 15u, a = (w >> 4) & 255u, b = (w >> 12) & 255u, d = (w >> 20) & 255u;
+        if (ended) { set_error("residual program: word %d follows OUT", i); return PDE_E_INVALID; }
+        auto need = [&](unsigned k) { return k < 256 && defined[k]; };
+        auto dst_ok = [&](unsigned k) { return (int)k >= first_tmp && k < PDE_R_MAX_FILE; };
+        bool ok = true;
+        switch (op) {
+            case PDE_R_MUL: ok = need(a) && need(b) && dst_ok(d); if (ok) { defined[d] = 1; if ((int)d + 1 > n_file) n_file = d + 1; } break;
+            case PDE_R_ACC0: ok = need(a) && need(b); acc_set = true; break;
+            case PDE_R_ACC: ok = need(a) && need(b) && acc_set; break;
+            case PDE_R_LDA: ok = need(a); acc_set = true; break;
+            case PDE_R_ADDA: ok = need(a) && acc_set; break;
+            case PDE_R_STA: ok = acc_set && dst_ok(d); if (ok) { defined[d] = 1; if ((int)d + 1 > n_file) n_file = d + 1; } break;
+            case PDE_R_OUT: ok = acc_set; ended = true; break;
+            default: ok = false;
+        }
+        if (!ok) { set_error("residual program: word %d (op %u a %u b %u dst %u) reads an undefined entry, writes an input, or has no accumulator", i, op, a, b, d); return PDE_E_INVALID; }
+    }
+    if (!ended) { set_error("residual program does not end with OUT"); return PDE_E_INVALID; }
+    pde_program* p = new pde_program();
+    p->problem = PDE_PROBLEM_PROGRAM;
+    p->order = jet_order; p->n_coef = nc; p->cols = n_cols; p->n_file = n_file;
+    p->words.assign(words, words + n_words);
+    p->prog_consts.assign(consts, consts + n_consts);
+    *out = p;
+    return PDE_OK;
+}
+
 void pde_program_free(pde_program* p) { delete p; }
 
 int pde_program_info(const pde_program* p, int* jet_order, int* n_coef, int* n_point_cols) {
@@ -228,6 +258,10 @@ int pde_program_info(const pde_program* p, int* jet_order, int* n_coef, int* n_p
 
 int pde_program_point_table(const pde_program* p, const double* pts, int P, double* tab) {
     if (!p || !pts || !tab || P <= 0) { set_error("pde_program_point_table: bad argument"); return PDE_E_INVALID; }
+    if (p->problem == PDE_PROBLEM_PROGRAM) {
+        set_error("pde_program_point_table: the table of a run-time residual program is computed by its front end (residual_compiler.py)");
+        return PDE_E_INVALID;
+    }
     if (p->problem == PDE_PROBLEM_FORCE_FREE) {
         for (int i = 0; i < P; ++i) tab[i] = 1.0 / pts[i];     // w = 1/rho  (FFV:319: u_rho/rho)
     } else {
@@ -252,74 +286,7 @@ int pde_program_point_table(const pde_program* p, const double* pts, int P, doub
 
 }  // extern "C"
 
-// ------------------------------------------------------------- stage 2
-static int upload_tables(const pde_session* s, double tau, double t0, cudaStream_t st) {
-    double cv[PDE_N_CONST], pv[PDE_N_POW];
-    pde_session_tables(s, cv, nullptr, pv, nullptr);
-    double rv[PDE_N_CONST];
-    for (int i = 0; i < PDE_N_CONST; ++i) rv[i] = 1.0 / cv[i];
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_const, cv, sizeof(cv), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconst, rv, sizeof(rv), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow, pv, sizeof(pv), 0, cudaMemcpyHostToDevice, st));
-    // Taylor-ratio rows: x**k has f_{j+1}/f_j = (k - j)/(j + 1) / x_0
-    double fr[kNRows][4];
-    for (int sl = 0; sl < kNRows; ++sl) {
-        for (int j = 0; j < 4; ++j) fr[sl][j] = (pv[sl] - j) / (j + 1);
-    }
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_frow, fr, sizeof(fr), 0, cudaMemcpyHostToDevice, st));
-    // x**n, n = 0, 1, 2, ... <= 64: binomial coefficients C(n, 0..4) (the division-free Taylor coefficients)
-    int pi[kNRows];
-    double fb[kNRows][5];
-    for (int sl = 0; sl < kNRows; ++sl) {
-        const double k = pv[sl];
-        pi[sl] = (k >= 0.0 && k <= 64.0 && k == floor(k)) ? (int)k : -1;
-        fb[sl][0] = 1.0;
-        for (int j = 0; j < 4; ++j) fb[sl][j + 1] = fb[sl][j] * (k - j) / (j + 1);
-    }
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_pow_int, pi, sizeof(pi), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_fbin, fb, sizeof(fb), 0, cudaMemcpyHostToDevice, st));
-    // round-off majorants: theta_n / W = 2 eps n! / (t0^n tau) (+ 0.2 % for the float32 arithmetic of the majorants)
-    const float t0f = (float)t0;
-    double th[4], fact = 1.0, tp = 1.0;
-    for (int n = 1; n <= 4; ++n) {
-        fact *= n; tp *= (double)t0f;
-        th[n - 1] = 2.0 * 2.220446049250313e-16 * fact / (tp * tau) * 1.002;
-    }
-    float cf[PDE_N_CONST], rf[PDE_N_CONST], pf[PDE_N_POW];
-    for (int i = 0; i < PDE_N_CONST; ++i) { cf[i] = fmaxf((float)fabs(cv[i]), 1e-18f); rf[i] = fmaxf((float)fabs(rv[i]), 1e-18f); }
-    for (int i = 0; i < PDE_N_POW; ++i) pf[i] = (float)pv[i];
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_constf, cf, sizeof(cf), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_rconstf, rf, sizeof(rf), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_powf, pf, sizeof(pf), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_t0, &t0f, sizeof(t0f), 0, cudaMemcpyHostToDevice, st));
-    PDE_CUDA(cudaMemcpyToSymbolAsync(c_theta, th, sizeof(th), 0, cudaMemcpyHostToDevice, st));
-    return PDE_OK;
-}
-
-template <int PROBLEM, bool DUMP, int W, int NP, int MINB, bool MAJ>
-static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* fits) {
-    constexpr int N = Residual<PROBLEM>::N;
-    const size_t smem = cta_smem_bytes<N, NP>(vp.L, vp.ns, W);
-    auto kern = validate_kernel<PROBLEM, DUMP, W, NP, MINB, MAJ>;
-    int dev = 0, sms = 0, occ = 0, max_smem = 0;
-    PDE_CUDA(cudaGetDevice(&dev));
-    PDE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PDE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem > (size_t)max_smem) { if (fits) { *fits = false; return PDE_OK; } set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
-    PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
-    if (occ < 1) { if (fits) { *fits = false; return PDE_OK; } set_error("validate kernel does not fit: smem %zu B per block", smem); return PDE_E_INVALID; }
-    if (fits) *fits = true;
-    const long long rounds = (vp.n + W - 1) / W;
-    const long long resident = (long long)sms * occ;    // persistent grid: a multiple of the SM count
-    int grid = (int)(rounds < resident ? rounds : resident);
-    if (grid < 1) grid = 1;
-    kern<<<grid, W * 32, smem, st>>>(vp);
-    count_launch();
-    PDE_CUDA(cudaGetLastError());
-    return PDE_OK;
-}
-
+// ------------------------------------------------------------- stage 2 (launch plumbing: launch.cuh)
 // Kernel configuration: a CTA is W/4 groups of 4 warps (validate.cuh).  One CTA per SM:
 //   W = 20 (640 threads, 94 registers, no local-memory spills): five warps per scheduler; fits up to
 //          2 spill slots per lane (154 KB); W = 24 (80 registers, 128 B of register spills) measured equal;
@@ -364,6 +331,11 @@ static int launch_validate(const ValidateParams& vp, cudaStream_t st) {
     }
 }
 
+template <int PROBLEM>
+struct BuiltinLauncher {
+    template <bool MAJ> static int launch(const ValidateParams& vp, cudaStream_t st) { return launch_validate<PROBLEM, false, MAJ>(vp, st); }
+};
+
 static int check_common(const pde_session* s, const pde_program* p, const void* code, const void* len,
                         int64_t n, int L, const void* pts, const void* tab, int P, int ns) {
     if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
@@ -401,8 +373,11 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
     }
     if (confirm_points > 0 && !out->scratch) { set_error("pde_validate: the two-pass mode needs out->scratch [n + 2] int32"); return PDE_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    rc = upload_tables(s, tau, t0, st);
-    if (rc) return rc;
+    const bool is_program = p->problem == PDE_PROBLEM_PROGRAM;      // program.cu owns (and uploads) its own tables
+    if (!is_program) {
+        rc = upload_tables(s, tau, t0, st);
+        if (rc) return rc;
+    }
     PDE_CUDA(cudaMemsetAsync(out->survivor_bits, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
     ValidateParams vp{};
     vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
@@ -410,25 +385,9 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
     vp.ns = spill_slots; vp.t0 = (float)t0; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
     vp.ratio_max = out->ratio_max; vp.resid_max = out->resid_max; vp.scale_at = out->scale_at;
     vp.n_finite = out->n_finite; vp.n_votes = out->n_votes; vp.ref_rs = out->ref_rs; vp.survivor_bits = out->survivor_bits;
-    const bool ff = p->problem == PDE_PROBLEM_FORCE_FREE;
-    if (confirm_points == 0) {
-        // one pass over the whole grid with the majorants carried
-        return ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, true>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, true>(vp, st);
-    }
-    // pass 1: all P points, no majorants -- proposes rejections
-    rc = ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, false>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, false>(vp, st);
-    if (rc) return rc;
-    // pass 2: the proposed rejections again on the first confirm_points points WITH the majorants; a rejection
-    // stands only if this pass votes it too (include/pde_b200.h)
-    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(out->scratch);
-    int* index = out->scratch + 2;
-    PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
-    if (out->confirm) PDE_CUDA(cudaMemsetAsync(out->confirm, 0xff, sizeof(int32_t) * 2 * (size_t)n, st));   // -1: not re-examined
-    compact_rejects_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out->survivor_bits, n, index, cnt);
-    count_launch();
-    PDE_CUDA(cudaGetLastError());
-    vp.index = index; vp.n_index = cnt; vp.confirm = out->confirm; vp.P_eval = confirm_points;
-    return ff ? launch_validate<PDE_PROBLEM_FORCE_FREE, false, true>(vp, st) : launch_validate<PDE_PROBLEM_KERR, false, true>(vp, st);
+    if (is_program) return program_validate(s, p, vp, out, confirm_points, tau, t0, st);
+    if (p->problem == PDE_PROBLEM_FORCE_FREE) return run_two_pass<BuiltinLauncher<PDE_PROBLEM_FORCE_FREE>>(vp, out, confirm_points, st);
+    return run_two_pass<BuiltinLauncher<PDE_PROBLEM_KERR>>(vp, out, confirm_points, st);
 }
 
 int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
@@ -441,11 +400,14 @@ int pde_eval_points(const pde_session* s, const pde_program* p, const uint8_t* c
     if (rc) return rc;
     if (n == 0) return PDE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = upload_tables(s, tau, t0, st);
-    if (rc) return rc;
+    if (p->problem != PDE_PROBLEM_PROGRAM) {
+        rc = upload_tables(s, tau, t0, st);
+        if (rc) return rc;
+    }
     ValidateParams vp{};
     vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
     vp.P_eval = P; vp.ns = spill_slots; vp.t0 = (float)t0; vp.tau = tau; vp.jets = jets; vp.resid = resid; vp.scale = scale; vp.scale_maj = scale_maj; vp.maj = maj;
+    if (p->problem == PDE_PROBLEM_PROGRAM) return program_eval_points(s, p, vp, tau, t0, st);
     if (p->problem == PDE_PROBLEM_FORCE_FREE) return launch_validate<PDE_PROBLEM_FORCE_FREE, true, true>(vp, st);
     return launch_validate<PDE_PROBLEM_KERR, true, true>(vp, st);
 }

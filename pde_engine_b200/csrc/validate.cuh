@@ -31,26 +31,27 @@ namespace pde {
 
 constexpr int kMaxL = 256;
 
-// per-launch tables (warp-uniform reads -> constant cache)
-__constant__ double c_const[PDE_N_CONST];
-__constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
-__constant__ double c_pow[PDE_N_POW];
+// per-launch tables (warp-uniform reads -> constant cache).  `static`: every translation unit that instantiates the
+// kernel (pde_b200.cu: the built-in residuals; program.cu: run-time residual programs) owns and uploads its own copy.
+static __constant__ double c_const[PDE_N_CONST];
+static __constant__ double c_rconst[PDE_N_CONST];   // reciprocals (division by a constant leaf)
+static __constant__ double c_pow[PDE_N_POW];
 // Taylor-ratio rows of x**k (U_POW): f_{j+1} = f_j * row[j] / x_0, row[j] = (k - j)/(j + 1)
 constexpr int kNRows = PDE_N_POW;
-__constant__ double c_frow[kNRows][4];
+static __constant__ double c_frow[kNRows][4];
 // x**n with n = 0, 1, 2, ...: c_pow_int[slot] = n (else -1) and the binomial coefficients C(n, j), j = 0..4, so that
 // the Taylor coefficients C(n, j) x^(n-j) need no division and stay finite at x = 0
-__constant__ int c_pow_int[kNRows];
-__constant__ double c_fbin[kNRows][5];
+static __constant__ int c_pow_int[kNRows];
+static __constant__ double c_fbin[kNRows][5];
 // round-off majorants (oracle/majorant.py): expansion radius t0 and theta_n / W = 2 eps n! / (t0^n tau), n = 1..4
-__constant__ float c_t0;
-__constant__ float c_constf[PDE_N_CONST];    // |c_const| and |c_rconst| as float (clamped like maj_abs), c_pow as float
-__constant__ float c_rconstf[PDE_N_CONST];
-__constant__ float c_powf[kNRows];
-__constant__ double c_theta[4];
-__constant__ double c_one = 1.0;                       // constant-bank operand: no register, no per-dispatch move
-__constant__ double c_sign[2] = {1.0, -1.0};
-__constant__ double c_rfact[4] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4};   // 1/(j + 1)
+static __constant__ float c_t0;
+static __constant__ float c_constf[PDE_N_CONST];    // |c_const| and |c_rconst| as float (clamped like maj_abs), c_pow as float
+static __constant__ float c_rconstf[PDE_N_CONST];
+static __constant__ float c_powf[kNRows];
+static __constant__ double c_theta[4];
+static __constant__ double c_one = 1.0;                       // constant-bank operand: no register, no per-dispatch move
+static __constant__ double c_sign[2] = {1.0, -1.0};
+static __constant__ double c_rfact[4] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4};   // 1/(j + 1)
 
 // Micro-ops.  Every arithmetic body exists exactly ONCE in the kernel so the interpreter's
 // code stays inside the instruction cache: an earlier version that inlined the bodies per
@@ -149,7 +150,7 @@ __host__ __device__ constexpr int kUcodeMax(int L) { return 2 * L + 6; }
 //   pass 1: sub-tree start and spill need of every position (stack of root positions in `stk`);
 //   pass 2: emission with an explicit frame stack (position, phase) in `stk`.
 // start[], need[] and stk[] are caller-provided byte arrays of L, L and 2L bytes.
-__device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* start, uint8_t* need, uint8_t* stk, int ns_max, int n_prim) {
+static __device__ __noinline__ int translate(const uint8_t* code, int len, uint32_t* uc, uint8_t* start, uint8_t* need, uint8_t* stk, int ns_max, int n_prim) {
     // ---- pass 1 ----
     int sp = 0;
     for (int i = 0; i < len; ++i) {
@@ -844,9 +845,11 @@ template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
     static constexpr int N = 4;
     static constexpr int COLS = 1;
     // FFV:305-347; entries expanded by tools/gen_residual.py
-    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[1]) { c[0] = ldg_early(tab + pt); }
-    template <bool SHARP>
-    __device__ static __forceinline__ void eval(const Jet<4>& u, const double (&c)[1], double Wd, double& R, double& St, double& S) {
+    struct Coef { double c[1]; };
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, Coef& k) { k.c[0] = ldg_early(tab + pt); }
+    template <bool SHARP, int STRIDE>
+    __device__ static __forceinline__ void eval(const Jet<4>& u, const Coef& k, double Wd, unsigned, double& R, double& St, double& S) {
+        const double (&c)[1] = k.c;
         double d[15];
 #pragma unroll
         for (int n = 0; n <= 4; ++n) {
@@ -856,8 +859,10 @@ template <> struct Residual<PDE_PROBLEM_FORCE_FREE> {
         const double w = c[0];   // 1/rho
         double p[4], a[4];
         ff_residual_entries(d, w, p, a);
-        R = p[0] * p[3] - p[1] * p[2];       // det M, FFV:347
-        if (SHARP) S = a[0] * a[3] + a[1] * a[2];
+        // det M, FFV:347 -- the contraction is spelled out so that the run-time program of the same residual
+        // (residual_programs.py, generated from the same schedule) is bit-identical
+        R = fma(p[0], p[3], -(p[1] * p[2]));
+        if (SHARP) S = fma(a[0], a[3], a[1] * a[2]);
         // isotropic majorant (oracle/majorant.py: iso_tables): every partial of order n replaced by
         // m_n = sum_{|g| = n} |d_g| + theta_n; one polynomial in m_1..m_4 and |w| instead of 48 monomials
         const double m1 = fma(Wd, c_theta[0], fabs(d[1]) + fabs(d[2]));
@@ -878,19 +883,22 @@ template <> struct Residual<PDE_PROBLEM_KERR> {
     static constexpr int N = 2;
     static constexpr int COLS = 4;
     // KV:77-91 expanded: R = c1_r u_r + c1 u_rr + c2_x u_x + c2 u_xx
-    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, double (&c)[4]) {
-        c[0] = ldg_early(tab + pt); c[1] = ldg_early(tab + P + pt);
-        c[2] = ldg_early(tab + 2 * (size_t)P + pt); c[3] = ldg_early(tab + 3 * (size_t)P + pt);
+    struct Coef { double c[4]; };
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, Coef& k) {
+        k.c[0] = ldg_early(tab + pt); k.c[1] = ldg_early(tab + P + pt);
+        k.c[2] = ldg_early(tab + 2 * (size_t)P + pt); k.c[3] = ldg_early(tab + 3 * (size_t)P + pt);
     }
-    template <bool SHARP>
-    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&c)[4], double Wd, double& R, double& St, double& S) {
-        const double c1 = c[0], c1r = c[1], c2 = c[2], c2x = c[3];
-        const double t0 = c1r * u.c[1];
-        const double t1 = c1 * (2.0 * u.c[3]);
-        const double t2 = c2x * u.c[2];
-        const double t3 = c2 * (2.0 * u.c[5]);
-        R = (t0 + t1) + (t2 + t3);
-        const double s = (fabs(t0) + fabs(t1)) + (fabs(t2) + fabs(t3));
+    template <bool SHARP, int STRIDE>
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const Coef& k, double Wd, unsigned, double& R, double& St, double& S) {
+        const double c1 = k.c[0], c1r = k.c[1], c2 = k.c[2], c2x = k.c[3];
+        // products and sums by intrinsics: never contracted into FMAs, so the run-time program of the same residual
+        // (residual_programs.py) is bit-identical
+        const double t0 = __dmul_rn(c1r, u.c[1]);
+        const double t1 = __dmul_rn(c1, 2.0 * u.c[3]);
+        const double t2 = __dmul_rn(c2x, u.c[2]);
+        const double t3 = __dmul_rn(c2, 2.0 * u.c[5]);
+        R = __dadd_rn(__dadd_rn(t0, t1), __dadd_rn(t2, t3));
+        const double s = __dadd_rn(__dadd_rn(fabs(t0), fabs(t1)), __dadd_rn(fabs(t2), fabs(t3)));
         if (SHARP) S = s;
         const double th1 = Wd * c_theta[0], th2 = Wd * c_theta[1];
         St = fma(fabs(c1r) + fabs(c2x), th1, fma(fabs(c1) + fabs(c2), th2, s));
@@ -903,13 +911,121 @@ constexpr int kProblemValue = 2;
 template <> struct Residual<kProblemValue> {
     static constexpr int N = 2;
     static constexpr int COLS = 1;
-    __device__ static __forceinline__ void fetch(const double*, int, int, double (&c)[1]) { c[0] = 0.0; }
-    template <bool SHARP>
-    __device__ static __forceinline__ void eval(const Jet<2>& u, const double (&)[1], double, double& R, double& St, double& S) {
+    struct Coef {};
+    __device__ static __forceinline__ void fetch(const double*, int, int, Coef&) {}
+    template <bool SHARP, int STRIDE>
+    __device__ static __forceinline__ void eval(const Jet<2>& u, const Coef&, double, unsigned, double& R, double& St, double& S) {
         R = u.c[0];
         St = S = fabs(u.c[1]) + fabs(u.c[2]);
     }
 };
+
+// ---------------------------------------------------------------------------------
+// Run-time residual programs (BASELINE north_star item 3; the plugin seam is ProblemSpec.validator, PI:34-63, and a
+// plugin's own `_lhs(u)`, KV:77-91): the residual operator of a problem arrives at run time as a straight-line scalar
+// program over the finished partial derivatives of u -- pde_compile_residual_program, include/pde_b200.h; produced from
+// the plugin's SymPy formula by pde_engine_b200/residual_compiler.py -- so a new plugin needs no CUDA and no rebuild.
+//
+// Machine: a scalar FILE F[0..n_file) of float64 per lane + one accumulator in a register.
+//   F[0 .. NC)                 the partial derivatives d_g (jet index order, factorials applied)
+//   F[NC .. NC + n_cols)       this point's row of the coefficient table (functions of the point only)
+//   F[.. + n_consts)           the program's constants
+//   above                      temporaries (written by MUL / STA before they are read: checked on the host)
+// The file lives in the lane's SPILL COLUMN of shared memory ([element][thread], conflict free): when the residual
+// runs the interpreter's spill stack is empty, so the column is free; the launcher sizes it (spill slots) for n_file.
+// Instruction word: op | a << 4 | b << 12 | dst << 20 | neg << 28, fetched from the constant bank (warp-uniform).
+// The program runs TWICE per point: on the values (R) and on magnitudes (|d_g| + theta_|g|, |c|, |k|, signs dropped)
+// -- the residual's majorant at the round-off-inflated partials, i.e. the decision scale S~ of oracle/majorant.py in
+// its non-isotropic form; with theta = 0 it is S = sum of |monomial|, the scale parity is quoted against.
+// ---------------------------------------------------------------------------------
+constexpr int kResMaxWords = PDE_R_MAX_WORDS;
+constexpr int kResMaxConsts = PDE_R_MAX_CONSTS;
+static __constant__ uint32_t c_res_words[kResMaxWords];
+static __constant__ double c_res_consts[kResMaxConsts];
+static __constant__ int c_res_dims[2];            // n_cols, n_consts
+
+template <int STRIDE>
+__device__ __forceinline__ double file_ld(unsigned base, unsigned k) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + k * (unsigned)STRIDE));
+    return v;
+}
+template <int STRIDE>
+__device__ __forceinline__ void file_st(unsigned base, unsigned k, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + k * (unsigned)STRIDE), "d"(v) : "memory");
+}
+
+// MAG: the magnitude pass (every sign dropped).  One copy per instantiation (__noinline__): the program is the same
+// for the whole launch, the loop is warp-uniform.
+template <bool MAG, int STRIDE>
+__device__ __noinline__ double res_run(unsigned base) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int pc = 0; pc < kResMaxWords; ++pc) {
+        const unsigned w = c_res_words[pc];
+        const unsigned op = w & 15u, a = (w >> 4) & 255u, b = (w >> 12) & 255u, d = (w >> 20) & 255u;
+        const bool neg = !MAG && ((w >> 28) & 1u);
+        if (op == PDE_R_OUT || op == PDE_R_END) break;
+        if (op == PDE_R_STA) { file_st<STRIDE>(base, d, acc); continue; }
+        double x = file_ld<STRIDE>(base, a);
+        if (neg) x = -x;
+        if (op == PDE_R_LDA) { acc = x; continue; }
+        if (op == PDE_R_ADDA) { acc = __dadd_rn(acc, x); continue; }
+        const double y = file_ld<STRIDE>(base, b);
+        if (op == PDE_R_MUL) file_st<STRIDE>(base, d, __dmul_rn(x, y));
+        else if (op == PDE_R_ACC0) acc = __dmul_rn(x, y);
+        else acc = __fma_rn(x, y, acc);               // PDE_R_ACC
+    }
+    return acc;
+}
+
+template <int N_>
+struct ResidualProg {
+    static constexpr int N = N_;
+    static constexpr int NC = Jet<N_>::NC;
+    static constexpr int COLS = 0;                    // nothing prefetched: the row is read when the residual runs
+    struct Coef { const double* row; int P; };
+    __device__ static __forceinline__ void fetch(const double* tab, int P, int pt, Coef& k) { k.row = tab + pt; k.P = P; }
+    template <bool SHARP, int STRIDE>
+    __device__ static __forceinline__ void eval(const Jet<N_>& u, const Coef& k, double Wd, unsigned F, double& R, double& St, double& S) {
+        const int nc = c_res_dims[0], nk = c_res_dims[1];
+        double d[NC];
+#pragma unroll
+        for (int n = 0; n <= N; ++n) {
+#pragma unroll
+            for (int j = 0; j <= n; ++j) d[jidx(n - j, j)] = u.c[jidx(n - j, j)] * (factorial(n - j) * factorial(j));
+        }
+        // ---- values ----
+#pragma unroll
+        for (int g = 0; g < NC; ++g) file_st<STRIDE>(F, g, d[g]);
+        for (int c = 0; c < nc; ++c) file_st<STRIDE>(F, NC + c, __ldg(k.row + (size_t)c * k.P));
+        for (int c = 0; c < nk; ++c) file_st<STRIDE>(F, NC + nc + c, c_res_consts[c]);
+        R = res_run<false, STRIDE>(F);
+        // ---- magnitudes at the inflated partials: theta_n = W * 2 eps n! / (t0^n tau), theta_0 = theta_1 t0 ----
+        double th[N + 1];
+        th[0] = Wd * c_theta[0] * (double)c_t0;
+#pragma unroll
+        for (int n = 1; n <= N; ++n) th[n] = Wd * c_theta[n - 1];
+#pragma unroll
+        for (int n = 0; n <= N; ++n) {
+#pragma unroll
+            for (int j = 0; j <= n; ++j) file_st<STRIDE>(F, jidx(n - j, j), fabs(d[jidx(n - j, j)]) + th[n]);
+        }
+        for (int c = 0; c < nc + nk; ++c) file_st<STRIDE>(F, NC + c, fabs(file_ld<STRIDE>(F, NC + c)));
+        St = res_run<true, STRIDE>(F);
+        if (SHARP) {
+            S = St;
+            if (Wd != 0.0) {
+#pragma unroll
+                for (int g = 0; g < NC; ++g) file_st<STRIDE>(F, g, fabs(d[g]));
+                S = res_run<true, STRIDE>(F);
+            }
+        }
+    }
+};
+constexpr int kProblemProgram2 = 16 + 2, kProblemProgram4 = 16 + 4;     // template tags of ResidualProg<2>, <4>
+template <> struct Residual<kProblemProgram2> : ResidualProg<2> {};
+template <> struct Residual<kProblemProgram4> : ResidualProg<4> {};
 
 // ---------------------------------------------------------------------------------
 // Work decomposition.  Warps own candidates, lanes own collocation points.  A CTA is G groups
@@ -1019,7 +1135,7 @@ validate_kernel(const ValidateParams p) {
 #pragma unroll
                     for (int h = 0; h < NP; ++h) { cx[h].ax0 = maj_abs(cx[h].x0); cx[h].ax1 = maj_abs(cx[h].x1); }
                 }
-                double coef[NP][Res::COLS];
+                typename Res::Coef coef[NP];
                 int pt[NP];
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
@@ -1033,7 +1149,7 @@ validate_kernel(const ValidateParams p) {
 #pragma unroll
                 for (int h = 0; h < NP; ++h) {
                     double R, S, St;
-                    Res::template eval<DUMP>(T[h], coef[h], MAJ ? maj_final(MT[h].W) : 0.0, R, St, S);
+                    Res::template eval<DUMP, TPB * 8>(T[h], coef[h], MAJ ? maj_final(MT[h].W) : 0.0, spill_addr, R, St, S);
                     if (DUMP) {
                         if (p.jets) {
 #pragma unroll

@@ -88,7 +88,7 @@ def run_discovery(spec: Any, normalizer: Any, max_depth: int, *, db_path: Option
     import sympy as sp
     gv: GpuBatchValidator = spec.validator
     locs = spec.sympify_locals()
-    gen = GpuExpressionGenerator(normalizer, spec.slug, pre_batch_hook=gv.prefetch)
+    gen = GpuExpressionGenerator(normalizer, getattr(spec, "coordinate_system", spec.slug), pre_batch_hook=gv.prefetch)
     rows: List[dict] = []
     seen_norm = set()
     t_start = time.time()

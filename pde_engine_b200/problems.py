@@ -126,6 +126,58 @@ def _create_kerr_magnetosphere_problem(cpu_validator=None, make_gpu=True, **gpu_
                  primitives, cpu_validator, {"1 - x": "Monopole (a -> 0 limit)"}, make_gpu, gpu_kwargs)
 
 
+class SymbolicResidualValidator:
+    """CPU confirmation for a custom plugin: the validator protocol (PI:52) over `lhs(u)` -- valid iff the residual
+    simplifies to zero identically (what KerrMagnetosphereValidator.validate does with its own `_lhs`, KV:284-292)."""
+
+    def __init__(self, lhs: Callable, coords):
+        self._lhs_fn, self.coords = lhs, tuple(coords)
+
+    def _lhs(self, u):
+        return self._lhs_fn(u)
+
+    def validate(self, u, check_regularity: bool = True, fast_point_only: bool = False, **kw):
+        try:
+            if not any(sp.sympify(u).has(c) for c in self.coords):
+                return False, "Trivial constant solution excluded"
+            res = sp.simplify(self._lhs_fn(u).doit())
+            return (True, "Valid (exact zero)") if res == 0 else (False, f"PDE residual != 0 | residual: {str(res)[:80]}")
+        except Exception as e:   # KV:344-345
+            return False, f"Validation error: {e}"
+
+    def describe(self):
+        return {"method_name": "pde_engine_b200.problems.SymbolicResidualValidator.validate", "math_definition": "lhs(u) = 0"}
+
+
+def custom_problem(name: str, slug: str, lhs: Callable, base: str = "force_free", primitives: Optional[List] = None,
+                   known_solutions: Optional[Dict[str, str]] = None, cpu_validator: Any = "symbolic",
+                   params: Optional[dict] = None, **gpu_kwargs) -> ProblemSpec:
+    """A new plugin with NO CUDA and no rebuild (BASELINE north_star item 3).  `lhs(u)` states the PDE like the
+    reference's `KerrMagnetosphereValidator._lhs` (KV:77-91): it is called once with a generic `Function('u')` of the
+    base problem's coordinates and compiled into a device residual program (residual_compiler.compile_residual);
+    the ProblemSpec keeps the reference's fields (PI:34-63).  `base` supplies the coordinate system, constants,
+    default primitives and the collocation grid; `params` gives numeric values for symbolic constants in lhs."""
+    from .residual_compiler import compile_residual
+    from .validator import GpuBatchValidator
+    b = load_problem(base, make_gpu=False)
+    coords = tuple(b.symbols.values())
+    u = sp.Function("u")(*coords)
+    cr = compile_residual(lhs(u), u, coords, params=params, description=name)
+    if cpu_validator == "symbolic":
+        cpu_validator = SymbolicResidualValidator(lhs, coords)
+    spec = ProblemSpec(
+        name=name, slug=slug, symbols=b.symbols, constants=b.constants,
+        primitives=list(primitives) if primitives is not None else b.primitives,
+        unary_ops=_unary_ops(), binary_ops=_binary_ops(), special_ops=_special_ops(),
+        all_binary_ops={**_binary_ops(), **_special_ops()}, validator=cpu_validator,
+        known_solutions=dict(known_solutions or {}), output_root=os.path.join("problems", slug, "outputs"))
+    spec.coordinate_system = b.slug
+    spec.compiled_residual = cr
+    spec.validator = GpuBatchValidator(cpu_validator, b.slug, sympify_locals=spec.sympify_locals(), program=cr.program(),
+                                       math_definition=f"{sp.sstr(lhs(u))} = 0", **gpu_kwargs)
+    return spec
+
+
 def load_problem(name: str, cpu_validator=None, make_gpu: bool = True, **gpu_kwargs) -> ProblemSpec:
     """PI:355-361 (same aliases, same error)."""
     key = (name or "").strip().lower()
@@ -136,4 +188,4 @@ def load_problem(name: str, cpu_validator=None, make_gpu: bool = True, **gpu_kwa
     raise ValueError(f"Unknown problem '{name}'. Available: 'force_free', 'kerr_magnetosphere'")
 
 
-__all__ = ["ProblemSpec", "load_problem"]
+__all__ = ["ProblemSpec", "load_problem", "custom_problem", "SymbolicResidualValidator"]

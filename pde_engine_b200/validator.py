@@ -72,12 +72,18 @@ class GpuBatchValidator:
     def __init__(self, cpu_validator: Any = None, problem: str = "force_free", P: int = 4096,
                  tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, L: int = 128,
                  spill_slots: int = 2, sympify_locals: Optional[dict] = None, device=None, t0: float = core.T0_DEFAULT,
-                 confirm_points: int = core.CONFIRM_POINTS_DEFAULT, group: Any = "auto"):
+                 confirm_points: int = core.CONFIRM_POINTS_DEFAULT, group: Any = "auto",
+                 program: Optional[core.ResidualProgram] = None, math_definition: Optional[str] = None):
+        """`problem` names the coordinate system / symbol table and the collocation grid (a built-in slug); `program`
+        replaces the built-in residual by a run-time residual program (residual_compiler.compile_residual(...).program(),
+        problems.custom_problem): a new plugin needs no CUDA."""
         import torch
         self.cpu_validator = cpu_validator
         self.problem = canonical_slug(problem)
         self.session = core.Session.for_problem(self.problem)
-        self.program = core.ResidualProgram.for_problem(self.problem)
+        self.program = program if program is not None else core.ResidualProgram.for_problem(self.problem)
+        self.custom = program is not None
+        self.math_definition = math_definition
         self.P, self.tau, self.min_finite, self.vote_frac = P, tau, min_finite, vote_frac
         self.L, self.spill_slots, self.t0, self.confirm_points = L, spill_slots, t0, confirm_points
         self.sympify_locals = sympify_locals
@@ -176,7 +182,7 @@ class GpuBatchValidator:
             return False
         n, sizes_b = int(h[1]), [int(x) for x in h[2:]]
         if rank == 0:
-            payload = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(cdev)
+            payload = torch.from_numpy(np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()).to(cdev)
         else:
             payload = torch.empty(sum(sizes_b), dtype=torch.uint8, device=cdev)
         dist.broadcast(payload, src=0, group=grp)
@@ -187,33 +193,40 @@ class GpuBatchValidator:
             lo = sum(sizes_b[:rank])
             mine = payload[lo:lo + sizes_b[rank]].cpu().numpy().tobytes()
             bv = self._prefilter_local(None, compile_threads=max(1, (os.cpu_count() or 1) // world), blob=mine, n=count)
-        # one float64 row per candidate: 5 scalars + ref_rs (6) + confirm (2) + survivor + flags
-        rows = np.zeros((count, 15))
-        for k, name in enumerate(self._COLS):
-            rows[:, k] = getattr(bv, name)
-        rows[:, 5:11] = bv.ref_rs.reshape(count, 6)
-        rows[:, 11:13] = bv.confirm if bv.confirm is not None else -1
-        rows[:, 13] = bv.survivor
-        rows[:, 14] = bv.flags
+        # the verdict columns of the shard as ONE byte buffer in native dtypes (struct of arrays, 97 B per candidate;
+        # a float64 row per candidate cost more host time in conversions than the kernel takes)
         sizes = [shard_range(n, r, world)[1] for r in range(world)]
         nmax = max(sizes)
-        pad = torch.zeros((nmax, 15), dtype=torch.float64, device=cdev)
-        pad[:count] = torch.from_numpy(rows).to(cdev)
+        fields = [(name, np.dtype(np.float64), 1) for name in self._COLS[:3]] + \
+                 [("n_finite", np.dtype(np.int32), 1), ("n_votes", np.dtype(np.int32), 1), ("ref_rs", np.dtype(np.float64), 6),
+                  ("confirm", np.dtype(np.int32), 2), ("survivor", np.dtype(np.uint8), 1), ("flags", np.dtype(np.uint8), 1)]
+        per = sum(dt.itemsize * k for _, dt, k in fields)
+        buf = np.zeros(nmax * per, np.uint8)
+        pos = 0
+        for name, dt, k in fields:
+            if name == "confirm" and bv.confirm is None:
+                col = np.full((count, 2), -1, np.int32)
+            else:
+                col = np.ascontiguousarray(getattr(bv, name), dtype=dt)
+            buf[pos:pos + count * k * dt.itemsize] = col.reshape(-1).view(np.uint8)
+            pos += nmax * k * dt.itemsize
+        pad = torch.from_numpy(buf).to(cdev)
         got = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
         dist.gather(pad, got, dst=0, group=grp)
         if rank != 0:
             return None
-        allr = np.concatenate([g[:c].cpu().numpy() for g, c in zip(got, sizes)], axis=0)
-        out = {name: allr[:, k].copy() for k, name in enumerate(self._COLS)}
-        out["n_finite"] = out["n_finite"].astype(np.int32)
-        out["n_votes"] = out["n_votes"].astype(np.int32)
-        out["ref_rs"] = allr[:, 5:11].reshape(n, 3, 2).copy()
-        out["confirm"] = allr[:, 11:13].astype(np.int32)
-        surv = allr[:, 13].astype(bool)
-        bits = np.zeros((n + 31) // 32, np.uint32)
-        np.bitwise_or.at(bits, np.flatnonzero(surv) >> 5, (np.uint32(1) << (np.flatnonzero(surv) & 31).astype(np.uint32)))
-        out["survivor_bits"] = bits.view(np.int32)
-        return BatchVerdict(strs, allr[:, 14].astype(np.uint8), out)
+        host = [g.cpu().numpy() for g in got]
+        out, pos = {}, 0
+        for name, dt, k in fields:
+            parts = [h[pos:pos + c * k * dt.itemsize].view(dt) for h, c in zip(host, sizes)]
+            out[name] = np.concatenate(parts)
+            pos += nmax * k * dt.itemsize
+        out["ref_rs"] = out["ref_rs"].reshape(n, 3, 2)
+        out["confirm"] = out["confirm"].reshape(n, 2)
+        surv = np.zeros((n + 31) // 32 * 32, bool)
+        surv[:n] = out.pop("survivor").astype(bool)
+        out["survivor_bits"] = np.packbits(surv, bitorder="little").view(np.int32)
+        return BatchVerdict(strs, out.pop("flags"), out)
 
     def _prefilter_local(self, expr_strs: Optional[Sequence[str]], compile_threads: Optional[int] = None,
                          blob: Optional[bytes] = None, n: Optional[int] = None) -> BatchVerdict:
@@ -315,6 +328,9 @@ class GpuBatchValidator:
             self._cache[key] = (bool(bv.survivor[i]), bv.evidence(i), r0)
 
     def _reject_reason(self, r0: Optional[float], ev: dict) -> str:
+        if self.custom:
+            return (f"PDE residual != 0 (GPU residual filter: max|R|={ev['resid_max']:.3e}, |R|/S up to {ev['ratio_max']:.2e} "
+                    f"at {ev['n_votes']}/{ev['n_finite']} points)")
         if self.problem == "force_free":
             # mirrors FFV:395 "Invalid (point check ≈ {abs(det_val):.2e})"
             if r0 is not None and np.isfinite(r0) and r0 != 0.0:
@@ -403,9 +419,9 @@ class GpuBatchValidator:
                 base = {}
         return {
             "method_name": base.get("method_name", f"{self.__class__.__module__}.{self.__class__.__name__}.validate"),
-            "math_definition": base.get("math_definition",
+            "math_definition": base.get("math_definition", self.math_definition or (
                                         "det[[L_T A, L_T B],[L_T^2 A, L_T^2 B]] = 0" if self.problem == "force_free"
-                                        else "d_r[(G/(1-x^2)) d_r u] + d_x[(G/Delta) d_x u] = 0"),
+                                        else "d_r[(G/(1-x^2)) d_r u] + d_x[(G/Delta) d_x u] = 0")),
         }
 
     def last_evidence(self) -> dict:

@@ -1,0 +1,141 @@
+"""Run-time residual programs on the device (north_star item 3): the interpreter against the CUDA specialisations of
+the same two residuals (bit for bit), the SymPy front end against them (to tolerance), and a third plugin -- the
+axisymmetric Laplace equation, stated only as a SymPy formula -- end to end with no rebuild."""
+import json
+import os
+
+import numpy as np
+import pytest
+import sympy as sp
+
+from conftest import GOLDEN, uniques_by_depth
+from oracle.normalizer import OracleNormalizer
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.asarray(a, np.float64).view(np.int64), np.asarray(b, np.float64).view(np.int64))
+
+
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_program_equals_builtin_bit_for_bit(problem, cuda_device, enum_ff, enum_kerr):
+    """Residual<FORCE_FREE> / Residual<KERR> (compiled in) vs the SAME residual as a run-time program
+    (residual_programs.py, generated from the same schedule): R and the plain scale S agree in every bit at every
+    point, NaN patterns included; the decision scale S~ of the program (non-isotropic majorant) never exceeds the
+    specialisation's isotropic one."""
+    import torch
+    import test_gpu_validate as tv
+    import pde_engine_b200 as pb
+    E = uniques_by_depth(enum_ff if problem == "force_free" else enum_kerr)
+    strs = E[1] + E[2] + E[3][::(7 if problem == "force_free" else 31)]
+    _, sess, prog, pts, pts_t, tab_t = tv._setup(problem, 64, cuda_device)
+    gen = pb.ResidualProgram.builtin_as_program(problem)
+    assert gen.problem_id == pb.core.PROBLEM_PROGRAM and (gen.order, gen.cols) == (prog.order, prog.cols)
+    np.testing.assert_array_equal(gen.point_table(pts), prog.point_table(pts))
+    a, flags = tv._device_eval(pb, sess, prog, strs, pts_t, tab_t, cuda_device)
+    b, _ = tv._device_eval(pb, sess, gen, strs, pts_t, tab_t, cuda_device)
+    ok = flags == 0
+    assert ok.sum() > 0.95 * len(strs)
+    assert _same_bits(a["jets"][ok], b["jets"][ok])
+    assert _same_bits(a["R"][ok], b["R"][ok])
+    assert _same_bits(a["S"][ok], b["S"][ok])
+    fin = ok[:, None] & np.isfinite(a["St"]) & np.isfinite(b["St"])
+    assert fin.sum() > 0.5 * fin.size
+    if problem == "force_free":
+        assert np.all(b["St"][fin] <= a["St"][fin] * (1 + 1e-12))
+        assert np.all(b["St"][fin] >= a["S"][fin] * (1 - 1e-12))          # and never below the plain scale
+    else:
+        assert np.allclose(b["St"][fin], a["St"][fin], rtol=1e-12)
+    n = int(np.isfinite(a["R"][ok]).sum())
+    print(f"{problem}: {ok.sum()} candidates x 64 points, {n} finite residuals, R and S bit-identical")
+
+
+@pytest.mark.parametrize("problem,depth", [("force_free", 3), ("kerr_magnetosphere", 3)])
+def test_program_filter_vs_builtin_and_reference_verdicts(problem, depth, cuda_device, enum_ff, enum_kerr):
+    """pde_validate with the run-time program: no reference-valid candidate is rejected, and -- its decision scale
+    being at most the specialisation's -- it rejects everything the specialisation rejects."""
+    import pde_engine_b200 as pb
+    from pde_engine_b200.validator import GpuBatchValidator
+    E = uniques_by_depth(enum_ff if problem == "force_free" else enum_kerr)
+    strs = E[depth][::(1 if problem == "force_free" else 3)]
+    recs = json.load(open(os.path.join(GOLDEN, f"verdicts_{problem}_d{depth}.json")))["records"]
+    valid = {r["s"] for r in recs if r.get("is_valid")}
+    strs = strs + [s for s in valid if s not in set(strs)]
+    builtin = GpuBatchValidator(None, problem, P=1024)
+    generic = GpuBatchValidator(None, problem, P=1024, program=pb.ResidualProgram.builtin_as_program(problem))
+    a, b = builtin.prefilter(strs), generic.prefilter(strs)
+    assert a.rejected.sum() > 0.3 * len(strs)
+    lost = [s for s, ra, rb in zip(strs, a.rejected, b.rejected) if ra and not rb]
+    assert len(lost) <= 0.002 * len(strs), lost[:5]       # vote counts at the threshold may differ by a point or two
+    assert all(b.survivor[i] for i, s in enumerate(strs) if s in valid)
+    np.testing.assert_array_equal(a.n_finite < 0, b.n_finite < 0)
+    print(f"{problem}: rejected {int(a.rejected.sum())} (specialisation) / {int(b.rejected.sum())} (program) of {len(strs)}")
+
+
+def test_front_end_programs_on_device(cuda_device, enum_ff, enum_kerr):
+    """compile_residual on the reference's formulas (FFV:305-347 det M; KV:77-91 `_lhs` of a generic u): a different
+    evaluation order of the same polynomials -- device residuals within 1e-10 * S of the specialisations."""
+    import test_gpu_validate as tv
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.residual_compiler import compile_residual
+    rho, z = sp.symbols("rho z", positive=True)
+    u = sp.Function("u")(rho, z)
+    ur, uz = u.diff(rho), u.diff(z)
+    A = ur.diff(rho) + uz.diff(z) - ur / rho
+    B = ur ** 2 + uz ** 2
+    LT = lambda f: uz * f.diff(rho) - ur * f.diff(z)      # noqa: E731
+    cr_ff = compile_residual(sp.Matrix([[LT(A), LT(B)], [LT(LT(A)), LT(LT(B))]]).det(), u, (rho, z))
+    r, x, Ms, a_ = sp.symbols("r x M a", real=True)
+    v = sp.Function("u")(r, x)
+    Delta = r ** 2 - 2 * Ms * r + a_ ** 2
+    G = 1 - 2 * Ms * r / (r ** 2 + a_ ** 2 * x ** 2)
+    cr_k = compile_residual(sp.diff(G / (1 - x ** 2) * v.diff(r), r) + sp.diff(G / Delta * v.diff(x), x), v, (r, x),
+                            params={Ms: 1, a_: sp.Rational(1, 10)})
+    for problem, cr, g in (("force_free", cr_ff, enum_ff), ("kerr_magnetosphere", cr_k, enum_kerr)):
+        E = uniques_by_depth(g)
+        strs = E[1] + E[2] + E[3][::23]
+        _, sess, prog, pts, pts_t, tab_t = tv._setup(problem, 64, cuda_device)
+        gen = cr.program()
+        gtab = torch.from_numpy(gen.point_table(pts)).to(cuda_device)
+        a, flags = tv._device_eval(pb, sess, prog, strs, pts_t, tab_t, cuda_device)
+        b, _ = tv._device_eval(pb, sess, gen, strs, pts_t, gtab, cuda_device)
+        ok = (flags == 0)[:, None] & np.isfinite(a["R"]) & np.isfinite(b["R"]) & np.isfinite(a["S"]) & (a["S"] > 0)
+        assert ok.sum() > 0.6 * ok.size
+        err = np.abs(a["R"] - b["R"])[ok] / np.maximum(a["S"], b["S"])[ok]
+        assert err.max() <= 1e-10, (problem, float(err.max()))
+        # the two scales bound the same round-off: same order of magnitude
+        q = (b["S"] / a["S"])[ok]
+        assert np.median(q) < 30 and np.all(q > 0.2), (float(np.median(q)), float(q.min()))
+        print(f"{problem}: front-end program {len(cr.words)} words, file {cr.n_file}; worst |dR|/S {err.max():.2e} over {int(ok.sum())} points")
+
+
+def test_third_plugin_without_rebuild(cuda_device, tmp_path):
+    """A plugin the library was never compiled for: u_rr + u_r/rho + u_zz = 0 (axisymmetric Laplace), given only as
+    `lhs(u)` in SymPy -- the reference's way of stating a PDE (KV:77-91).  Enumerate -> device filter with the
+    run-time program -> symbolic confirmation, through the same engine as the two shipped problems."""
+    from pde_engine_b200.engine import run_discovery
+    from pde_engine_b200.problems import custom_problem
+    rho, z = sp.Symbol("rho", real=True, positive=True), sp.Symbol("z", real=True)
+
+    def lhs(u):
+        return sp.diff(u, rho, 2) + sp.diff(u, rho) / rho + sp.diff(u, z, 2)
+
+    spec = custom_problem("Axisymmetric Laplace", "laplace_axisym", lhs, base="force_free",
+                          primitives=[rho, z, rho ** 2 + z ** 2, sp.Integer(1)],
+                          known_solutions={"1/sqrt(rho**2 + z**2)": "Coulomb"}, P=1024)
+    assert spec.validator.program.problem_id == 3 and spec.compiled_residual.order == 2
+    res = run_discovery(spec, OracleNormalizer(), 3, db_path=str(tmp_path / "run.db"), run_id="laplace")
+    rows = res["rows"]
+    valid = {r["expression"] for r in rows if r["is_valid"]}
+    assert "z" in valid and any(r["paper_solution_name"] == "Coulomb" for r in rows if r["is_paper_solution"]), sorted(valid)[:20]
+    st = res["stats"]
+    assert st["gpu_rejected"] > 0.8 * st["gpu_evaluated"] and st["cpu_confirmed"] < 0.2 * st["gpu_evaluated"], st
+    # no false reject: a sample of the rows decided on the device is invalid for SymPy as well
+    gpu_rej = [r for r in rows if r["is_valid"] == 0 and "GPU residual filter" in (r["validation_reason"] or "")]
+    assert len(gpu_rej) > 100
+    locs = spec.sympify_locals()
+    for r in gpu_rej[:: max(1, len(gpu_rej) // 60)]:
+        assert sp.simplify(lhs(sp.sympify(r["expression"], locals=locs)).doit()) != 0, r["expression"]
+    print(f"laplace_axisym depth 3: {len(rows)} rows, {len(valid)} valid, {st}")

@@ -11,16 +11,24 @@ matrix entry is expanded into monomials; the device evaluates every monomial
 once and accumulates both the signed sum p_k and the absolute sum a_k
 (S = a0 a3 + a1 a2 is the round-off scale of R = p0 p3 - p1 p2).
 
-Run:  python tools/gen_residual.py   (needs sympy; the output is committed so
+The SAME schedule (which products are shared, which fused multiply-adds are formed, in which order they are
+accumulated) is also emitted as a run-time residual program (pde_engine_b200/residual_programs.py, the input of
+pde_compile_residual_program), together with the Kerr residual in the schedule of Residual<KERR> (validate.cuh):
+tests/test_gpu_program.py shows that the interpreter and the CUDA specialisations agree bit for bit.
+
+Run:  python tools/gen_residual.py   (needs sympy; the outputs are committed so
 the build itself does not).
 """
 from __future__ import annotations
 
 import os
+import sys
 
 import sympy as sp
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from pde_engine_b200.residual_compiler import ProgramBuilder   # noqa: E402
 
 
 def jidx(i, j):
@@ -65,6 +73,14 @@ def main():
     order = sorted(range(len(gens)), key=lambda v: -freq[v])
     prefix = {}          # tuple of var indices -> C name
     decl = []
+    # the run-time program of the same schedule
+    pb = ProgramBuilder(4, 1)
+    inv_idx = {}
+    for i_ in range(5):
+        for j_ in range(5 - i_):
+            inv_idx[jidx(i_, j_)] = (i_, j_)
+    operand = {f"d{g}": pb.d(*inv_idx[g]) for g in range(15)}
+    operand["w"] = pb.col(0)
 
     def name_of(v):
         return str(gens[v])
@@ -78,6 +94,7 @@ def main():
             nm = f"m{len(prefix)}"
             prefix[key] = nm
             decl.append(f"    const double {nm} = {left} * {name_of(factors[-1])};")
+            operand[nm] = pb.mul(operand[left], operand[name_of(factors[-1])])
         return prefix[key]
 
     body = []
@@ -97,8 +114,11 @@ def main():
                 sl = f"-{left}" if sgn < 0 else left
                 if n_ == 0:
                     body.append(f"    double {ps} = {sl} * {right}, {as_} = fabs({left}) * fabs({right});")
+                    pb.acc0(operand[left], operand[right], sgn < 0)
                 else:
                     body.append(f"    {ps} = fma({sl}, {right}, {ps}); {as_} = fma(fabs({left}), fabs({right}), {as_});")
+                    pb.acc(operand[left], operand[right], sgn < 0)
+            operand[ps] = pb.sta()
             pk.append((c, ps))
             ak.append((c, as_))
 
@@ -111,6 +131,18 @@ def main():
                     out = f"fma({float(c)!r}, {nm}, {out})" if c != 1 else f"({out} + {nm})"
             return out
         body.append(f"    p[{k}] = {combine(pk)}; a[{k}] = {combine(ak)};")
+        # the same combination in the program: c * nm | fma(c, nm, out) | (out + nm)
+        for q, (c, nm) in enumerate(pk):
+            if q == 0:
+                if c == 1:
+                    pb.lda(operand[nm])
+                else:
+                    pb.acc0(pb.const(float(c)), operand[nm])
+            elif c != 1:
+                pb.acc(pb.const(float(c)), operand[nm])
+            else:
+                pb.adda(operand[nm])
+        operand[f"p{k}"] = pb.sta()
 
     lines = []
     lines.append("// GENERATED by tools/gen_residual.py -- do not edit.")
@@ -131,6 +163,32 @@ def main():
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     print("wrote", path, "monomials", len(monos), "shared sub-products", len(prefix))
+    # R = fma(p0, p3, -(p1 * p2))   (Residual<FORCE_FREE>::eval)
+    pb.acc0(operand["p1"], operand["p2"], True)
+    pb.acc(operand["p0"], operand["p3"])
+    pb.out()
+    ff_words, ff_file = pb.assemble()
+
+    # Kerr (KV:77-91 expanded; Residual<KERR>::eval): R = (c1r u_r + c1 u_rr) + (c2x u_x + c2 u_xx), columns
+    # c1 = G/(1-x^2), c1r = d_r c1, c2 = G/Delta, c2x = d_x c2; four products, three sums, nothing fused
+    kb = ProgramBuilder(2, 4)
+    t0 = kb.mul(kb.col(1), kb.d(1, 0))
+    t1 = kb.mul(kb.col(0), kb.d(2, 0))
+    t2 = kb.mul(kb.col(3), kb.d(0, 1))
+    t3 = kb.mul(kb.col(2), kb.d(0, 2))
+    kb.lda(t0); kb.adda(t1); s01 = kb.sta()
+    kb.lda(t2); kb.adda(t3); s23 = kb.sta()
+    kb.lda(s01); kb.adda(s23); kb.out()
+    k_words, k_file = kb.assemble()
+
+    out = os.path.join(REPO, "pde_engine_b200", "residual_programs.py")
+    with open(out, "w") as f:
+        f.write('"""GENERATED by tools/gen_residual.py -- do not edit.\n\n'
+                'The two built-in residuals as run-time residual programs (pde_compile_residual_program), in the exact\n'
+                'schedule of their CUDA specialisations (csrc/residual_ff_gen.cuh, Residual<KERR> in csrc/validate.cuh).\n"""\n')
+        f.write(f"FORCE_FREE = dict(order=4, n_cols=1, consts={pb.consts!r}, n_file={ff_file},\n    words={ff_words!r})\n\n")
+        f.write(f"KERR = dict(order=2, n_cols=4, consts={kb.consts!r}, n_file={k_file},\n    words={k_words!r})\n")
+    print("wrote", out, "force-free:", len(ff_words), "words, file", ff_file, "| Kerr:", len(k_words), "words, file", k_file)
 
 
 if __name__ == "__main__":
