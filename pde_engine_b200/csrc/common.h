@@ -11,6 +11,11 @@ void set_error(const char* fmt, ...);
 int cuda_fail(int err, const char* what);   // records message, returns PDE_E_CUDA
 void count_launch(int n = 1);
 bool have_device();
+// Stream-ordered scratch memory from a pool the library owns (one per device, never trimmed): per-call work space
+// without file-scope buffers -- safe with several host threads and streams -- and without paying cudaMalloc /
+// cudaFree around every call (8-70 ms for the 400 MB dedup table).
+int scratch_alloc(void** ptr, size_t bytes, void* stream);
+void scratch_free(void* ptr, void* stream);
 
 #define PDE_CUDA(call)                                                     \
     do {                                                                   \
@@ -60,6 +65,14 @@ struct pde_exprset {
     int8_t* d_term_sign = nullptr;
     uint32_t* d_term_off = nullptr;
     uint8_t* d_pool = nullptr;
+    // result of the enumerator's count pass (enumerate.cu), cached on the handle: a windowed pde_enumerate (one window
+    // per rank / per chunk) does not repeat it.  Valid for (count_depth, count_prune, count_db) on `device`.
+    int count_depth = 0, count_prune = -1;
+    int32_t count_db[16] = {0};
+    long long count_blocks = 0, count_total = 0;
+    unsigned* d_count_sums = nullptr;             // candidates per block
+    unsigned* d_count_in_tile = nullptr;          // exclusive prefix inside a 1024-block tile
+    unsigned long long* d_count_tile = nullptr;   // exclusive prefix of the tile totals
     std::vector<uint32_t> desc;         // [n][2] splice descriptors (enumerate.cu)
     std::vector<uint8_t> wpool;         // whole programs, padded by 8 bytes
     uint32_t* d_desc = nullptr;

@@ -321,8 +321,16 @@ __device__ __forceinline__ void splice(RowWriter& w, const uint32_t* pool32, int
 __host__ __device__ constexpr int enum_row_stride(int L) { return L + 16; }
 
 __global__ void __launch_bounds__(kEnumThreads)
-enum_emit_kernel(const EnumParams p, const unsigned* in_tile, const unsigned long long* tile_off, long long first, long long count, int L,
+enum_emit_kernel(const EnumParams p, const unsigned* sums, const unsigned* in_tile, const unsigned long long* tile_off, long long first, long long count, int L,
                  int32_t* triple, uint8_t* code, uint8_t* len_out, unsigned long long* hash_out) {
+    // A block outside the window [first, first + count) leaves before it touches shared memory: the count pass
+    // already knows every block's candidate range, so an 8-way sharded pass costs each rank 1/8 of the work
+    // (+ ~10 us of empty blocks), not a full pass.
+    const long long base = (long long)(tile_off[blockIdx.x / kScanTile] + in_tile[blockIdx.x]);
+    {
+        const long long n_blk = (long long)sums[blockIdx.x];
+        if (n_blk == 0 || base + n_blk <= first || base >= first + count) return;
+    }
     extern __shared__ __align__(16) uint8_t s_rows[];   // [kEnumThreads][L + 16] rows, then per-row hash / triple / len
     __shared__ int s_flag[kEnumThreads];
     __shared__ int s_warp[kEnumThreads / 32];
@@ -338,8 +346,6 @@ enum_emit_kernel(const EnumParams p, const unsigned* in_tile, const unsigned lon
     const Slot sl = decode_slot(p);
     int total;
     const int local = block_exclusive_scan(sl.keep ? 1 : 0, sl.local, s_flag, s_warp, total);
-    const long long base = (long long)(tile_off[blockIdx.x / kScanTile] + in_tile[blockIdx.x]);
-    if (total == 0 || base + total <= first || base >= first + count) return;
     if (sl.keep) {
         uint8_t* row = s_rows + (size_t)local * Ls;
         RowWriter w{reinterpret_cast<uint32_t*>(row), L / 4, 0ULL, 0, 0, 0};
@@ -519,51 +525,42 @@ static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int dep
 
 using namespace pde;
 
-// scratch shared by count + emit (per process; one host thread per device)
-static unsigned* g_sums = nullptr;
-static unsigned* g_in_tile = nullptr;
-static unsigned long long* g_tile = nullptr;
-static long long* g_total = nullptr;
-static long long g_cap = 0;
-static unsigned long long* g_dedup_keys = nullptr;
-static unsigned* g_dedup_vals = nullptr;
-static unsigned long long* g_dedup_cnt = nullptr;
-static unsigned g_dedup_cap = 0;
-
-// the scratch buffers belong to the device that was current when they were allocated: a process that switches
-// devices (one process per GPU is the normal deployment) gets fresh ones
-static int g_scratch_dev = -1, g_dedup_dev = -1;
+// The count pass (candidates per block + their two-level exclusive scan) is cached ON THE HANDLE: its buffers belong to
+// the exprset, are valid for one (depth, prune, depth_begin) on one device, and are freed with it -- no file-scope state,
+// and a windowed pde_enumerate (one window per rank or per chunk) does not repeat the pass.
 static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
-static int ensure_scratch(long long nblocks) {
-    const int dev = current_device();
-    if (dev != g_scratch_dev) { g_sums = nullptr; g_in_tile = nullptr; g_tile = nullptr; g_total = nullptr; g_cap = 0; g_scratch_dev = dev; }
-    if (nblocks <= g_cap) return PDE_OK;
-    cudaFree(g_sums); cudaFree(g_in_tile); cudaFree(g_tile); cudaFree(g_total);
-    g_sums = nullptr; g_in_tile = nullptr; g_tile = nullptr; g_total = nullptr; g_cap = 0;
-    PDE_CUDA(cudaMalloc(&g_sums, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&g_in_tile, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&g_tile, sizeof(unsigned long long) * (nblocks / kScanTile + 1)));
-    PDE_CUDA(cudaMalloc(&g_total, sizeof(long long)));
-    g_cap = nblocks;
-    return PDE_OK;
+static bool count_cached(const pde_exprset* e, const EnumParams& p) {
+    if (!e->d_count_sums || e->count_depth != p.depth || e->count_prune != p.prune || e->device != current_device()) return false;
+    for (int k = 0; k < p.depth; ++k) if (e->count_db[k] != p.depth_begin[k]) return false;
+    return e->count_blocks == p.seg_block[p.depth];
 }
 
-static int run_count(const EnumParams& p, cudaStream_t st, long long* total_host) {
+static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long long* total_host) {
     const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0) { if (total_host) *total_host = 0; return PDE_OK; }
-    int rc = ensure_scratch(nblocks);
-    if (rc) return rc;
+    if (count_cached(e, p)) { if (total_host) *total_host = e->count_total; return PDE_OK; }
+    cudaFree(e->d_count_sums); cudaFree(e->d_count_in_tile); cudaFree(e->d_count_tile);
+    e->d_count_sums = nullptr; e->d_count_in_tile = nullptr; e->d_count_tile = nullptr;
     const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
-    enum_count_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, g_sums);
-    scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(g_sums, g_in_tile, g_tile, (int)nblocks);
-    scan_super_kernel<<<1, 1024, 0, st>>>(g_tile, ntiles, g_total);
+    PDE_CUDA(cudaMalloc(&e->d_count_sums, sizeof(unsigned) * nblocks));
+    PDE_CUDA(cudaMalloc(&e->d_count_in_tile, sizeof(unsigned) * nblocks));
+    PDE_CUDA(cudaMalloc(&e->d_count_tile, sizeof(unsigned long long) * (ntiles + 1)));
+    long long* d_total = nullptr;
+    int rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
+    if (rc) return rc;
+    enum_count_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, e->d_count_sums);
+    scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(e->d_count_sums, e->d_count_in_tile, e->d_count_tile, (int)nblocks);
+    scan_super_kernel<<<1, 1024, 0, st>>>(e->d_count_tile, ntiles, d_total);
     count_launch(3);
     PDE_CUDA(cudaGetLastError());
-    if (total_host) {
-        PDE_CUDA(cudaMemcpyAsync(total_host, g_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
-        PDE_CUDA(cudaStreamSynchronize(st));
-    }
+    long long total = 0;
+    PDE_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PDE_CUDA(cudaStreamSynchronize(st));
+    scratch_free(d_total, st);
+    e->count_depth = p.depth; e->count_prune = p.prune; e->count_blocks = nblocks; e->count_total = total;
+    for (int k = 0; k < p.depth; ++k) e->count_db[k] = p.depth_begin[k];
+    if (total_host) *total_host = total;
     return PDE_OK;
 }
 
@@ -577,7 +574,7 @@ int pde_enumerate_count(const pde_exprset* e, const int32_t* depth_begin, int de
     int rc = fill_params(e, depth_begin, depth, prune, p);
     if (rc) return rc;
     long long total = 0;
-    rc = run_count(p, (cudaStream_t)stream, &total);
+    rc = run_count(const_cast<pde_exprset*>(e), p, (cudaStream_t)stream, &total);
     if (rc) return rc;
     *n_candidates = total;
     return PDE_OK;
@@ -595,13 +592,15 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
     if (count == 0) return PDE_OK;           // an empty window is a no-op (its buffers may be null: the reference just moves on, LBF:139-195)
     if (!triple || !code || !len || !hash) { set_error("pde_enumerate: null output"); return PDE_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    rc = run_count(p, st, nullptr);
+    long long total = 0;
+    rc = run_count(const_cast<pde_exprset*>(e), p, st, &total);
     if (rc) return rc;
     const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0) return PDE_OK;
+    if (first + count > total) { set_error("pde_enumerate: window [%lld, %lld) exceeds the %lld candidates", (long long)first, (long long)(first + count), total); return PDE_E_INVALID; }
     const size_t smem = (size_t)kEnumThreads * (enum_row_stride(L) + 8 + 12 + 1) + 16;
     PDE_CUDA(cudaFuncSetAttribute(enum_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enum_emit_kernel<<<(unsigned)nblocks, kEnumThreads, smem, st>>>(p, g_in_tile, g_tile, first, count, L, triple, code, len,
+    enum_emit_kernel<<<(unsigned)nblocks, kEnumThreads, smem, st>>>(p, e->d_count_sums, e->d_count_in_tile, e->d_count_tile, first, count, L, triple, code, len,
                                                                     reinterpret_cast<unsigned long long*>(hash));
     count_launch();
     PDE_CUDA(cudaGetLastError());
@@ -617,20 +616,15 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned cap = 1024;
     while ((long long)cap < 2 * n) cap <<= 1;
-    // grow-only scratch table, kept across calls (allocating and freeing 400 MB per call cost 8-70 ms
-    // around 1.7 ms of kernels)
-    if (current_device() != g_dedup_dev) { g_dedup_keys = nullptr; g_dedup_vals = nullptr; g_dedup_cnt = nullptr; g_dedup_cap = 0; g_dedup_dev = current_device(); }
-    if (cap > g_dedup_cap) {
-        cudaFree(g_dedup_keys); cudaFree(g_dedup_vals); cudaFree(g_dedup_cnt);
-        g_dedup_keys = nullptr; g_dedup_vals = nullptr; g_dedup_cnt = nullptr; g_dedup_cap = 0;
-        PDE_CUDA(cudaMalloc(&g_dedup_keys, sizeof(unsigned long long) * cap));
-        PDE_CUDA(cudaMalloc(&g_dedup_vals, sizeof(unsigned) * cap));
-        PDE_CUDA(cudaMalloc(&g_dedup_cnt, sizeof(unsigned long long)));
-        g_dedup_cap = cap;
-    }
-    unsigned long long* keys = g_dedup_keys;
-    unsigned* vals = g_dedup_vals;
-    unsigned long long* cnt = g_dedup_cnt;
+    // per-call table from the library's stream-ordered pool (kept warm between calls: allocating and freeing 400 MB
+    // with cudaMalloc cost 8-70 ms around 1.7 ms of kernels)
+    unsigned long long* keys = nullptr;
+    unsigned* vals = nullptr;
+    unsigned long long* cnt = nullptr;
+    int rc = scratch_alloc(reinterpret_cast<void**>(&keys), sizeof(unsigned long long) * cap, st);
+    if (!rc) rc = scratch_alloc(reinterpret_cast<void**>(&vals), sizeof(unsigned) * cap, st);
+    if (!rc) rc = scratch_alloc(reinterpret_cast<void**>(&cnt), sizeof(unsigned long long), st);
+    if (rc) { scratch_free(keys, st); scratch_free(vals, st); scratch_free(cnt, st); return rc; }
     PDE_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * cap, st));
     PDE_CUDA(cudaMemsetAsync(vals, 0xff, sizeof(unsigned) * cap, st));
     PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
@@ -643,6 +637,7 @@ int pde_dedup(const uint8_t* code, const uint8_t* len, const uint64_t* hash, int
     unsigned long long c = 0;
     PDE_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
     PDE_CUDA(cudaStreamSynchronize(st));
+    scratch_free(keys, st); scratch_free(vals, st); scratch_free(cnt, st);
     if (n_unique) *n_unique = (int64_t)c;
     return PDE_OK;
 }

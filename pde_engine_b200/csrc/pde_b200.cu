@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -30,6 +31,37 @@ int cuda_fail(int err, const char* what) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+// ---- library-owned, stream-ordered scratch pool (one per device) ----
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+int scratch_alloc(void** ptr, size_t bytes, void* stream) {
+    int dev = 0;
+    PDE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return PDE_E_INVALID; }
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pools[dev]) {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            PDE_CUDA(cudaMemPoolCreate(&g_pools[dev], &props));
+            unsigned long long keep = ~0ULL;                    // never give memory back between calls
+            PDE_CUDA(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = g_pools[dev];
+    }
+    PDE_CUDA(cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pool, (cudaStream_t)stream));
+    return PDE_OK;
+}
+
+void scratch_free(void* ptr, void* stream) {
+    if (ptr) cudaFreeAsync(ptr, (cudaStream_t)stream);
+}
 
 bool have_device() {
     int n = 0;
