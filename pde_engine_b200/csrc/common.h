@@ -73,6 +73,7 @@ struct pde_exprset {
     unsigned* d_count_sums = nullptr;             // candidates per block
     unsigned* d_count_in_tile = nullptr;          // exclusive prefix inside a 1024-block tile
     unsigned long long* d_count_tile = nullptr;   // exclusive prefix of the tile totals
+    std::vector<unsigned long long> count_tile_host;   // the same on the host: a window launches only its tiles
     std::vector<uint32_t> desc;         // [n][2] splice descriptors (enumerate.cu)
     std::vector<uint8_t> wpool;         // whole programs, padded by 8 bytes
     uint32_t* d_desc = nullptr;

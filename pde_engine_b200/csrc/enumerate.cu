@@ -22,6 +22,8 @@
 // stores; measured 2.9 TB/s = 75 % of the write-only HBM rate (profiles/README.md).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
+#include <vector>
 
 #include "common.h"
 
@@ -49,6 +51,7 @@ struct EnumParams {
     // segment 0 = unary (160 consecutive slots per block), segment d1 >= 1 = binary (32 pairs x 5 ops per block)
     long long seg_block[kMaxDepth + 1];    // first block of the segment; seg_block[depth] = number of blocks
     long long seg_groups[kMaxDepth + 1];   // unary: slots; binary: pairs
+    long long block0;                      // first block of this launch (windowed passes launch only the tiles they need)
 };
 
 // enumerator unary op index -> opcode (iteration order of UNARY_OPS, expression_operations.py:80-89)
@@ -71,7 +74,7 @@ __device__ __forceinline__ Slot decode_slot(const EnumParams& p) {
     Slot r;
     r.keep = false; r.op = 0; r.a = 0; r.b = -1;
     const int d = p.depth;
-    const long long blk = blockIdx.x;
+    const long long blk = p.block0 + blockIdx.x;
     if (blk < p.seg_block[1]) {
         // unary, LBF:142-153
         r.local = threadIdx.x;
@@ -326,9 +329,10 @@ enum_emit_kernel(const EnumParams p, const unsigned* sums, const unsigned* in_ti
     // A block outside the window [first, first + count) leaves before it touches shared memory: the count pass
     // already knows every block's candidate range, so an 8-way sharded pass costs each rank 1/8 of the work
     // (+ ~10 us of empty blocks), not a full pass.
-    const long long base = (long long)(tile_off[blockIdx.x / kScanTile] + in_tile[blockIdx.x]);
+    const long long blk = p.block0 + blockIdx.x;
+    const long long base = (long long)(tile_off[blk / kScanTile] + in_tile[blk]);
     {
-        const long long n_blk = (long long)sums[blockIdx.x];
+        const long long n_blk = (long long)sums[blk];
         if (n_blk == 0 || base + n_blk <= first || base >= first + count) return;
     }
     extern __shared__ __align__(16) uint8_t s_rows[];   // [kEnumThreads][L + 16] rows, then per-row hash / triple / len
@@ -499,7 +503,7 @@ static int fill_params(const pde_exprset* e, const int32_t* depth_begin, int dep
     if (int rc = exprset_ensure_device(const_cast<pde_exprset*>(e))) return rc;
     if (depth_begin[0] != 0 || depth_begin[depth - 1] != e->n) { set_error("depth_begin must start at 0 and end at n_expr"); return PDE_E_INVALID; }
     p.desc = reinterpret_cast<const uint2*>(e->d_desc); p.wpool = e->d_wpool; p.attrs = e->d_attrs; p.rank = e->d_rank;
-    p.depth = depth; p.prune = prune;
+    p.depth = depth; p.prune = prune; p.block0 = 0;
     for (int k = 0; k < depth; ++k) {
         p.depth_begin[k] = depth_begin[k];
         if (k > 0 && depth_begin[k] < depth_begin[k - 1]) { set_error("depth_begin must be non-decreasing"); return PDE_E_INVALID; }
@@ -555,7 +559,9 @@ static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long 
     count_launch(3);
     PDE_CUDA(cudaGetLastError());
     long long total = 0;
+    e->count_tile_host.assign(ntiles, 0ULL);
     PDE_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PDE_CUDA(cudaMemcpyAsync(e->count_tile_host.data(), e->d_count_tile, sizeof(unsigned long long) * ntiles, cudaMemcpyDeviceToHost, st));
     PDE_CUDA(cudaStreamSynchronize(st));
     scratch_free(d_total, st);
     e->count_depth = p.depth; e->count_prune = p.prune; e->count_blocks = nblocks; e->count_total = total;
@@ -600,7 +606,14 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
     if (first + count > total) { set_error("pde_enumerate: window [%lld, %lld) exceeds the %lld candidates", (long long)first, (long long)(first + count), total); return PDE_E_INVALID; }
     const size_t smem = (size_t)kEnumThreads * (enum_row_stride(L) + 8 + 12 + 1) + 16;
     PDE_CUDA(cudaFuncSetAttribute(enum_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enum_emit_kernel<<<(unsigned)nblocks, kEnumThreads, smem, st>>>(p, e->d_count_sums, e->d_count_in_tile, e->d_count_tile, first, count, L, triple, code, len,
+    // launch only the 1024-block tiles whose candidate range meets the window (the host keeps the tile prefix)
+    const std::vector<unsigned long long>& tp = e->count_tile_host;
+    long long t0 = 0, t1 = (long long)tp.size() - 1;
+    while (t0 < t1 && tp[t0 + 1] <= (unsigned long long)first) ++t0;
+    while (t1 > t0 && tp[t1] >= (unsigned long long)(first + count)) --t1;
+    p.block0 = t0 * kScanTile;
+    const long long launch_blocks = std::min<long long>(nblocks, (t1 + 1) * kScanTile) - p.block0;
+    enum_emit_kernel<<<(unsigned)launch_blocks, kEnumThreads, smem, st>>>(p, e->d_count_sums, e->d_count_in_tile, e->d_count_tile, first, count, L, triple, code, len,
                                                                     reinterpret_cast<unsigned long long*>(hash));
     count_launch();
     PDE_CUDA(cudaGetLastError());

@@ -29,3 +29,20 @@ for r in range(reps):
     ms = a.elapsed_time(b)
     print(f"L {L} rep {r}: {ms:.3f} ms  {n5} candidates  {n5 * (L + 21) / ms / 1e6:.0f} GB/s (incl. output allocation)", flush=True)
 print("nonempty rows:", int((cand["len"] > 0).sum()), "mean len:", float(cand["len"].float().mean()))
+# one eighth of the index space (what one of 8 ranks enumerates): should cost ~1/8 of the full pass
+import ctypes as C
+from pde_engine_b200 import _lib as _l
+dbc = (C.c_int32 * len(db))(*db)
+for first, count, tag in ((0, n5, "full"), (3 * (n5 // 8), n5 // 8, "window 3/8..4/8")):
+    out = {k: v[:max(count, 1)] for k, v in cand.items()}
+    best = 1e9
+    for r in range(reps + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _l.check(_l.lib.pde_enumerate(es._h, dbc, 5, 1, first, count, L, C.c_void_p(out["triple"].data_ptr()),
+                                      C.c_void_p(out["code"].data_ptr()), C.c_void_p(out["len"].data_ptr()),
+                                      C.c_void_p(out["hash"].data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    print(f"{tag}: {best:.3f} ms for {count} candidates (count pass cached on the handle)", flush=True)
