@@ -121,7 +121,8 @@ int  pde_compile_exprs(pde_session *s, const char *const *strs, int n, pde_exprs
 /* same, for one NUL-separated blob: string i = blob + offsets[i], offsets[n] = blob size (each
  * string NUL terminated).  The parse runs on up to 16 host threads (PDE_B200_COMPILE_THREADS);
  * table slots are assigned afterwards in string order, so the bytecode does not depend on the
- * thread count. */
+ * thread count.  offsets may be NULL: the blob is then n NUL-terminated strings back to back and
+ * the library finds the terminators itself. */
 int  pde_compile_exprs_packed(pde_session *s, const char *blob, const uint32_t *offsets, int n, pde_exprset **out);
 void pde_exprset_free(pde_exprset *e);
 int  pde_exprset_size(const pde_exprset *e, int *n_expr, int *n_terms, int *n_pool_bytes);

@@ -116,15 +116,16 @@ class ExprSet:
         if blob is None:
             blob, n = pack_strings(strs)
         self.n = int(n)
-        # one NUL-separated blob + the offsets of the strings in it (found with two vectorised numpy passes):
-        # building a ctypes array of 10^5 char pointers costs more than compiling the strings
-        ends = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0) if self.n else np.zeros(0, np.int64)
-        if len(ends) != self.n:
+        # one blob of NUL-terminated strings; the library finds the terminators (offsets = NULL): building a ctypes
+        # array of 10^5 char pointers, or the offsets with numpy, costs more than compiling the strings
+        if blob.count(b"\0") != self.n or (self.n and not blob.endswith(b"\0")):
             raise ValueError("expression strings must not contain NUL")
-        off = np.zeros(self.n + 1, dtype=np.uint32)
-        off[1:] = ends + 1
         h = C.c_void_p()
-        check(lib.pde_compile_exprs_packed(session._h, bytes(blob) if not isinstance(blob, bytes) else blob, _np_ptr(off), self.n, C.byref(h)))
+        check(lib.pde_compile_exprs_packed(session._h, bytes(blob) if not isinstance(blob, bytes) else blob, None, self.n, C.byref(h)))
+        if self.n:
+            got = C.c_int()
+            check(lib.pde_exprset_size(h, C.byref(got), None, None))
+            assert got.value == self.n
         self._h = h
 
     def __del__(self):

@@ -348,12 +348,12 @@ struct Worker {
     std::vector<uint32_t> term_off;     // end offset (in `pool`) of every term
     std::vector<Fix> fixes;
     std::vector<uint32_t> n_terms, pool_end, fix_end;   // per expression (cumulative ends)
-    std::vector<uint8_t> flags;
+    std::vector<uint8_t> flags, attrs;
 
     void run(const char* blob, const uint32_t* off, const pde_session* sess) {
         Arena ar;
         const int n = hi - lo;
-        n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0);
+        n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0); attrs.assign(n, 0);
         pool.reserve((size_t)n * 24);
         std::vector<Emitter::Term> terms;
         for (int k = 0; k < n; ++k) {
@@ -383,6 +383,11 @@ struct Worker {
             n_terms[k] = (uint32_t)(term_sign.size() - nt0);
             pool_end[k] = (uint32_t)pool.size();
             fix_end[k] = (uint32_t)fixes.size();
+            uint8_t attr = 0;                                  // string attributes of the prune predicates (LBF:134-152)
+            if (has_vars(str)) attr |= PDE_ATTR_HAS_VARS;
+            if (str[0] == '1' && str[1] == '\0') attr |= PDE_ATTR_IS_ONE;
+            if (strncmp(str, "inv(", 4) == 0) attr |= PDE_ATTR_STARTS_INV;
+            attrs[k] = attr;
         }
     }
 };
@@ -421,7 +426,6 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     e->flags.assign(n, 0);
     e->attrs.assign(n, 0);
     e->term_begin.assign(n + 1, 0);
-    e->term_off.push_back(0);
     e->str_off.assign(off, off + n + (n > 0 ? 1 : 0));
     if (n > 0) e->str_blob.assign(blob, blob + off[n]);
     const bool prof = getenv("PDE_B200_PROFILE") != nullptr;
@@ -444,46 +448,75 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
         for (auto& x : th) x.join();
     }
     auto t_b = tnow();
-    // ---- phase B (sequential, in expression order): table slots, pool assembly ----
-    size_t total_pool = 0, total_terms = 0;
-    for (auto& w : workers) { total_pool += w.pool.size(); total_terms += w.term_sign.size(); }
-    e->pool.reserve(total_pool); e->term_sign.reserve(total_terms); e->term_off.reserve(total_terms + 1);
+    // ---- phase B: table slots (sequential, in expression order -- the numbering is part of the bytecode), then the
+    //      assembly of the pools at precomputed offsets (parallel again) ----
+    // B1: slots.  Only the CONST / POW placeholders are visited; an expression whose constants do not fit the
+    //     tables any more is flagged and its slots are rolled back (tables stay append-only for successful compiles).
     for (auto& w : workers) {
-        uint32_t p0 = 0, f0 = 0, t0 = 0;
+        uint32_t f0 = 0;
         for (int k = 0; k < w.hi - w.lo; ++k) {
-            const int i = w.lo + k;
-            const char* str = blob + off[i];
-            uint8_t attr = 0;
-            if (has_vars(str)) attr |= PDE_ATTR_HAS_VARS;
-            if (strcmp(str, "1") == 0) attr |= PDE_ATTR_IS_ONE;
-            if (strncmp(str, "inv(", 4) == 0) attr |= PDE_ATTR_STARTS_INV;
-            e->attrs[i] = attr;
-            e->term_begin[i] = (uint32_t)e->term_sign.size();
-            e->flags[i] = w.flags[k];
-            const uint32_t p1 = w.pool_end[k], f1 = w.fix_end[k], nt = w.n_terms[k];
-            if (!e->flags[i]) {
+            const uint32_t f1 = w.fix_end[k];
+            if (!w.flags[k] && f1 > f0) {
                 const size_t nc0 = s->const_keys.size(), np0 = s->pow_keys.size();
                 for (uint32_t f = f0; f < f1; ++f) {
                     const int slot = table_slot(s, w.fixes[f]);
-                    if (slot < 0) { e->flags[i] = PDE_FLAG_TABLE_FULL; break; }
+                    if (slot < 0) { w.flags[k] = PDE_FLAG_TABLE_FULL; break; }
                     w.pool[w.fixes[f].pos] = (uint8_t)((w.fixes[f].is_pow ? PDE_OP_POW0 : PDE_OP_CONST0) + slot);
                 }
-                if (e->flags[i]) {   // tables stay append-only only for successful compiles
+                if (w.flags[k]) {
                     s->const_keys.resize(nc0); s->const_vals.resize(nc0); s->const_num.resize(nc0); s->const_den.resize(nc0);
                     s->pow_keys.resize(np0); s->pow_vals.resize(np0); s->pow_num.resize(np0); s->pow_den.resize(np0);
-                } else {
-                    const uint32_t base = (uint32_t)e->pool.size();
-                    e->pool.insert(e->pool.end(), w.pool.begin() + p0, w.pool.begin() + p1);
-                    for (uint32_t t = 0; t < nt; ++t) {
-                        e->term_sign.push_back(w.term_sign[t0 + t]);
-                        e->term_off.push_back(base + (w.term_off[t0 + t] - p0));
-                    }
                 }
             }
-            p0 = p1; f0 = f1; t0 += nt;
+            f0 = f1;
         }
     }
-    e->term_begin[n] = (uint32_t)e->term_sign.size();
+    // B2: sizes per worker (expressions flagged in B1 contribute nothing), exclusive offsets
+    std::vector<size_t> pool_base(nthreads + 1, 0), term_base(nthreads + 1, 0);
+    for (int t = 0; t < nthreads; ++t) {
+        Worker& w = workers[t];
+        size_t pb = 0, tb = 0;
+        uint32_t p0 = 0;
+        for (int k = 0; k < w.hi - w.lo; ++k) {
+            if (!w.flags[k]) { pb += w.pool_end[k] - p0; tb += w.n_terms[k]; }
+            p0 = w.pool_end[k];
+        }
+        pool_base[t + 1] = pool_base[t] + pb;
+        term_base[t + 1] = term_base[t] + tb;
+    }
+    e->pool.resize(pool_base[nthreads]);
+    e->term_sign.resize(term_base[nthreads]);
+    e->term_off.resize(term_base[nthreads] + 1);
+    e->term_off[0] = 0;
+    // B3: copy (parallel)
+    auto assemble = [&](int t) {
+        Worker& w = workers[t];
+        size_t pb = pool_base[t], tb = term_base[t];
+        uint32_t p0 = 0, t0 = 0;
+        for (int k = 0; k < w.hi - w.lo; ++k) {
+            const int i = w.lo + k;
+            const uint32_t p1 = w.pool_end[k], nt = w.n_terms[k];
+            e->attrs[i] = w.attrs[k];
+            e->flags[i] = w.flags[k];
+            e->term_begin[i] = (uint32_t)tb;
+            if (!w.flags[k]) {
+                memcpy(e->pool.data() + pb, w.pool.data() + p0, p1 - p0);
+                for (uint32_t q = 0; q < nt; ++q) {
+                    e->term_sign[tb + q] = w.term_sign[t0 + q];
+                    e->term_off[tb + q + 1] = (uint32_t)(pb + (w.term_off[t0 + q] - p0));
+                }
+                pb += p1 - p0; tb += nt;
+            }
+            p0 = p1; t0 += nt;
+        }
+    };
+    if (nthreads == 1) assemble(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(assemble, t);
+        for (auto& x : th) x.join();
+    }
+    e->term_begin[n] = (uint32_t)term_base[nthreads];
     if (prof) {
         auto t_c = tnow();
         fprintf(stderr, "[pde_compile] n=%d threads=%d parse %.2f ms, slots+assembly %.2f ms\n", n, nthreads,
@@ -598,7 +631,23 @@ int pde_compile_exprs(pde_session* s, const char* const* strs, int n, pde_exprse
 }
 
 int pde_compile_exprs_packed(pde_session* s, const char* blob, const uint32_t* offsets, int n, pde_exprset** out) {
-    if (!s || !out || n < 0 || (n > 0 && (!blob || !offsets))) { pde::set_error("pde_compile_exprs_packed: bad argument"); return PDE_E_INVALID; }
+    if (!s || !out || n < 0 || (n > 0 && !blob)) { pde::set_error("pde_compile_exprs_packed: bad argument"); return PDE_E_INVALID; }
+    std::vector<uint32_t> found;
+    if (!offsets && n > 0) {
+        // offsets = NULL: the blob is n NUL-terminated strings back to back; find the terminators here (memchr runs at
+        // memory speed; numpy needed 5-10 ms for the 4.7 MB of the depth-4 uniques)
+        found.resize((size_t)n + 1);
+        const char* p = blob;
+        for (int i = 0; i < n; ++i) {
+            found[i] = (uint32_t)(p - blob);
+            const char* q = (const char*)memchr(p, 0, (size_t)0xffffffffu - (size_t)(p - blob));
+            if (!q) { pde::set_error("pde_compile_exprs_packed: string %d is not NUL terminated", i); return PDE_E_INVALID; }
+            p = q + 1;
+            if ((size_t)(p - blob) >= 0xffffffffULL) { pde::set_error("pde_compile_exprs_packed: input too large"); return PDE_E_OVERFLOW; }
+        }
+        found[n] = (uint32_t)(p - blob);
+        offsets = found.data();
+    }
     for (int i = 0; i < n; ++i) {
         if (offsets[i + 1] <= offsets[i] || blob[offsets[i + 1] - 1] != '\0') {
             pde::set_error("pde_compile_exprs_packed: string %d is not NUL terminated at offsets[%d] - 1", i, i + 1);
