@@ -74,7 +74,7 @@ class Session:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:          # (module globals are gone at interpreter shutdown)
             lib.pde_session_free(h)
 
     def tables(self):
@@ -130,7 +130,7 @@ class ExprSet:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.pde_exprset_free(h)
 
     def sizes(self):
@@ -214,7 +214,7 @@ class ResidualProgram:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.pde_program_free(h)
 
     def point_table(self, pts: np.ndarray) -> np.ndarray:

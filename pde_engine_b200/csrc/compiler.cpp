@@ -105,7 +105,7 @@ struct Parser {
     const pde_session* sess;
     Arena& ar;
     int depth = 0;
-    Parser(const char* str, const pde_session* se, Arena& a) : s(str), n(strlen(str)), sess(se), ar(a) {}
+    Parser(const char* str, size_t len, const pde_session* se, Arena& a) : s(str), n(len), sess(se), ar(a) {}
 
     void ws() { while (pos < n && (s[pos] == ' ' || s[pos] == '\t')) ++pos; }
     bool peek(char c) { ws(); return pos < n && s[pos] == c; }
@@ -204,10 +204,12 @@ struct Parser {
         if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') {
             size_t st = pos;
             while (pos < n && ((s[pos] >= 'a' && s[pos] <= 'z') || (s[pos] >= 'A' && s[pos] <= 'Z') || (s[pos] >= '0' && s[pos] <= '9') || s[pos] == '_')) ++pos;
-            const std::string name(s + st, pos - st);
+            const char* nm = s + st;
+            const size_t nl = pos - st;
+            auto is = [&](const std::string& t) { return t.size() == nl && memcmp(t.data(), nm, nl) == 0; };
             if (peek('(')) {
                 ++pos;
-                int opc = func_opcode(name);
+                int opc = func_opcode(nm, nl);
                 Node* arg = parse_expr();
                 if (peek(',')) throw Unsupported();
                 if (!peek(')')) throw Unsupported();
@@ -217,25 +219,32 @@ struct Parser {
                 x->idx = opc; x->a = arg;
                 return x;
             }
-            if (name == sess->var[0]) { Node* x = ar.make(K_VAR); x->idx = 0; return x; }
-            if (name == sess->var[1]) { Node* x = ar.make(K_VAR); x->idx = 1; return x; }
+            if (is(sess->var[0])) { Node* x = ar.make(K_VAR); x->idx = 0; return x; }
+            if (is(sess->var[1])) { Node* x = ar.make(K_VAR); x->idx = 1; return x; }
             for (size_t i = 0; i < sess->named.size(); ++i)
-                if (name == sess->named[i]) { Node* x = ar.make(K_NCONST); x->idx = (int)i; return x; }
+                if (is(sess->named[i])) { Node* x = ar.make(K_NCONST); x->idx = (int)i; return x; }
             throw Unsupported();
         }
         throw Unsupported();
     }
-    static int func_opcode(const std::string& f) {
-        if (f == "neg") return PDE_OP_FN_NEG;
-        if (f == "inv") return PDE_OP_FN_INV;
-        if (f == "square") return PDE_OP_FN_SQUARE;
-        if (f == "pow_3_2") return PDE_OP_FN_POW32;
-        if (f == "pow_neg_3_2") return PDE_OP_FN_POWN32;
-        if (f == "exp_neg") return PDE_OP_FN_EXPNEG;
-        if (f == "sqrt") return PDE_OP_SQRT;
-        if (f == "exp") return PDE_OP_EXP;
-        if (f == "Abs") return PDE_OP_ABS;
-        return -1;
+    static int func_opcode(const char* f, size_t n) {
+        auto eq = [&](const char* t, size_t tn) { return n == tn && memcmp(f, t, tn) == 0; };
+        switch (n) {
+            case 3:
+                if (eq("neg", 3)) return PDE_OP_FN_NEG;
+                if (eq("inv", 3)) return PDE_OP_FN_INV;
+                if (eq("exp", 3)) return PDE_OP_EXP;
+                if (eq("Abs", 3)) return PDE_OP_ABS;
+                return -1;
+            case 4: return eq("sqrt", 4) ? PDE_OP_SQRT : -1;
+            case 6: return eq("square", 6) ? PDE_OP_FN_SQUARE : -1;
+            case 7:
+                if (eq("pow_3_2", 7)) return PDE_OP_FN_POW32;
+                if (eq("exp_neg", 7)) return PDE_OP_FN_EXPNEG;
+                return -1;
+            case 11: return eq("pow_neg_3_2", 11) ? PDE_OP_FN_POWN32 : -1;
+            default: return -1;
+        }
     }
     Node* binop(char op, Node* l, Node* r) {
         if (l->kind == K_CONST && r->kind == K_CONST) {
@@ -269,12 +278,27 @@ struct Fix {
     i64 num, den;
 };
 
+// Term lists live on the stack up to 24 entries (a heap allocation per additive group was a visible share of the parse)
+template <class T, int N>
+struct SmallVec {
+    T inl[N];
+    std::vector<T> big;
+    int n = 0;
+    void push_back(const T& v) { if (n < N) inl[n] = v; else { if (n == N) big.assign(inl, inl + N); big.push_back(v); } ++n; }
+    T& operator[](size_t i) { return n <= N ? inl[i] : big[i]; }
+    size_t size() const { return (size_t)n; }
+    void clear() { n = 0; big.clear(); }
+    T* begin() { return n <= N ? inl : big.data(); }
+    T* end() { return begin() + n; }
+};
+
 struct Emitter {
     std::vector<uint8_t>& out;
     std::vector<Fix>& fixes;
     Arena& ar;
 
     struct Term { int sign; Node* body; };
+    typedef SmallVec<Term, 24> Terms;
 
     // leading unary minus: leftmost leaf of the * / chain
     Node* extract_sign(Node* t, int& sign) {
@@ -290,8 +314,8 @@ struct Emitter {
         return t;
     }
 
-    void split_terms(Node* ir, std::vector<Term>& terms) {
-        std::vector<Term> chain;
+    void split_terms(Node* ir, Terms& terms) {
+        Terms chain;
         while (ir->kind == K_BIN && (ir->op == '+' || ir->op == '-')) {
             chain.push_back({ir->op == '+' ? 1 : -1, ir->b});
             ir = ir->a;
@@ -305,7 +329,7 @@ struct Emitter {
     }
 
     void emit(Node* ir) {
-        std::vector<Term> terms;
+        Terms terms;
         split_terms(ir, terms);
         for (size_t k = 0; k < terms.size(); ++k) {
             emit_term(terms[k].body);
@@ -355,13 +379,13 @@ struct Worker {
         const int n = hi - lo;
         n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0); attrs.assign(n, 0);
         pool.reserve((size_t)n * 24);
-        std::vector<Emitter::Term> terms;
+        Emitter::Terms terms;
         for (int k = 0; k < n; ++k) {
             const char* str = blob + off[lo + k];
             const size_t pool0 = pool.size(), nt0 = term_sign.size(), nf0 = fixes.size();
             try {
                 ar.reset();
-                Parser ps(str, sess, ar);
+                Parser ps(str, (size_t)(off[lo + k + 1] - off[lo + k] - 1), sess, ar);
                 Node* ir = ps.parse_expr();
                 ps.ws();
                 if (ps.pos != ps.n) throw Unsupported();
@@ -435,7 +459,7 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     int nthreads = 1;
     if (const char* ev = getenv("PDE_B200_COMPILE_THREADS")) nthreads = atoi(ev);
     else nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-    nthreads = std::max(1, std::min(nthreads, n / 4096 + 1));
+    nthreads = std::max(1, std::min(nthreads, n / 1024 + 1));
     std::vector<Worker> workers(nthreads);
     for (int t = 0; t < nthreads; ++t) {
         workers[t].lo = (int)((long long)n * t / nthreads);

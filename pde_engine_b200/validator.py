@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import json
 import os
+import sys
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -66,6 +67,38 @@ class BatchVerdict:
             "confirm_pass": None if self.confirm is None else [int(v) for v in self.confirm[i]],
             "ref_points_R_S": None if self.ref_rs is None else [[float(v) for v in row] for row in self.ref_rs[i]],
         }
+
+
+def _cut_blob(blob: bytes, n: int, bounds: Sequence[int]):
+    """Cut a blob of n NUL-terminated strings at the string indices `bounds` (0 = bounds[0] < ... < bounds[-1] = n)
+    without materialising all terminator positions: jump close to the expected byte position, count, then walk the
+    few remaining terminators.  Returns [(byte_lo, byte_hi, str_lo, str_hi)]."""
+    cuts, b_lo = [], 0
+    mean = len(blob) / max(n, 1)
+    for s_lo, s_hi in zip(bounds[:-1], bounds[1:]):
+        if s_hi == n:
+            b_hi = len(blob)
+        else:
+            guess = min(len(blob), b_lo + int((s_hi - s_lo) * mean))
+            k = blob.find(b"\0", guess)
+            pos = (k + 1) if k >= 0 else len(blob)
+            have = s_lo + blob.count(b"\0", b_lo, pos)
+            while have < s_hi:                                  # walk forward
+                pos = blob.index(b"\0", pos) + 1
+                have += 1
+            while have > s_hi:                                  # walk back: drop the last string before pos
+                pos = blob.rindex(b"\0", b_lo, pos - 1) + 1
+                have -= 1
+            b_hi = pos
+        cuts.append((b_lo, b_hi, s_lo, s_hi))
+        b_lo = b_hi
+    return cuts
+
+
+# Shares of a large batch per pipeline part (part k + 1 is compiled while the device validates part k).  Measured on the
+# 143 461 depth-4 uniques: three parts 41.6 ms, five uneven parts (small first and last) 43.2 ms -- the host work
+# (compile 25 ms) exceeds the kernel (23.5 ms), so more parts only add fixed per-part cost.
+PART_SHARES = (0.30, 0.36, 0.34)
 
 
 class GpuBatchValidator:
@@ -166,9 +199,12 @@ class GpuBatchValidator:
         (NUL-terminated strings, the compiler's own input format): header [cmd, n, bytes of shard 0..world-1], then the
         payload.  Pickling the string list instead cost 44 + 25 ms for the 143 461 depth-4 uniques -- more than
         compiling and validating them.  Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
+        import time
         import torch
         from .distributed import shard_range
         dist, grp, rank, world = d
+        prof = os.environ.get("PDE_B200_PROFILE") is not None
+        tm = [time.perf_counter()]
         cdev = self._comm_device(dist, grp)
         hdr = torch.zeros(world + 2, dtype=torch.int64, device=cdev)
         blobs = None
@@ -185,14 +221,17 @@ class GpuBatchValidator:
             payload = torch.from_numpy(np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()).to(cdev)
         else:
             payload = torch.empty(sum(sizes_b), dtype=torch.uint8, device=cdev)
+        tm.append(time.perf_counter())
         dist.broadcast(payload, src=0, group=grp)
         first, count = shard_range(n, rank, world)
+        tm.append(time.perf_counter())
         if rank == 0:
             bv = self._prefilter_local(strs[first:first + count], compile_threads=max(1, (os.cpu_count() or 1) // world), blob=blobs[0])
         else:
             lo = sum(sizes_b[:rank])
             mine = payload[lo:lo + sizes_b[rank]].cpu().numpy().tobytes()
             bv = self._prefilter_local(None, compile_threads=max(1, (os.cpu_count() or 1) // world), blob=mine, n=count)
+        tm.append(time.perf_counter())
         # the verdict columns of the shard as ONE byte buffer in native dtypes (struct of arrays, 97 B per candidate;
         # a float64 row per candidate cost more host time in conversions than the kernel takes)
         sizes = [shard_range(n, r, world)[1] for r in range(world)]
@@ -213,6 +252,10 @@ class GpuBatchValidator:
         pad = torch.from_numpy(buf).to(cdev)
         got = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
         dist.gather(pad, got, dst=0, group=grp)
+        tm.append(time.perf_counter())
+        if prof:
+            print(f"[sharded_prefilter rank {rank}] pack+header {1e3 * (tm[1] - tm[0]):.1f} ms, payload {1e3 * (tm[2] - tm[1]):.1f}, "
+                  f"local filter {1e3 * (tm[3] - tm[2]):.1f}, rows+gather {1e3 * (tm[4] - tm[3]):.1f}", file=sys.stderr, flush=True)
         if rank != 0:
             return None
         host = [g.cpu().numpy() for g in got]
@@ -255,17 +298,23 @@ class GpuBatchValidator:
         }
         flags = np.zeros(n, np.uint8)
         n_uncompiled = 0
-        # a few parts for large batches (part k + 1 is compiled while the device validates part k),
-        # fixed-size chunks only for very large ones
+        # a few parts for large batches (part k + 1 is compiled while the device validates part k), fixed-size chunks
+        # only for very large ones; every boundary is a multiple of 32 (survivor words never straddle two parts)
         if n > 2 * self.PIPELINE_CHUNK:
-            step = self.PIPELINE_CHUNK
+            bounds = list(range(0, n, self.PIPELINE_CHUNK)) + [n]
         elif n >= self.SPLIT_MIN:
-            parts = int(os.environ.get("PDE_B200_SPLIT", "3"))     # measured on the 143 461 depth-4 uniques: 47 / 42 / 53 ms for 2 / 3 / 4 parts, 52 unsplit
-            step = ((n + parts - 1) // parts + 31) // 32 * 32
+            shares = [float(x) for x in os.environ["PDE_B200_SHARES"].split(",")] if "PDE_B200_SHARES" in os.environ else PART_SHARES
+            acc, bounds = 0.0, [0]
+            for sh in shares[:-1]:
+                acc += sh
+                b = min(n, int(acc * n) // 32 * 32)
+                if b > bounds[-1]:
+                    bounds.append(b)
+            bounds.append(n)
         else:
-            step = max(n, 1)
+            bounds = [0, n] if n else [0]
+        step = max([b - a for a, b in zip(bounds[:-1], bounds[1:])] + [1])
         copied = None                      # event: the previous chunk's H2D copies have left the staging buffers
-        ends = None
         # pinned staging buffers, grown on demand and reused: pageable copies of the 18 MB of programs and the
         # 12 MB of results cost several milliseconds each way
         cap = min(step, max(n, 1))
@@ -273,23 +322,28 @@ class GpuBatchValidator:
             self._pin = {"code": torch.empty((cap, self.L), dtype=torch.uint8).pin_memory(),
                          "len": torch.empty(cap, dtype=torch.uint8).pin_memory(),
                          "host": {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}, "out_n": n}
-        for lo in range(0, n, step):
-            hi = min(lo + step, n)
+        import time
+        prof = os.environ.get("PDE_B200_PROFILE") is not None
+        tms = []
+        if blob is not None:
+            cuts = _cut_blob(blob, n, bounds)              # [(byte_lo, byte_hi, lo, hi)]
+        else:
+            cuts = [(None, None, lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:])]
+        for b0, b1, lo, hi in cuts:
+            t_a = time.perf_counter()
             if blob is None:
                 exprs = self.session.compile(strs[lo:hi])
-            else:                              # byte range of strings lo..hi-1 in the blob
-                if ends is None:
-                    ends = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0) + 1 if n else np.zeros(0, np.int64)
-                    if len(ends) != n:
-                        raise ValueError("blob does not hold n NUL-terminated strings")
-                b0 = int(ends[lo - 1]) if lo else 0
-                exprs = self.session.compile_blob(blob[b0:int(ends[hi - 1])] if (lo or hi < n) else blob, hi - lo)
+            else:
+                exprs = self.session.compile_blob(blob if (b0 == 0 and b1 == len(blob)) else blob[b0:b1], hi - lo)
+            t_b = time.perf_counter()
             code_h, len_h = self._pin["code"][:hi - lo], self._pin["len"][:hi - lo]
             if copied is not None:
                 copied.synchronize()       # (not the kernel: only the copies out of the staging buffers)
+            t_c = time.perf_counter()
             exprs.programs(self.L, out=(code_h.numpy(), len_h.numpy()))
             flags[lo:hi] = exprs.flags()
             n_uncompiled += int((len_h == 0).sum())
+            t_d = time.perf_counter()
             code_t = code_h.to(dev, non_blocking=True)
             len_t = len_h.to(dev, non_blocking=True)
             copied = torch.cuda.Event()
@@ -298,14 +352,21 @@ class GpuBatchValidator:
             core.validate(self.session, self.program, code_t, len_t, self.pts, self.table, None,
                           tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac, t0=self.t0,
                           confirm_points=self.confirm_points, n_ref=3, spill_slots=self.spill_slots, out=part)
+            tms.append((t_b - t_a, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
+        t_e = time.perf_counter()
         host = {}
         for k, v in out.items():
             h = self._pin["host"][k][:v.shape[0]]
             h.copy_(v, non_blocking=True)
             host[k] = h
         torch.cuda.current_stream().synchronize()
+        t_f = time.perf_counter()
         host = {k: v.numpy().copy() for k, v in host.items()}      # the staging buffers are reused by the next call
         bv = BatchVerdict(strs, flags, host, n=n)
+        if prof:
+            print("[prefilter_local] parts (compile, wait-copy, programs, h2d+launch) ms: " +
+                  "; ".join("/".join(f"{1e3 * x:.1f}" for x in t) for t in tms) +
+                  f" | drain {1e3 * (t_f - t_e):.1f} host-copies+verdict {1e3 * (time.perf_counter() - t_f):.1f}", file=sys.stderr, flush=True)
         self.stats["gpu_evaluated"] += n
         self.stats["gpu_rejected"] += int(bv.rejected.sum())
         self.stats["not_compilable"] += n_uncompiled
