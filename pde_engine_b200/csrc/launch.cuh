@@ -86,9 +86,17 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
     const long long resident = (long long)sms * occ;    // persistent grid: a multiple of the SM count
     int grid = (int)(rounds < resident ? rounds : resident);
     if (grid < 1) grid = 1;
-    kern<<<grid, W * 32, smem, st>>>(vp);
+    // the dynamic chunk counter: 8 bytes from the library's stream-ordered pool, zeroed and released on the stream
+    ValidateParams v = vp;
+    unsigned long long* ctr = nullptr;
+    if (int rc = scratch_alloc(reinterpret_cast<void**>(&ctr), sizeof(unsigned long long), st)) return rc;
+    PDE_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+    v.chunk_counter = ctr;
+    kern<<<grid, W * 32, smem, st>>>(v);
     count_launch();
-    PDE_CUDA(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    scratch_free(ctr, st);
+    if (le != cudaSuccess) return cuda_fail((int)le, "validate_kernel launch");
     return PDE_OK;
 }
 

@@ -103,6 +103,7 @@ struct ValidateParams {
     const int* index;
     const unsigned long long* n_index;
     int* confirm;         // [n, 2] (n_finite, n_votes) of the confirmation pass, or null
+    unsigned long long* chunk_counter;   // zeroed by the launcher: chunks are dealt dynamically (null: round-robin)
     int ns;               // spill slots per lane
     float t0;             // expansion radius of the round-off majorants
     double tau;
@@ -1087,7 +1088,18 @@ validate_kernel(const ValidateParams p) {
     const bool indexed = MAJ && p.index != nullptr;
     const long long n_items = indexed ? (long long)*p.n_index : p.n;
     const long long n_chunks = (n_items + 3) / 4;
-    for (long long chunk = (long long)blockIdx.x * G + grp; chunk < n_chunks; chunk += (long long)gridDim.x * G) {
+    // Chunks are dealt DYNAMICALLY (one atomicAdd per chunk by the group's first lane): candidates differ in cost by an
+    // order of magnitude (2 to 60 micro-ops), and with a static round-robin the last groups of a small batch -- one
+    // rank's shard of the depth-4 uniques is 6 chunks per group -- ran long after the others had finished.  Which
+    // group evaluates a candidate never changes its outputs.
+    int* s_next = reinterpret_cast<int*>(s_status) + 4 * (G - grp) + grp;          // [G] ints behind the status words
+    for (long long chunk = (long long)blockIdx.x * G + grp;; chunk += (long long)gridDim.x * G) {
+        if (p.chunk_counter) {
+            if (wg == 0 && lane == 0) *s_next = (int)atomicAdd(p.chunk_counter, 1ULL);
+            group_barrier(grp);
+            chunk = *s_next;
+        }
+        if (chunk >= n_chunks) break;
         const long long cand0 = chunk * 4;
         // ---- phase 1: every warp of the group stages + translates its own candidate ----
         {

@@ -31,3 +31,15 @@ for r in range(reps):
     print(f"spill_slots {ss} rep {r}: {a.elapsed_time(b):.2f} ms", flush=True)
 nf = out["n_finite"].cpu().numpy()
 print("overflowed (needs more spill slots):", int((nf == -3).sum()), "not evaluable:", int((nf < 0).sum()))
+# one rank's shard at N = 8 (the first 1/8 of the strings): how close to 1/8 of the full time?  (kernel tail)
+n8 = (len(strs) // 8) // 32 * 32
+o8 = None
+best = 1e9
+for r in range(reps + 2):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    o8 = pb.validate(sess, prog, c[:n8], l[:n8], pts_t, tab_t, None, spill_slots=ss, out=o8)
+    b.record()
+    torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+print(f"shard 1/8 ({n8} candidates): {best:.2f} ms", flush=True)
