@@ -105,6 +105,8 @@ def main():
     todo = [s for s in exprs if s not in done]
     print(len(done), "already done,", len(todo), "to do,", workers, "workers", flush=True)
     t0 = time.time()
+    if budget <= 0:
+        todo = []                 # wall budget 0: only fold the records of the work log into the fixture
     with mp.Pool(workers, initializer=_init, initargs=(problem, cap), maxtasksperchild=20) as pool, open(log_path, "a") as log:
         k = 0
         for r in pool.imap_unordered(_one, todo, chunksize=1):
@@ -118,6 +120,13 @@ def main():
                 print("wall budget spent after", k, "records", flush=True)
                 pool.terminate()
                 break
+    # the reference's validator catches the alarm inside validate() (FFV:434-437: `except Exception as e: "Error: {e}"`),
+    # so a candidate that hit the wall cap comes back as (False, "Error: ") after `cap` seconds: record it as a timeout
+    for r in done.values():
+        if r.get("reason", "").strip() == "Error:" and r.get("t", 0) >= cap - 1:
+            r.pop("is_valid", None)
+            r.pop("reason", None)
+            r["timeout"] = True
     recs = [done[s] for s in uniques if s in done]
     strides = sorted(set([step] + [int(x) for x in str(old.get("step", "")).split("+") if x.isdigit()])) if os.path.exists(path) else [step]
     out = {"problem": problem, "depth": depth, "step": "+".join(str(x) for x in strides), "cap_seconds": cap,

@@ -319,6 +319,55 @@ def test_filter_keeps_every_reference_valid_row(cuda_device):
     assert np.median(bv.ratio_max[ok]) < 1e-12
 
 
+def test_ill_conditioned_true_solutions(cuda_device):
+    """exact solutions written so that float64 loses most of its digits INSIDE u's own jet -- cancelling
+    sub-expressions, large offsets, exponent shifts -- on the product grid and on a grid skewed to rho/z ~ 1e-3.
+    Their residual is noise of the size of the plain scale S (the round-1 rule rejects several of them); the majorant
+    rule must let every one of them survive, in both filter modes."""
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.grids import collocation_grid
+    sols = ["rho**2*z", "rho**2*exp(-2*z)", "sqrt(rho**2 + z**2) - z", "rho**2/(rho**2 + z**2)**(3/2)", "1 - z/sqrt(rho**2 + z**2)", "1/rho"]
+    disguised = []
+    for u in sols:
+        disguised += [f"({u} + exp(z)) - exp(z)", f"({u} + 1000000) - 1000000", f"({u})*(rho + 1000)/(rho + 1000)",
+                      f"({u} + rho/z) - rho/z", f"(({u}) + 1/(rho - 1)) - 1/(rho - 1)"]
+    disguised += ["z*inv(z)/rho", "rho**2*exp(-2*z + 30)/exp(30)", "(rho + z) - rho", "exp(z + rho)/exp(rho)*0 + rho**2*z",
+                  "sqrt((rho**2 + z**2)**2)/sqrt(rho**2 + z**2) - z"]
+    sess = pb.Session.for_problem("force_free")
+    prog = pb.ResidualProgram.for_problem("force_free")
+    es = sess.compile(disguised)
+    assert not es.flags().any()
+    c, ln = es.programs(128)
+    code_t, len_t = torch.from_numpy(c).to(cuda_device), torch.from_numpy(ln).to(cuda_device)
+    P = 1024
+    grids = {"product": collocation_grid("force_free", P)}
+    skew = collocation_grid("force_free", P).copy()
+    skew[0] = 1e-3 * (1.0 + skew[0])                      # rho in [1.25e-3, 3e-3], z in [0.25, 2]
+    grids["skewed rho/z ~ 1e-3"] = skew
+    n_plain_rejects = 0
+    for name, pts in grids.items():
+        pts_t = torch.from_numpy(pts).to(cuda_device)
+        tab_t = torch.from_numpy(prog.point_table(pts)).to(cuda_device)
+        for cp in (0, 128):                                # one pass with majorants / two passes
+            out = pb.validate(sess, prog, code_t, len_t, pts_t, tab_t, None, tau=TAU, min_finite=8, vote_frac=0.5,
+                              confirm_points=cp, n_ref=0, spill_slots=4)
+            bits = out["survivor_bits"].cpu().numpy().view(np.uint32)
+            surv = np.array([(bits[i >> 5] >> (i & 31)) & 1 for i in range(len(disguised))], bool)
+            assert surv.all(), (name, cp, [s for s, k in zip(disguised, surv) if not k])
+        # what the plain scale S (no round-off majorant) would have decided
+        _, R, S, St, _ = pb.eval_points(sess, prog, code_t, len_t, pts_t, tab_t, None, spill_slots=4, want_jets=False, want_maj=True, tau=TAU)
+        R, S, St = R.cpu().numpy(), S.cpu().numpy(), St.cpu().numpy()
+        with np.errstate(all="ignore"):
+            fin = np.isfinite(R) & np.isfinite(S) & (S > 0)
+            votes = (fin & (np.abs(R) > TAU * S)).sum(axis=1)
+            n_plain_rejects += int(((fin.sum(axis=1) >= 8) & (votes >= 0.5 * fin.sum(axis=1))).sum())
+            finm = np.isfinite(R) & np.isfinite(St) & (St > 0)
+            assert not (finm & (np.abs(R) > TAU * St)).any()          # no point of an exact solution votes
+    assert n_plain_rejects >= 3, n_plain_rejects           # the cases are hard: the rule without majorants flips some of them
+    print(f"ill-conditioned true solutions: {len(disguised)} x {len(grids)} grids survive; the plain-scale rule would reject {n_plain_rejects}")
+
+
 def test_kerr_primitives_rejected(cuda_device):
     """The committed Kerr run DB rejects all 9 primitives except constants with
     'PDE residual != 0 (fast point check)' (KV:265-271); so does the device."""
