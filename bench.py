@@ -150,6 +150,10 @@ def cpu_baseline_reference(wall_s):
         if not rb.available():
             return {"unavailable": "baseline/_ref (the reference's code, made by tools/refcopy.py) is not in this snapshot"}
         r = rb.run_reference_validators("force_free", 3, os.cpu_count() or 1, wall_s)
+        if r["rows_validated"] == 0:          # the pool did not come up inside the window (seen once on a busy host): one more try
+            first_try = {k: r[k] for k in ("validator_processes_started", "rows_inserted", "wall_s", "log_tail")}
+            r = rb.run_reference_validators("force_free", 3, os.cpu_count() or 1, wall_s)
+            r["first_try"] = first_try
         r["sample"] = (f"{r['rows_validated']} rows of the reference's own depth <= 3 force-free run validated by its "
                        f"{r['validators']} validator processes in {r['wall_s']} s (1 test point per row, FFV:296-297)")
         return r

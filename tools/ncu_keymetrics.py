@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Compact key,value CSV of the metrics the roofline discussion uses, from an .ncu-rep
-(ncu --set full).  usage: tools/ncu_keymetrics.py REPORT.ncu-rep > profiles/NAME_metrics.csv"""
+(ncu --set full).  usage: tools/ncu_keymetrics.py REPORT.ncu-rep [KERNEL_INDEX] > profiles/NAME_metrics.csv
+(KERNEL_INDEX: which captured launch, default the last)"""
 import csv, io, subprocess, sys
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[-1]
+hdr, units, vals = rows[0], rows[1], rows[2 + int(sys.argv[2])] if len(sys.argv) > 2 else rows[-1]
 KEYS = ("Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum",

@@ -82,14 +82,16 @@ def run_reference_validators(problem: str = "force_free", max_depth: int = 3, va
                 pass
             proc.wait()
         log.close()
-        started = open(os.path.join(tmp, "run.log")).read().count("Validator process started")
+        text = open(os.path.join(tmp, "run.log")).read()
+        started = text.count("Validator process started")
+        log_tail = text[-1500:] if stats["completed"] == 0 else ""
     pts = POINTS_PER_ROW[problem]
     rps = stats["completed"] / wall if wall > 0 else 0.0
     return dict(kind="reference", command=f"python {GM} --problem {problem} --max-depth {max_depth} --validators {validators}",
                 validators=validators, validator_processes_started=started, cores=os.cpu_count(), wall_s=round(wall, 2),
                 run_finished=finished, rows_inserted=stats["rows"], rows_validated=stats["completed"], rows_valid=stats["valid"],
                 by_depth=stats["by_depth"], rows_per_s=rps, points_per_row=pts, value=rps * pts, unit="evals/s",
-                patch=diff, note="bounded window: the process group is killed after wall_s; rows the pool completed are read from the run database")
+                patch=diff, log_tail=log_tail, note="bounded window: the process group is killed after wall_s; rows the pool completed are read from the run database")
 
 
 if __name__ == "__main__":
