@@ -190,15 +190,18 @@ struct Parser {
             return e;
         }
         if (c >= '0' && c <= '9') {
-            __int128 v = 0;
-            size_t st = pos;
+            // up to 18 digits in 64-bit arithmetic (every literal of the real candidate sets), beyond that 128-bit
+            unsigned long long v64 = 0;
+            int nd = 0;
+            while (pos < n && s[pos] >= '0' && s[pos] <= '9' && nd < 18) { v64 = v64 * 10 + (unsigned)(s[pos] - '0'); ++pos; ++nd; }
+            __int128 v = (__int128)v64;
             while (pos < n && s[pos] >= '0' && s[pos] <= '9') {
                 v = v * 10 + (s[pos] - '0');
                 if (v > ((__int128)1 << 100)) throw Unsupported();
                 ++pos;
             }
             if (pos < n && (s[pos] == '.' || s[pos] == 'e' || s[pos] == 'E' || s[pos] == '_' || s[pos] == 'j')) throw Unsupported();
-            (void)st;
+            if (nd < 16) { Rat r; r.n = (i64)v64; r.d = 1; return constant(r); }       // < 2^53: no reduction needed
             return constant(make_rat(v, 1));
         }
         if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') {
@@ -329,6 +332,14 @@ struct Emitter {
     }
 
     void emit(Node* ir) {
+        if (!(ir->kind == K_BIN && (ir->op == '+' || ir->op == '-'))) {
+            // one term (by far the common case: every operand of * / ** and of a call comes through here)
+            int sign = 1;
+            Node* body = (ir->kind == K_NEG || ir->kind == K_BIN) ? extract_sign(ir, sign) : ir;
+            emit_term(body);
+            if (sign < 0) out.push_back(PDE_OP_NEG);
+            return;
+        }
         Terms terms;
         split_terms(ir, terms);
         for (size_t k = 0; k < terms.size(); ++k) {
