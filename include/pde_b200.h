@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 4
+#define PDE_B200_ABI_VERSION 5
 
 /* ---- error codes ------------------------------------------------------- */
 #define PDE_OK            0
@@ -162,6 +162,22 @@ int  pde_enumerate(const pde_exprset *e, const int32_t *depth_begin, int depth, 
 int  pde_dedup(const uint8_t *code_dev, const uint8_t *len_dev, const uint64_t *hash_dev,
                int64_t n, int L, uint8_t *first_occurrence_dev, int64_t *n_unique, void *stream);
 
+/* CSR form of the same output: the programs back to back in ONE byte pool, each padded to 16 bytes (an empty
+ * program takes none), instead of [count][L] rows -- the mean program of the real candidate sets is 15 bytes, so
+ * a depth-5 pass writes ~49 B per candidate instead of 149 (L = 128).  offset[c] (16-byte units, relative to the
+ * start of the pool) is the start of candidate first + c, offset[count] the end.  L only bounds a program's length
+ * (longer ones are emitted empty, as above).  pde_enumerate_csr_size returns the pool bytes the window needs (the
+ * rows of the blocks it touches); triple / len / hash as in pde_enumerate.  pde_dedup_csr / pde_validate_csr read
+ * the same layout. */
+int  pde_enumerate_csr_size(const pde_exprset *e, const int32_t *depth_begin, int depth, int prune,
+                            int64_t first, int64_t count, int L, int64_t *pool_bytes, void *stream);
+int  pde_enumerate_csr(const pde_exprset *e, const int32_t *depth_begin, int depth, int prune,
+                       int64_t first, int64_t count, int L,
+                       int32_t *triple_dev, uint32_t *offset_dev /*[count + 1]*/, uint8_t *pool_dev,
+                       uint8_t *len_dev, uint64_t *hash_dev, void *stream);
+int  pde_dedup_csr(const uint8_t *pool_dev, const uint32_t *offset_dev, const uint8_t *len_dev, const uint64_t *hash_dev,
+                   int64_t n, uint8_t *first_occurrence_dev, int64_t *n_unique, void *stream);
+
 /* synthetic depth-d trees of SURVEY 8d (tree semantics, splitmix64 seeded per tree) */
 int  pde_synth_trees(uint64_t seed, int64_t first, int64_t count, int depth, int L,
                      uint8_t *code_dev, uint8_t *len_dev, uint64_t *hash_dev, void *stream);
@@ -288,6 +304,14 @@ int  pde_validate(const pde_session *s, const pde_program *p,
                   const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
                   double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
                   const pde_validate_out *out, void *stream);
+
+/* the same filter on CSR rows (pde_enumerate_csr): program c = pool + 16 * row_off[c], len[c] bytes; L = the
+ * staging size per program (>= the longest program, a multiple of 4) */
+int  pde_validate_csr(const pde_session *s, const pde_program *p,
+                      const uint8_t *pool_dev, const uint32_t *row_off_dev, const uint8_t *len_dev, int64_t n, int L,
+                      const double *pts_dev, const double *table_dev, const double *prim_dev, int n_prim, int P,
+                      double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
+                      const pde_validate_out *out, void *stream);
 
 /* parity / tooling entry: full per-point output for SMALL batches (each may be NULL).
  *   jets[n, n_coef, P]   normalised Taylor coefficients of u

@@ -67,6 +67,10 @@ _sig("pde_enumerate_count", c_int, c_void_p, P(C.c_int32), c_int, c_int, P(c_int
 _sig("pde_enumerate", c_int, c_void_p, P(C.c_int32), c_int, c_int, c_int64, c_int64, c_int,
      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_dedup", c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, P(c_int64), c_void_p)
+_sig("pde_enumerate_csr_size", c_int, c_void_p, P(C.c_int32), c_int, c_int, c_int64, c_int64, c_int, P(c_int64), c_void_p)
+_sig("pde_enumerate_csr", c_int, c_void_p, P(C.c_int32), c_int, c_int, c_int64, c_int64, c_int,
+     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("pde_dedup_csr", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, P(c_int64), c_void_p)
 _sig("pde_synth_trees", c_int, C.c_uint64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("pde_compile_residual", c_int, c_int, P(c_double), c_int, P(c_void_p))
 _sig("pde_compile_residual_program", c_int, c_int, c_int, P(c_double), c_int, P(C.c_uint32), c_int, P(c_void_p))
@@ -74,6 +78,8 @@ _sig("pde_program_free", None, c_void_p)
 _sig("pde_program_info", c_int, c_void_p, P(c_int), P(c_int), P(c_int))
 _sig("pde_program_point_table", c_int, c_void_p, c_void_p, c_int, c_void_p)
 _sig("pde_validate", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+     c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_double, c_int, c_int, c_int, P(ValidateOut), c_void_p)
+_sig("pde_validate_csr", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
      c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_double, c_double, c_int, c_int, c_int, P(ValidateOut), c_void_p)
 _sig("pde_eval_points", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
      c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
@@ -86,9 +92,9 @@ EXPORTED = [
     "pde_abi_version", "pde_last_error", "pde_device_count", "pde_launch_count",
     "pde_session_create", "pde_session_free", "pde_session_tables", "pde_session_const_key", "pde_session_pow_key",
     "pde_compile_exprs", "pde_compile_exprs_packed", "pde_exprset_free", "pde_exprset_size", "pde_exprset_export", "pde_exprset_programs",
-    "pde_enumerate_count", "pde_enumerate", "pde_dedup", "pde_synth_trees",
+    "pde_enumerate_count", "pde_enumerate", "pde_dedup", "pde_enumerate_csr_size", "pde_enumerate_csr", "pde_dedup_csr", "pde_synth_trees",
     "pde_compile_residual", "pde_compile_residual_program", "pde_program_free", "pde_program_info", "pde_program_point_table",
-    "pde_validate", "pde_eval_points", "pde_fingerprint", "pde_fp64_peak", "pde_fp64_peak_3op",
+    "pde_validate", "pde_validate_csr", "pde_eval_points", "pde_fingerprint", "pde_fp64_peak", "pde_fp64_peak_3op",
 ]
 
 

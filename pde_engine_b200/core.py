@@ -235,13 +235,16 @@ class ResidualProgram:
 def validate(session: Session, program: ResidualProgram, code, length, pts, table, prim=None, *,
              tau: float = 1e-10, min_finite: int = 8, vote_frac: float = 0.5, t0: float = T0_DEFAULT,
              confirm_points: int = CONFIRM_POINTS_DEFAULT, n_ref: int = 3,
-             spill_slots: int = 4, stream=None, out: Optional[dict] = None) -> dict:
+             spill_slots: int = 4, stream=None, out: Optional[dict] = None, row_off=None, L: Optional[int] = None) -> dict:
     """Stage 2 (pde_validate).  code [n, L] uint8, length [n] uint8, pts [2, P] f64,
     table [cols, P] f64, prim [n_prim, P/32, 16, 32] f64 (synthetic.pack_primitive_table) or None -- all CUDA tensors.
     confirm_points > 0: two passes (proposals on all P points, confirmation with round-off majorants on the first
     confirm_points points); 0: one pass with the majorants on all points (include/pde_b200.h)."""
     import torch
-    n, L = code.shape
+    if row_off is None:
+        n, L = code.shape
+    else:
+        n, L = int(length.shape[0]), int(L or 256)
     Pn = pts.shape[1]
     dev = code.device
     if out is None:
@@ -260,10 +263,16 @@ def validate(session: Session, program: ResidualProgram, code, length, pts, tabl
         out["scratch"] = torch.empty(n + 2, dtype=torch.int32, device=dev)
     vo = _lib.ValidateOut(*[_dev_ptr(out.get(k)) for k in
                             ("ratio_max", "resid_max", "scale_at", "n_finite", "n_votes", "ref_rs", "survivor_bits", "confirm", "scratch")])
-    check(lib.pde_validate(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
-                           _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
-                           float(tau), int(min_finite), float(vote_frac), float(t0), int(confirm_points), int(n_ref), int(spill_slots),
-                           C.byref(vo), _stream_ptr(stream)))
+    if row_off is None:
+        check(lib.pde_validate(session._h, program._h, _dev_ptr(code), _dev_ptr(length), n, L,
+                               _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
+                               float(tau), int(min_finite), float(vote_frac), float(t0), int(confirm_points), int(n_ref), int(spill_slots),
+                               C.byref(vo), _stream_ptr(stream)))
+    else:       # CSR rows: `code` is the byte pool, row_off [n (+1)] uint32 in 16-byte units (enumerate_candidates(csr=True))
+        check(lib.pde_validate_csr(session._h, program._h, _dev_ptr(code), _dev_ptr(row_off), _dev_ptr(length), n, L,
+                                   _dev_ptr(pts), _dev_ptr(table), _dev_ptr(prim), (0 if prim is None else int(prim.shape[0])), Pn,
+                                   float(tau), int(min_finite), float(vote_frac), float(t0), int(confirm_points), int(n_ref), int(spill_slots),
+                                   C.byref(vo), _stream_ptr(stream)))
     return out
 
 
@@ -333,6 +342,53 @@ def enumerate_candidates(exprs: ExprSet, depth_begin: Sequence[int], depth: int,
                             _dev_ptr(out["triple"]), _dev_ptr(out["code"]), _dev_ptr(out["len"]), _dev_ptr(out["hash"]),
                             _stream_ptr(stream)))
     return out
+
+
+def enumerate_candidates_csr(exprs: ExprSet, depth_begin: Sequence[int], depth: int, prune: bool = True,
+                             first: int = 0, count: Optional[int] = None, L: int = 256, device=None, stream=None) -> dict:
+    """Stage 1 in CSR form (pde_enumerate_csr): the programs back to back in one byte pool, 16-byte aligned.
+    Returns triple [count, 3], off [count + 1] uint32 (16-byte units into `pool`), pool uint8, len, hash."""
+    import torch
+    if count is None:
+        count = enumerate_count(exprs, depth_begin, depth, prune, stream) - first
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    db = (C.c_int32 * len(depth_begin))(*[int(x) for x in depth_begin])
+    nbytes = C.c_int64()
+    check(lib.pde_enumerate_csr_size(exprs._h, db, depth, int(prune), first, count, L, C.byref(nbytes), _stream_ptr(stream)))
+    out = {
+        "triple": torch.empty((count, 3), dtype=torch.int32, device=dev),
+        "off": torch.zeros(count + 1, dtype=torch.int32, device=dev),
+        "pool": torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=dev),
+        "len": torch.empty(count, dtype=torch.uint8, device=dev),
+        "hash": torch.empty(count, dtype=torch.int64, device=dev),
+        "L": L,
+    }
+    check(lib.pde_enumerate_csr(exprs._h, db, depth, int(prune), first, count, L,
+                                _dev_ptr(out["triple"]), _dev_ptr(out["off"]), _dev_ptr(out["pool"]), _dev_ptr(out["len"]),
+                                _dev_ptr(out["hash"]), _stream_ptr(stream)))
+    return out
+
+
+def csr_rows(cand: dict, L: Optional[int] = None):
+    """Host copy of CSR candidates as zero-padded rows [n, L] (tests / tooling)."""
+    off = cand["off"].cpu().numpy().view(np.uint32).astype(np.int64) * 16
+    ln = cand["len"].cpu().numpy()
+    pool = cand["pool"].cpu().numpy()
+    L = L or cand["L"]
+    rows = np.zeros((len(ln), L), np.uint8)
+    for i in range(len(ln)):
+        rows[i, :ln[i]] = pool[off[i]:off[i] + ln[i]]
+    return rows, ln
+
+
+def dedup_csr(pool, off, length, hashes, stream=None):
+    """First-occurrence flags of exact duplicate programs on CSR rows (pde_dedup_csr)."""
+    import torch
+    n = int(length.shape[0])
+    first = torch.empty(n, dtype=torch.uint8, device=length.device)
+    nu = C.c_int64()
+    check(lib.pde_dedup_csr(_dev_ptr(pool), _dev_ptr(off), _dev_ptr(length), _dev_ptr(hashes), n, _dev_ptr(first), C.byref(nu), _stream_ptr(stream)))
+    return first, int(nu.value)
 
 
 def dedup(code, length, hashes, stream=None):

@@ -74,6 +74,13 @@ struct pde_exprset {
     unsigned* d_count_in_tile = nullptr;          // exclusive prefix inside a 1024-block tile
     unsigned long long* d_count_tile = nullptr;   // exclusive prefix of the tile totals
     std::vector<unsigned long long> count_tile_host;   // the same on the host: a window launches only its tiles
+    // CSR form (pde_enumerate_csr): bytes per block for row length L = count_bytes_L, scanned the same way, and the
+    // per-block exclusive prefixes of candidates and bytes on the host (a window's pool range needs no device read)
+    int count_bytes_L = 0;
+    unsigned* d_bytes_sums = nullptr;
+    unsigned* d_bytes_in_tile = nullptr;
+    unsigned long long* d_bytes_tile = nullptr;
+    std::vector<unsigned long long> block_cand_host, block_bytes_host;     // [nblocks + 1]
     std::vector<uint32_t> desc;         // [n][2] splice descriptors (enumerate.cu)
     std::vector<uint8_t> wpool;         // whole programs, padded by 8 bytes
     uint32_t* d_desc = nullptr;

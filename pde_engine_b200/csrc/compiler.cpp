@@ -698,6 +698,7 @@ void pde_exprset_free(pde_exprset* e) {
         cudaFree(e->d_flags); cudaFree(e->d_attrs); cudaFree(e->d_rank); cudaFree(e->d_term_begin);
         cudaFree(e->d_term_sign); cudaFree(e->d_term_off); cudaFree(e->d_pool); cudaFree(e->d_desc); cudaFree(e->d_wpool);
         cudaFree(e->d_count_sums); cudaFree(e->d_count_in_tile); cudaFree(e->d_count_tile);
+        cudaFree(e->d_bytes_sums); cudaFree(e->d_bytes_in_tile); cudaFree(e->d_bytes_tile);
     }
     delete e;
 }

@@ -318,6 +318,46 @@ __device__ __forceinline__ void splice(RowWriter& w, const uint32_t* pool32, int
     if (bop == 2) w.copy(pool32, B.off + skip, (int)(B.len - skip));
 }
 
+// ---- CSR form of the output: programs back to back in one byte pool, each padded to 16 bytes (an empty program
+// takes none), offset[c] in 16-byte units.  Mean program 15.4 bytes: ~49 B per candidate instead of 149 at L = 128.
+__device__ __forceinline__ int csr_row_bytes(int n) { return (n + 15) & ~15; }
+
+// Length of what splice() writes, from the descriptors alone (the CSR count pass sizes the byte pool with it; the emit
+// pass checks it against the writer).
+__device__ __forceinline__ int splice_len(int op, const Desc& A, const Desc& B) {
+    if (op < 8) return (int)A.len + 1;
+    const int bop = op - 8;
+    const int skip = (int)B.skip(), rest = (int)B.len - skip, bneg = (B.fl & D_FIRST_NEG) ? 1 : 0;
+    if (bop <= 1) return (int)A.len + (int)B.first_len + 1 + rest;
+    const int head = (int)(A.last_off + A.last_len());
+    const int sign = (A.fl & D_MULTI) ? 1 : ((A.fl & D_FIRST_NEG) ? 1 : 0);
+    if (bop == 2) return head + (int)B.first_len + bneg + 1 + sign + rest;
+    if (bop == 3) return head + (int)B.len + 1 + sign;
+    return head + 1 + (int)B.first_len + bneg + 1 + rest + 1 + sign;
+}
+
+__device__ __forceinline__ int slot_program_len(const EnumParams& p, const Slot& sl, int L) {
+    if (!sl.keep) return 0;
+    const Desc A(__ldg(p.desc + sl.a));
+    const Desc B(sl.b >= 0 ? __ldg(p.desc + sl.b) : make_uint2(0u, 0u));
+    if ((A.fl | B.fl) & D_BAD) return 0;
+    const int n = splice_len(sl.op, A, B);
+    return (n > L || n > 255) ? 0 : n;
+}
+
+__global__ void __launch_bounds__(kEnumThreads) enum_count_bytes_kernel(const EnumParams p, int L, unsigned* block_bytes) {
+    __shared__ unsigned s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const Slot sl = decode_slot(p);
+    unsigned b = (unsigned)csr_row_bytes(slot_program_len(p, sl, L));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) b += __shfl_xor_sync(0xffffffffu, b, off);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_sum, b);
+    __syncthreads();
+    if (threadIdx.x == 0) block_bytes[blockIdx.x] = s_sum;
+}
+
 // Shared-memory rows are L + 16 bytes apart: with a stride of L = 128 bytes every lane's row starts in the
 // same bank and each word store of the row owners was a 32-way conflict (mio_throttle + short_scoreboard
 // were the top stalls, profiles/README.md); L + 16 keeps rows 16-byte aligned for the vector copy-out.
@@ -398,7 +438,127 @@ enum_emit_kernel(const EnumParams p, const unsigned* sums, const unsigned* in_ti
     }
 }
 
+// CSR emit: the same block / slot mapping, rows assembled in shared memory as above; the copy-out packs them.
+//   byte base of the block   = bytes_tile[blk / 1024] + bytes_in_tile[blk]     (scan of enum_count_bytes_kernel)
+//   offset of row r          = base + exclusive scan of the padded lengths inside the block
+// offset_out[c] is in 16-byte units relative to `pool_lo` (the byte base of the first block of the launch); the last
+// candidate of the window also writes offset_out[count] (the end), so a row's padded size is off[c + 1] - off[c].
+struct CsrParams {
+    const unsigned* sums; const unsigned* in_tile; const unsigned long long* tile_off;              // candidates
+    const unsigned* bytes_in_tile; const unsigned long long* bytes_tile;                            // bytes
+    long long first, count;
+    unsigned long long pool_lo;
+    int L;
+    int32_t* triple; uint8_t* pool; unsigned* offset; uint8_t* len_out; unsigned long long* hash_out;
+};
+
+__global__ void __launch_bounds__(kEnumThreads) enum_emit_csr_kernel(const EnumParams p, const CsrParams c) {
+    const long long blk = p.block0 + blockIdx.x;
+    const long long base = (long long)(c.tile_off[blk / kScanTile] + c.in_tile[blk]);
+    {
+        const long long n_blk = (long long)c.sums[blk];
+        if (n_blk == 0 || base + n_blk <= c.first || base >= c.first + c.count) return;
+    }
+    extern __shared__ __align__(16) uint8_t s_rows[];
+    __shared__ int s_flag[kEnumThreads];
+    __shared__ int s_warp[kEnumThreads / 32];
+    __shared__ int s_boff[kEnumThreads + 1];          // byte offset of row r inside the block (compacted order)
+    const int L = c.L, Ls = enum_row_stride(L);
+    unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(s_rows + (size_t)kEnumThreads * Ls);
+    int* s_triple = reinterpret_cast<int*>(s_hash + kEnumThreads);
+    uint8_t* s_len = reinterpret_cast<uint8_t*>(s_triple + 3 * kEnumThreads);
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_rows);
+        const int nz = kEnumThreads * Ls / 16;
+        for (int i = threadIdx.x; i < nz; i += kEnumThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    const Slot sl = decode_slot(p);
+    int total;
+    const int local = block_exclusive_scan(sl.keep ? 1 : 0, sl.local, s_flag, s_warp, total);
+    int n = 0;
+    if (sl.keep) {
+        uint8_t* row = s_rows + (size_t)local * Ls;
+        RowWriter w{reinterpret_cast<uint32_t*>(row), L / 4, 0ULL, 0, 0, 0};
+        const Desc A(__ldg(p.desc + sl.a));
+        const Desc B(sl.b >= 0 ? __ldg(p.desc + sl.b) : make_uint2(0u, 0u));
+        const bool bad = (A.fl | B.fl) & D_BAD;
+        if (!bad) splice(w, reinterpret_cast<const uint32_t*>(p.wpool), sl.op, A, B);
+        n = w.n;
+        w.finish();
+        if (bad || n > L || n > 255) {
+            n = 0;
+            for (int i = 0; i < L / 4 && i < w.nw; ++i) reinterpret_cast<uint32_t*>(row)[i] = 0u;
+        }
+        s_len[local] = (uint8_t)n;
+        s_triple[3 * local + 0] = sl.op; s_triple[3 * local + 1] = sl.a; s_triple[3 * local + 2] = sl.b;
+        s_hash[local] = hash_row(row, n);
+    }
+    // padded byte offsets in COMPACTED row order: scan over the slots in slot order (kept slots only contribute)
+    __syncthreads();
+    int dummy;
+    const int boff = block_exclusive_scan(sl.keep ? csr_row_bytes(n) : 0, sl.local, s_flag, s_warp, dummy);
+    if (sl.keep) s_boff[local] = boff;
+    if (threadIdx.x == 0) s_boff[total] = dummy;
+    __syncthreads();
+    const unsigned long long bbase = c.bytes_tile[blk / kScanTile] + c.bytes_in_tile[blk] - c.pool_lo;     // relative to the pool
+    const long long lo = max(base, c.first), hi = min(base + (long long)total, c.first + c.count);
+    const int r0 = (int)(lo - base), nr = (int)(hi - lo);
+    const long long o0 = lo - c.first;
+    // every kept row is copied by its owner: 16-byte vectors at consecutive pool addresses across consecutive rows
+    if (sl.keep && local >= r0 && local < r0 + nr) {
+        const uint4* src = reinterpret_cast<const uint4*>(s_rows + (size_t)local * Ls);
+        uint4* dst = reinterpret_cast<uint4*>(c.pool + bbase + (unsigned long long)s_boff[local]);
+        const int nv = (s_boff[local + 1] - s_boff[local]) >> 4;
+        for (int v = 0; v < nv; ++v) dst[v] = src[v];
+    }
+    {
+        unsigned long long* ho = c.hash_out + o0;
+        uint8_t* lo8 = c.len_out + o0;
+        unsigned* oo = c.offset + o0;
+        int* to = c.triple + o0 * 3;
+        for (int i = threadIdx.x; i < nr; i += kEnumThreads) {
+            ho[i] = s_hash[r0 + i]; lo8[i] = s_len[r0 + i];
+            oo[i] = (unsigned)((bbase + (unsigned long long)s_boff[r0 + i]) >> 4);
+        }
+        if (threadIdx.x == 0 && hi == c.first + c.count) oo[nr] = (unsigned)((bbase + (unsigned long long)s_boff[r0 + nr]) >> 4);
+        for (int i = threadIdx.x; i < 3 * nr; i += kEnumThreads) to[i] = s_triple[3 * r0 + i];
+    }
+}
+
 // ------------------------------------------------------------------ dedup
+// CSR rows: candidate i's program = pool + 16 * off[i], len[i] bytes (padding zero)
+__global__ void __launch_bounds__(256) dedup_lookup_csr_kernel(const uint8_t* pool, const unsigned* off, const uint8_t* len, const unsigned long long* hash,
+                                                               long long n, const unsigned long long* keys, const unsigned* vals,
+                                                               unsigned mask, uint8_t* first_occ, unsigned long long* n_unique) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int keep = 0;
+    if (i < n) {
+        keep = 1;
+        if (len[i] != 0) {
+            unsigned long long h = hash[i];
+            if (h == 0) h = 1;
+            unsigned slot = (unsigned)(h >> 20) & mask;
+            while (keys[slot] != h) slot = (slot + 1) & mask;
+            const long long f = vals[slot];
+            if (f != i) {
+                bool same = len[f] == len[i];
+                const uint4* x = reinterpret_cast<const uint4*>(pool + (size_t)off[i] * 16);
+                const uint4* y = reinterpret_cast<const uint4*>(pool + (size_t)off[f] * 16);
+                const int nv = ((int)len[i] + 15) >> 4;
+                for (int k = 0; same && k < nv; ++k) {
+                    const uint4 u = x[k], v = y[k];
+                    same = (u.x == v.x) && (u.y == v.y) && (u.z == v.z) && (u.w == v.w);
+                }
+                if (same) keep = 0;
+            }
+        }
+        first_occ[i] = (uint8_t)keep;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_unique, (unsigned long long)__popc(b));
+}
+
+
 __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint8_t* len, const unsigned long long* hash, long long n,
                                                            unsigned long long* keys, unsigned* vals, unsigned mask) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,6 +706,7 @@ static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long 
     if (count_cached(e, p)) { if (total_host) *total_host = e->count_total; return PDE_OK; }
     cudaFree(e->d_count_sums); cudaFree(e->d_count_in_tile); cudaFree(e->d_count_tile);
     e->d_count_sums = nullptr; e->d_count_in_tile = nullptr; e->d_count_tile = nullptr;
+    e->count_bytes_L = 0;                  // the CSR byte counts belong to the same (depth, prune, depth_begin)
     const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
     PDE_CUDA(cudaMalloc(&e->d_count_sums, sizeof(unsigned) * nblocks));
     PDE_CUDA(cudaMalloc(&e->d_count_in_tile, sizeof(unsigned) * nblocks));
@@ -568,6 +729,51 @@ static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long 
     for (int k = 0; k < p.depth; ++k) e->count_db[k] = p.depth_begin[k];
     if (total_host) *total_host = total;
     return PDE_OK;
+}
+
+// CSR: bytes per block (programs padded to 16 bytes) for row length L, their scan, and the host copies of the
+// per-block prefixes.  Cached on the handle next to the candidate counts.
+static int run_count_bytes(pde_exprset* e, const EnumParams& p, int L, cudaStream_t st) {
+    const long long nblocks = p.seg_block[p.depth];
+    if (nblocks == 0 || (e->count_bytes_L == L && e->d_bytes_sums)) return PDE_OK;
+    cudaFree(e->d_bytes_sums); cudaFree(e->d_bytes_in_tile); cudaFree(e->d_bytes_tile);
+    e->d_bytes_sums = nullptr; e->d_bytes_in_tile = nullptr; e->d_bytes_tile = nullptr;
+    const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
+    PDE_CUDA(cudaMalloc(&e->d_bytes_sums, sizeof(unsigned) * nblocks));
+    PDE_CUDA(cudaMalloc(&e->d_bytes_in_tile, sizeof(unsigned) * nblocks));
+    PDE_CUDA(cudaMalloc(&e->d_bytes_tile, sizeof(unsigned long long) * (ntiles + 1)));
+    long long* d_total = nullptr;
+    int rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
+    if (rc) return rc;
+    enum_count_bytes_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, L, e->d_bytes_sums);
+    scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(e->d_bytes_sums, e->d_bytes_in_tile, e->d_bytes_tile, (int)nblocks);
+    scan_super_kernel<<<1, 1024, 0, st>>>(e->d_bytes_tile, ntiles, d_total);
+    count_launch(3);
+    PDE_CUDA(cudaGetLastError());
+    // host prefixes per block: candidates and bytes
+    std::vector<unsigned> cs(nblocks), bs(nblocks);
+    PDE_CUDA(cudaMemcpyAsync(cs.data(), e->d_count_sums, sizeof(unsigned) * nblocks, cudaMemcpyDeviceToHost, st));
+    PDE_CUDA(cudaMemcpyAsync(bs.data(), e->d_bytes_sums, sizeof(unsigned) * nblocks, cudaMemcpyDeviceToHost, st));
+    PDE_CUDA(cudaStreamSynchronize(st));
+    scratch_free(d_total, st);
+    e->block_cand_host.assign(nblocks + 1, 0ULL);
+    e->block_bytes_host.assign(nblocks + 1, 0ULL);
+    for (long long b = 0; b < nblocks; ++b) {
+        e->block_cand_host[b + 1] = e->block_cand_host[b] + cs[b];
+        e->block_bytes_host[b + 1] = e->block_bytes_host[b] + bs[b];
+    }
+    e->count_bytes_L = L;
+    return PDE_OK;
+}
+
+// blocks [b0, b1) that hold the candidates [first, first + count)
+static void window_blocks(const pde_exprset* e, long long first, long long count, long long& b0, long long& b1) {
+    const std::vector<unsigned long long>& cp = e->block_cand_host;
+    b0 = (long long)(std::upper_bound(cp.begin(), cp.end(), (unsigned long long)first) - cp.begin()) - 1;
+    b1 = (long long)(std::lower_bound(cp.begin(), cp.end(), (unsigned long long)(first + count)) - cp.begin());
+    if (b0 < 0) b0 = 0;
+    if (b1 > (long long)cp.size() - 1) b1 = (long long)cp.size() - 1;
+    if (b1 < b0) b1 = b0;
 }
 
 extern "C" {
@@ -617,6 +823,95 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
                                                                     reinterpret_cast<unsigned long long*>(hash));
     count_launch();
     PDE_CUDA(cudaGetLastError());
+    return PDE_OK;
+}
+
+static int csr_prepare(const pde_exprset* e, const int32_t* depth_begin, int depth, int prune, int64_t first, int64_t count, int L,
+                       cudaStream_t st, EnumParams& p, long long& b0, long long& b1) {
+    if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
+    if (first < 0 || count < 0) { set_error("pde_enumerate_csr: bad argument"); return PDE_E_INVALID; }
+    if (L < 16 || L > kMaxRow || (L % 16) != 0) { set_error("L must be a multiple of 16 in [16, %d]", kMaxRow); return PDE_E_INVALID; }
+    int rc = fill_params(e, depth_begin, depth, prune, p);
+    if (rc) return rc;
+    long long total = 0;
+    pde_exprset* em = const_cast<pde_exprset*>(e);
+    rc = run_count(em, p, st, &total);
+    if (rc) return rc;
+    if (first + count > total) { set_error("pde_enumerate_csr: window [%lld, %lld) exceeds the %lld candidates", (long long)first, (long long)(first + count), total); return PDE_E_INVALID; }
+    b0 = b1 = 0;
+    if (count == 0 || p.seg_block[p.depth] == 0) return PDE_OK;
+    rc = run_count_bytes(em, p, L, st);
+    if (rc) return rc;
+    window_blocks(e, first, count, b0, b1);
+    return PDE_OK;
+}
+
+int pde_enumerate_csr_size(const pde_exprset* e, const int32_t* depth_begin, int depth, int prune,
+                           int64_t first, int64_t count, int L, int64_t* pool_bytes, void* stream) {
+    if (!pool_bytes) { set_error("null pool_bytes"); return PDE_E_INVALID; }
+    EnumParams p;
+    long long b0, b1;
+    int rc = csr_prepare(e, depth_begin, depth, prune, first, count, L, (cudaStream_t)stream, p, b0, b1);
+    if (rc) return rc;
+    *pool_bytes = (count == 0 || p.seg_block[p.depth] == 0) ? 0 : (int64_t)(e->block_bytes_host[b1] - e->block_bytes_host[b0]);
+    if (*pool_bytes >= (int64_t)16 * 0xffffffffLL) { set_error("pde_enumerate_csr: the window's pool exceeds 64 GiB (32-bit offsets in 16-byte units): use smaller windows"); return PDE_E_OVERFLOW; }
+    return PDE_OK;
+}
+
+int pde_enumerate_csr(const pde_exprset* e, const int32_t* depth_begin, int depth, int prune,
+                      int64_t first, int64_t count, int L,
+                      int32_t* triple, uint32_t* offset, uint8_t* pool, uint8_t* len, uint64_t* hash, void* stream) {
+    EnumParams p;
+    long long b0, b1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = csr_prepare(e, depth_begin, depth, prune, first, count, L, st, p, b0, b1);
+    if (rc) return rc;
+    if (count == 0 || p.seg_block[p.depth] == 0) return PDE_OK;
+    if (!triple || !offset || !len || !hash || (!pool && e->block_bytes_host[b1] > e->block_bytes_host[b0])) { set_error("pde_enumerate_csr: null output"); return PDE_E_INVALID; }
+    const size_t smem = (size_t)kEnumThreads * (enum_row_stride(L) + 8 + 12 + 1) + 16;
+    PDE_CUDA(cudaFuncSetAttribute(enum_emit_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CsrParams c;
+    c.sums = e->d_count_sums; c.in_tile = e->d_count_in_tile; c.tile_off = e->d_count_tile;
+    c.bytes_in_tile = e->d_bytes_in_tile; c.bytes_tile = e->d_bytes_tile;
+    c.first = first; c.count = count; c.pool_lo = e->block_bytes_host[b0]; c.L = L;
+    c.triple = triple; c.pool = pool; c.offset = offset; c.len_out = len; c.hash_out = reinterpret_cast<unsigned long long*>(hash);
+    p.block0 = b0;
+    enum_emit_csr_kernel<<<(unsigned)(b1 - b0), kEnumThreads, smem, st>>>(p, c);
+    count_launch();
+    PDE_CUDA(cudaGetLastError());
+    return PDE_OK;
+}
+
+int pde_dedup_csr(const uint8_t* pool, const uint32_t* offset, const uint8_t* len, const uint64_t* hash, int64_t n,
+                  uint8_t* first_occurrence, int64_t* n_unique, void* stream) {
+    if (!have_device()) { set_error("no CUDA device: pde_engine_b200 has no CPU fallback"); return PDE_E_NODEVICE; }
+    if (n == 0) { if (n_unique) *n_unique = 0; return PDE_OK; }
+    if (!pool || !offset || !len || !hash || !first_occurrence || n < 0) { set_error("pde_dedup_csr: bad argument"); return PDE_E_INVALID; }
+    if (n > (1LL << 30)) { set_error("pde_dedup_csr: n too large (the 32-bit table index covers 2^30 candidates per call)"); return PDE_E_OVERFLOW; }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned cap = 1024;
+    while ((long long)cap < 2 * n) cap <<= 1;
+    unsigned long long* keys = nullptr;
+    unsigned* vals = nullptr;
+    unsigned long long* cnt = nullptr;
+    int rc = scratch_alloc(reinterpret_cast<void**>(&keys), sizeof(unsigned long long) * cap, st);
+    if (!rc) rc = scratch_alloc(reinterpret_cast<void**>(&vals), sizeof(unsigned) * cap, st);
+    if (!rc) rc = scratch_alloc(reinterpret_cast<void**>(&cnt), sizeof(unsigned long long), st);
+    if (rc) { scratch_free(keys, st); scratch_free(vals, st); scratch_free(cnt, st); return rc; }
+    PDE_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * cap, st));
+    PDE_CUDA(cudaMemsetAsync(vals, 0xff, sizeof(unsigned) * cap, st));
+    PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    dedup_insert_kernel<<<blocks, 256, 0, st>>>(len, reinterpret_cast<const unsigned long long*>(hash), n, keys, vals, cap - 1);
+    dedup_lookup_csr_kernel<<<blocks, 256, 0, st>>>(pool, offset, len, reinterpret_cast<const unsigned long long*>(hash), n, keys, vals,
+                                                    cap - 1, first_occurrence, cnt);
+    count_launch(2);
+    PDE_CUDA(cudaGetLastError());
+    unsigned long long c = 0;
+    PDE_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
+    PDE_CUDA(cudaStreamSynchronize(st));
+    scratch_free(keys, st); scratch_free(vals, st); scratch_free(cnt, st);
+    if (n_unique) *n_unique = (int64_t)c;
     return PDE_OK;
 }
 

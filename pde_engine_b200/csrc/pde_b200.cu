@@ -386,10 +386,32 @@ static int check_tau_t0(double tau, double t0) {
 
 extern "C" {
 
+static int validate_impl(const pde_session* s, const pde_program* p, const uint8_t* code, const uint32_t* row_off, const uint8_t* len,
+                         int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
+                         double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
+                         const pde_validate_out* out, void* stream);
+
 int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code, const uint8_t* len,
                  int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
                  double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
                  const pde_validate_out* out, void* stream) {
+    return validate_impl(s, p, code, nullptr, len, n, L, pts, tab, prim, n_prim, P, tau, min_finite, vote_frac, t0, confirm_points,
+                         n_ref, spill_slots, out, stream);
+}
+
+int pde_validate_csr(const pde_session* s, const pde_program* p, const uint8_t* pool, const uint32_t* row_off, const uint8_t* len,
+                     int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
+                     double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
+                     const pde_validate_out* out, void* stream) {
+    if (n > 0 && !row_off) { set_error("pde_validate_csr: null row offsets"); return PDE_E_INVALID; }
+    return validate_impl(s, p, pool, row_off, len, n, L, pts, tab, prim, n_prim, P, tau, min_finite, vote_frac, t0, confirm_points,
+                         n_ref, spill_slots, out, stream);
+}
+
+static int validate_impl(const pde_session* s, const pde_program* p, const uint8_t* code, const uint32_t* row_off, const uint8_t* len,
+                         int64_t n, int L, const double* pts, const double* tab, const double* prim, int n_prim, int P,
+                         double tau, int min_finite, double vote_frac, double t0, int confirm_points, int n_ref, int spill_slots,
+                         const pde_validate_out* out, void* stream) {
     int rc = check_common(s, p, code, len, n, L, pts, tab, P, spill_slots);
     if (rc) return rc;
     rc = check_tau_t0(tau, t0);
@@ -412,7 +434,7 @@ int pde_validate(const pde_session* s, const pde_program* p, const uint8_t* code
     }
     PDE_CUDA(cudaMemsetAsync(out->survivor_bits, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
     ValidateParams vp{};
-    vp.code = code; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
+    vp.code = code; vp.row_off = row_off; vp.len = len; vp.n = n; vp.L = L; vp.pts = pts; vp.tab = tab; vp.prim = prim; vp.n_prim = (prim && n_prim > 0) ? (n_prim < PDE_N_PRIM ? n_prim : PDE_N_PRIM) : 0; vp.P = P;
     vp.P_eval = P;
     vp.ns = spill_slots; vp.t0 = (float)t0; vp.tau = tau; vp.min_finite = min_finite; vp.vote_frac = vote_frac; vp.n_ref = out->ref_rs ? n_ref : 0;
     vp.ratio_max = out->ratio_max; vp.resid_max = out->resid_max; vp.scale_at = out->scale_at;

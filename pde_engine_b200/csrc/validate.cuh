@@ -90,6 +90,7 @@ enum UFn : unsigned { FN_INV = 0, FN_EXP = 1, FN_EXPN = 2, FN_POW = 3 };
 
 struct ValidateParams {
     const uint8_t* code;
+    const unsigned* row_off;   // CSR rows (pde_validate_csr): program c starts at code + 16 * row_off[c]; null: code + c * L
     const uint8_t* len;
     long long n;
     int L;
@@ -1109,7 +1110,7 @@ validate_kernel(const ValidateParams p) {
             if (item < n_items) {
                 int len = p.len[cand];
                 if (len > p.L) len = p.L + 1;          // a length beyond the row is malformed input (never read past the row)
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code + (size_t)cand * p.L);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.row_off ? p.code + (size_t)p.row_off[cand] * 16 : p.code + (size_t)cand * p.L);
                 uint32_t* dst = reinterpret_cast<uint32_t*>(s_code);
                 for (int i = lane; i * 4 < len && i * 4 < p.L; i += 32) dst[i] = __ldg(src + i);
                 __syncwarp();

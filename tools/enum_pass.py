@@ -46,3 +46,20 @@ for first, count, tag in ((0, n5, "full"), (3 * (n5 // 8), n5 // 8, "window 3/8.
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
     print(f"{tag}: {best:.3f} ms for {count} candidates (count pass cached on the handle)", flush=True)
+# CSR form: programs packed in one byte pool (16-byte aligned)
+csr = pb.enumerate_candidates_csr(es, db, 5, True, 0, n5, L)
+torch.cuda.synchronize()
+pool_bytes = csr["pool"].numel()
+best = 1e9
+for r in range(reps + 2):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _l.check(_l.lib.pde_enumerate_csr(es._h, dbc, 5, 1, 0, n5, L, C.c_void_p(csr["triple"].data_ptr()), C.c_void_p(csr["off"].data_ptr()),
+                                      C.c_void_p(csr["pool"].data_ptr()), C.c_void_p(csr["len"].data_ptr()),
+                                      C.c_void_p(csr["hash"].data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    b.record()
+    torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+real = pool_bytes + n5 * (4 + 1 + 8 + 12)
+print(f"CSR full: {best:.3f} ms; pool {pool_bytes / n5:.1f} B + 25 B per candidate = {real / n5:.1f} B; "
+      f"{real / best / 1e6:.0f} GB/s on real bytes, {n5 * 69 / best / 1e6:.0f} GB/s on SURVEY's 69 B", flush=True)
