@@ -459,57 +459,57 @@ __global__ void __launch_bounds__(kEnumThreads) enum_emit_csr_kernel(const EnumP
         const long long n_blk = (long long)c.sums[blk];
         if (n_blk == 0 || base + n_blk <= c.first || base >= c.first + c.count) return;
     }
-    extern __shared__ __align__(16) uint8_t s_rows[];
+    // The lengths are known from the descriptors BEFORE anything is spliced (splice_len), so ONE scan -- candidate
+    // count in the high bits, padded bytes in the low bits -- gives every kept slot its row index and its byte offset
+    // in the block's packed tile; the rows are spliced straight into place (no row stride, no zero fill, no second
+    // scan) and the tile leaves the block as one linear, coalesced copy.
+    extern __shared__ __align__(16) uint8_t s_tile[];          // [<= kEnumThreads * L] packed rows, then per-row hash / triple / len / offset
     __shared__ int s_flag[kEnumThreads];
     __shared__ int s_warp[kEnumThreads / 32];
-    __shared__ int s_boff[kEnumThreads + 1];          // byte offset of row r inside the block (compacted order)
-    const int L = c.L, Ls = enum_row_stride(L);
-    unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(s_rows + (size_t)kEnumThreads * Ls);
+    const int L = c.L;
+    unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(s_tile + (size_t)kEnumThreads * L);
     int* s_triple = reinterpret_cast<int*>(s_hash + kEnumThreads);
-    uint8_t* s_len = reinterpret_cast<uint8_t*>(s_triple + 3 * kEnumThreads);
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_rows);
-        const int nz = kEnumThreads * Ls / 16;
-        for (int i = threadIdx.x; i < nz; i += kEnumThreads) z[i] = make_uint4(0, 0, 0, 0);
-    }
+    int* s_boff = s_triple + 3 * kEnumThreads;                 // [kEnumThreads + 1]
+    uint8_t* s_len = reinterpret_cast<uint8_t*>(s_boff + kEnumThreads + 1);
     const Slot sl = decode_slot(p);
-    int total;
-    const int local = block_exclusive_scan(sl.keep ? 1 : 0, sl.local, s_flag, s_warp, total);
     int n = 0;
+    Desc A(make_uint2(0u, 0u)), B(make_uint2(0u, 0u));
     if (sl.keep) {
-        uint8_t* row = s_rows + (size_t)local * Ls;
-        RowWriter w{reinterpret_cast<uint32_t*>(row), L / 4, 0ULL, 0, 0, 0};
-        const Desc A(__ldg(p.desc + sl.a));
-        const Desc B(sl.b >= 0 ? __ldg(p.desc + sl.b) : make_uint2(0u, 0u));
-        const bool bad = (A.fl | B.fl) & D_BAD;
-        if (!bad) splice(w, reinterpret_cast<const uint32_t*>(p.wpool), sl.op, A, B);
-        n = w.n;
-        w.finish();
-        if (bad || n > L || n > 255) {
-            n = 0;
-            for (int i = 0; i < L / 4 && i < w.nw; ++i) reinterpret_cast<uint32_t*>(row)[i] = 0u;
+        A = Desc(__ldg(p.desc + sl.a));
+        if (sl.b >= 0) B = Desc(__ldg(p.desc + sl.b));
+        if (!((A.fl | B.fl) & D_BAD)) {
+            n = splice_len(sl.op, A, B);
+            if (n > L || n > 255) n = 0;                        // not compilable / too long: emitted empty
+        }
+    }
+    const int pb = csr_row_bytes(n);
+    int packed_total;
+    const int packed = block_exclusive_scan(sl.keep ? ((1 << 20) | pb) : 0, sl.local, s_flag, s_warp, packed_total);
+    const int local = packed >> 20, boff = packed & 0xfffff, total = packed_total >> 20;
+    if (sl.keep) {
+        uint8_t* row = s_tile + boff;
+        if (n > 0) {
+            RowWriter w{reinterpret_cast<uint32_t*>(row), pb / 4, 0ULL, 0, 0, 0};
+            splice(w, reinterpret_cast<const uint32_t*>(p.wpool), sl.op, A, B);
+            w.finish();
+            for (int i = (n + 3) >> 2; i < (pb >> 2); ++i) reinterpret_cast<uint32_t*>(row)[i] = 0u;       // pad to 16 bytes
         }
         s_len[local] = (uint8_t)n;
+        s_boff[local] = boff;
         s_triple[3 * local + 0] = sl.op; s_triple[3 * local + 1] = sl.a; s_triple[3 * local + 2] = sl.b;
         s_hash[local] = hash_row(row, n);
     }
-    // padded byte offsets in COMPACTED row order: scan over the slots in slot order (kept slots only contribute)
-    __syncthreads();
-    int dummy;
-    const int boff = block_exclusive_scan(sl.keep ? csr_row_bytes(n) : 0, sl.local, s_flag, s_warp, dummy);
-    if (sl.keep) s_boff[local] = boff;
-    if (threadIdx.x == 0) s_boff[total] = dummy;
+    if (threadIdx.x == 0) s_boff[total] = packed_total & 0xfffff;
     __syncthreads();
     const unsigned long long bbase = c.bytes_tile[blk / kScanTile] + c.bytes_in_tile[blk] - c.pool_lo;     // relative to the pool
     const long long lo = max(base, c.first), hi = min(base + (long long)total, c.first + c.count);
     const int r0 = (int)(lo - base), nr = (int)(hi - lo);
     const long long o0 = lo - c.first;
-    // every kept row is copied by its owner: 16-byte vectors at consecutive pool addresses across consecutive rows
-    if (sl.keep && local >= r0 && local < r0 + nr) {
-        const uint4* src = reinterpret_cast<const uint4*>(s_rows + (size_t)local * Ls);
-        uint4* dst = reinterpret_cast<uint4*>(c.pool + bbase + (unsigned long long)s_boff[local]);
-        const int nv = (s_boff[local + 1] - s_boff[local]) >> 4;
-        for (int v = 0; v < nv; ++v) dst[v] = src[v];
+    {   // the window's part of the packed tile: one linear copy
+        const int v0 = s_boff[r0] >> 4, v1 = s_boff[r0 + nr] >> 4;
+        const uint4* src = reinterpret_cast<const uint4*>(s_tile);
+        uint4* dst = reinterpret_cast<uint4*>(c.pool + bbase);
+        for (int v = v0 + (int)threadIdx.x; v < v1; v += kEnumThreads) dst[v] = src[v];
     }
     {
         unsigned long long* ho = c.hash_out + o0;
@@ -868,7 +868,7 @@ int pde_enumerate_csr(const pde_exprset* e, const int32_t* depth_begin, int dept
     if (rc) return rc;
     if (count == 0 || p.seg_block[p.depth] == 0) return PDE_OK;
     if (!triple || !offset || !len || !hash || (!pool && e->block_bytes_host[b1] > e->block_bytes_host[b0])) { set_error("pde_enumerate_csr: null output"); return PDE_E_INVALID; }
-    const size_t smem = (size_t)kEnumThreads * (enum_row_stride(L) + 8 + 12 + 1) + 16;
+    const size_t smem = (size_t)kEnumThreads * (L + 8 + 12 + 4 + 1) + 32;      // packed tile + hash / triple / offset / len per row
     PDE_CUDA(cudaFuncSetAttribute(enum_emit_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CsrParams c;
     c.sums = e->d_count_sums; c.in_tile = e->d_count_in_tile; c.tile_off = e->d_count_tile;

@@ -95,8 +95,9 @@ class GpuExpressionGenerator:
             depth_begin.append(len(all_strs))
         exprs = self.session.compile(all_strs)
         n = core.enumerate_count(exprs, depth_begin, depth, prune)
-        dev = core.enumerate_candidates(exprs, depth_begin, depth, prune, 0, n, self.L)
-        first, n_unique = core.dedup(dev["code"], dev["len"], dev["hash"])
+        # CSR rows: the programs packed in one byte pool (a third of the padded rows; include/pde_b200.h)
+        dev = core.enumerate_candidates_csr(exprs, depth_begin, depth, prune, 0, n, self.L)
+        first, n_unique = core.dedup_csr(dev["pool"], dev["off"], dev["len"], dev["hash"])
         out = {
             "n": n, "n_unique_programs": n_unique, "strings": all_strs,
             "triple": dev["triple"].cpu().numpy(), "first": first.cpu().numpy().astype(bool),
@@ -126,9 +127,9 @@ class GpuExpressionGenerator:
                 # stage 1 -> stage 2 on the device: the spliced programs are validated where they were written
                 dev = enum.pop("device")
                 enum.pop("device_first", None)
-                out = core.validate(self.session, filt.program, dev["code"], dev["len"], filt.pts, filt.table, None,
+                out = core.validate(self.session, filt.program, dev["pool"], dev["len"], filt.pts, filt.table, None,
                                     tau=filt.tau, min_finite=filt.min_finite, vote_frac=filt.vote_frac, t0=filt.t0, confirm_points=filt.confirm_points, n_ref=0,
-                                    spill_slots=filt.spill_slots)
+                                    spill_slots=filt.spill_slots, row_off=dev["off"], L=self.L)
                 bits = out["survivor_bits"].cpu().numpy().view(np.uint32)
                 k = np.arange(n)
                 surv = ((bits[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool)
