@@ -181,7 +181,7 @@ def test_opt_in_device_filter_before_the_normaliser(cuda_device, enum_ff):
     assert st["normalized"] + st["rejected_on_device_before_normalisation"] + st["exact_duplicates_dropped_on_device"] == st["candidates"]
     # every depth-3 expression the unmodified reference validated as a solution is still emitted
     ver = load_golden("verdicts_force_free_d3.json")["records"]
-    valid3 = [r["s"] for r in ver if r["is_valid"] and r["s"] in pos]
+    valid3 = [r["s"] for r in ver if r.get("is_valid") and r["s"] in pos]
     assert len(valid3) > 20
     missing = [s for s in valid3 if s not in set(got[3])]
     assert not missing, missing
