@@ -4,6 +4,7 @@
 // built-in specialisations and own their copy of the __constant__ tables.
 #include <cuda_runtime.h>
 #include <string.h>
+#include <vector>
 
 #include "common.h"
 #include "validate.cuh"
@@ -34,8 +35,8 @@ struct ProgramLauncher {
 
 // the program's words / constants / dimensions -> this unit's constant bank; the file must fit the spill column
 static int upload_program(const pde_program* p, ValidateParams& vp, cudaStream_t st) {
-    static uint32_t words[kResMaxWords];
-    memset(words, 0, sizeof(words));                        // PDE_R_END padding
+    std::vector<uint32_t> wbuf(kResMaxWords, 0u);            // PDE_R_END padding (per call: no shared host state)
+    uint32_t* words = wbuf.data();
     memcpy(words, p->words.data(), sizeof(uint32_t) * p->words.size());
     double consts[kResMaxConsts] = {0};
     for (size_t i = 0; i < p->prog_consts.size(); ++i) consts[i] = p->prog_consts[i];
@@ -43,6 +44,7 @@ static int upload_program(const pde_program* p, ValidateParams& vp, cudaStream_t
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_res_words, words, sizeof(uint32_t) * (p->words.size() + 1 < (size_t)kResMaxWords ? p->words.size() + 1 : (size_t)kResMaxWords), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_res_consts, consts, sizeof(consts), 0, cudaMemcpyHostToDevice, st));
     PDE_CUDA(cudaMemcpyToSymbolAsync(c_res_dims, dims, sizeof(dims), 0, cudaMemcpyHostToDevice, st));
+    // (pageable host sources: cudaMemcpy*Async returns once they are staged, like the table uploads of launch.cuh)
     // the spill column doubles as the residual's file: ns slots of (n_coef + 2) entries per lane
     const int per_slot = p->n_coef + 2;
     const int need = (p->n_file + per_slot - 1) / per_slot;
