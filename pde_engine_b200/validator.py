@@ -95,10 +95,11 @@ def _cut_blob(blob: bytes, n: int, bounds: Sequence[int]):
     return cuts
 
 
-# Shares of a large batch per pipeline part (part k + 1 is compiled while the device validates part k).  Measured on the
-# 143 461 depth-4 uniques: three parts 41.6 ms, five uneven parts (small first and last) 43.2 ms -- the host work
-# (compile 25 ms) exceeds the kernel (23.5 ms), so more parts only add fixed per-part cost.
-PART_SHARES = (0.30, 0.36, 0.34)
+# Shares of a large batch per pipeline part (part k + 1 is compiled while the device validates part k).  The host work
+# per part exceeds the kernel's (143 461 depth-4 uniques: compile 19-25 ms in total, kernel 21.8), so the wall is
+# roughly the sum of the compiles + the last part's kernel: few parts (each has a fixed cost; five parts measured
+# 43.2 ms against 41.6 for three; a small last part, 44/44/12 %, 40.7-45.0 ms against 38.4-47.5 for thirds: no gain).
+PART_SHARES = (0.34, 0.34, 0.32)
 
 
 class GpuBatchValidator:
@@ -329,9 +330,22 @@ class GpuBatchValidator:
             cuts = _cut_blob(blob, n, bounds)              # [(byte_lo, byte_hi, lo, hi)]
         else:
             cuts = [(None, None, lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:])]
-        for b0, b1, lo, hi in cuts:
+        # Python str -> bytes of part k + 1 (join + encode, ~2 ms per 48 k strings) runs on a helper thread while the
+        # C++ parser (which releases the GIL) works on part k
+        packer = None
+        packed_next = None
+        if blob is None and len(cuts) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            packer = ThreadPoolExecutor(1)
+            packed_next = packer.submit(core.pack_strings, strs[cuts[0][2]:cuts[0][3]])
+        for k_part, (b0, b1, lo, hi) in enumerate(cuts):
             t_a = time.perf_counter()
-            if blob is None:
+            if packer is not None:
+                part_blob, part_n = packed_next.result()
+                if k_part + 1 < len(cuts):
+                    packed_next = packer.submit(core.pack_strings, strs[cuts[k_part + 1][2]:cuts[k_part + 1][3]])
+                exprs = self.session.compile_blob(part_blob, part_n)
+            elif blob is None:
                 exprs = self.session.compile(strs[lo:hi])
             else:
                 exprs = self.session.compile_blob(blob if (b0 == 0 and b1 == len(blob)) else blob[b0:b1], hi - lo)
@@ -354,6 +368,8 @@ class GpuBatchValidator:
                           confirm_points=self.confirm_points, n_ref=3, spill_slots=self.spill_slots, out=part)
             tms.append((t_b - t_a, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
         t_e = time.perf_counter()
+        if packer is not None:
+            packer.shutdown(wait=False)
         host = {}
         for k, v in out.items():
             h = self._pin["host"][k][:v.shape[0]]
