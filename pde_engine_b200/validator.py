@@ -188,54 +188,76 @@ class GpuBatchValidator:
         if d is not None and d[2] == 0:
             import torch
             dist, grp, rank, world = d
-            hdr = torch.zeros(world + 2, dtype=torch.int64, device=self._comm_device(dist, grp))
+            hdr = torch.zeros(world + 3, dtype=torch.int64, device=self._comm_device(dist, grp))
             dist.broadcast(hdr, src=0, group=grp)
 
     def _comm_device(self, dist, grp):
         import torch
         return self.device if dist.get_backend(grp) == "nccl" else torch.device("cpu")
 
+    RANK0_SHARE = 0.55          # rank 0's shard relative to an equal share: it also turns everybody's strings into bytes
+
+    @classmethod
+    def _shard_bounds(cls, n: int, world: int) -> List[int]:
+        """String boundaries of the shards, 32-aligned (survivor words never straddle two shards), reference order."""
+        eq = n / world
+        w0 = cls.RANK0_SHARE * eq if world > 1 else n
+        rest = (n - w0) / max(world - 1, 1)
+        b, acc = [0], w0
+        for _ in range(1, world):
+            b.append(max(b[-1], min(n, int(acc) // 32 * 32)))
+            acc += rest
+        b.append(n)
+        return b
+
     def _sharded_prefilter(self, strs: Optional[List[str]], d):
-        """One sharded batch.  Rank 0 passes the strings; workers pass None and get them from rank 0 as ONE byte blob
-        (NUL-terminated strings, the compiler's own input format): header [cmd, n, bytes of shard 0..world-1], then the
-        payload.  Pickling the string list instead cost 44 + 25 ms for the 143 461 depth-4 uniques -- more than
-        compiling and validating them.  Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
+        """One sharded batch.  Rank 0 passes the strings; workers pass None.  Protocol: a broadcast header
+        [cmd, n, shard boundaries]; then rank 0 packs shard after shard into a byte blob (NUL-terminated strings, the
+        compiler's own input format -- pickling the 143 461 depth-4 strings cost 44 + 25 ms, more than compiling and
+        validating them) and SENDS each one as soon as it is packed, so the workers compile while rank 0 is still packing;
+        rank 0 takes a smaller shard (RANK0_SHARE) and does it last.  The verdict columns come back in one gather.
+        Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
         import time
         import torch
-        from .distributed import shard_range
         dist, grp, rank, world = d
         prof = os.environ.get("PDE_B200_PROFILE") is not None
         tm = [time.perf_counter()]
         cdev = self._comm_device(dist, grp)
-        hdr = torch.zeros(world + 2, dtype=torch.int64, device=cdev)
-        blobs = None
+        hdr = torch.zeros(world + 3, dtype=torch.int64, device=cdev)
         if rank == 0:
             n = len(strs)
-            blobs = [core.pack_strings(strs[f:f + c])[0] for f, c in (shard_range(n, r, world) for r in range(world))]
-            hdr = torch.tensor([1, n] + [len(b) for b in blobs], dtype=torch.int64).to(cdev)
+            hdr = torch.tensor([1, n] + self._shard_bounds(n, world), dtype=torch.int64).to(cdev)
         dist.broadcast(hdr, src=0, group=grp)
         h = hdr.cpu().tolist()
         if h[0] == 0:
             return False
-        n, sizes_b = int(h[1]), [int(x) for x in h[2:]]
+        n, bounds = int(h[1]), [int(x) for x in h[2:]]
+        first, count = bounds[rank], bounds[rank + 1] - bounds[rank]
+        threads = max(1, (os.cpu_count() or 1) // world)
         if rank == 0:
-            payload = torch.from_numpy(np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()).to(cdev)
+            for r in range(1, world):
+                blob_r = core.pack_strings(strs[bounds[r]:bounds[r + 1]])[0]
+                size = torch.tensor([len(blob_r)], dtype=torch.int64).to(cdev)
+                dist.send(size, dst=r, group=grp)
+                if len(blob_r):
+                    dist.send(torch.from_numpy(np.frombuffer(blob_r, dtype=np.uint8).copy()).to(cdev), dst=r, group=grp)
+            tm.append(time.perf_counter())
+            tm.append(tm[-1])
+            bv = self._prefilter_local(strs[first:first + count], compile_threads=threads)
         else:
-            payload = torch.empty(sum(sizes_b), dtype=torch.uint8, device=cdev)
-        tm.append(time.perf_counter())
-        dist.broadcast(payload, src=0, group=grp)
-        first, count = shard_range(n, rank, world)
-        tm.append(time.perf_counter())
-        if rank == 0:
-            bv = self._prefilter_local(strs[first:first + count], compile_threads=max(1, (os.cpu_count() or 1) // world), blob=blobs[0])
-        else:
-            lo = sum(sizes_b[:rank])
-            mine = payload[lo:lo + sizes_b[rank]].cpu().numpy().tobytes()
-            bv = self._prefilter_local(None, compile_threads=max(1, (os.cpu_count() or 1) // world), blob=mine, n=count)
-        tm.append(time.perf_counter())
+            size = torch.zeros(1, dtype=torch.int64, device=cdev)
+            dist.recv(size, src=0, group=grp)
+            tm.append(time.perf_counter())
+            nb = int(size.item())
+            payload = torch.empty(nb, dtype=torch.uint8, device=cdev)
+            if nb:
+                dist.recv(payload, src=0, group=grp)
+            mine = payload.cpu().numpy().tobytes()
+            tm.append(time.perf_counter())
+            bv = self._prefilter_local(None, compile_threads=threads, blob=mine, n=count)
+        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
         # the verdict columns of the shard as ONE byte buffer in native dtypes (struct of arrays, 97 B per candidate;
         # a float64 row per candidate cost more host time in conversions than the kernel takes)
-        sizes = [shard_range(n, r, world)[1] for r in range(world)]
         nmax = max(sizes)
         fields = [(name, np.dtype(np.float64), 1) for name in self._COLS[:3]] + \
                  [("n_finite", np.dtype(np.int32), 1), ("n_votes", np.dtype(np.int32), 1), ("ref_rs", np.dtype(np.float64), 6),
@@ -255,7 +277,7 @@ class GpuBatchValidator:
         dist.gather(pad, got, dst=0, group=grp)
         tm.append(time.perf_counter())
         if prof:
-            print(f"[sharded_prefilter rank {rank}] pack+header {1e3 * (tm[1] - tm[0]):.1f} ms, payload {1e3 * (tm[2] - tm[1]):.1f}, "
+            print(f"[sharded_prefilter rank {rank}] header+pack/wait {1e3 * (tm[1] - tm[0]):.1f} ms, payload {1e3 * (tm[2] - tm[1]):.1f}, "
                   f"local filter {1e3 * (tm[3] - tm[2]):.1f}, rows+gather {1e3 * (tm[4] - tm[3]):.1f}", file=sys.stderr, flush=True)
         if rank != 0:
             return None
