@@ -256,6 +256,7 @@ class GpuBatchValidator:
             tm.append(time.perf_counter())
             bv = self._prefilter_local(None, compile_threads=threads, blob=mine, n=count)
         sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+        tm.append(time.perf_counter())
         # the verdict columns of the shard as ONE byte buffer in native dtypes (struct of arrays, 97 B per candidate;
         # a float64 row per candidate cost more host time in conversions than the kernel takes)
         nmax = max(sizes)
