@@ -132,6 +132,7 @@ class GpuBatchValidator:
         self.table = torch.from_numpy(self.program.point_table(pts)).to(self.device)
         self._cache: Dict[str, Tuple[bool, dict, Optional[float]]] = {}
         self._pin = None
+        self._pin_gather = None
         self._last_evidence: dict = {}
         self.stats = {"gpu_evaluated": 0, "gpu_rejected": 0, "cpu_confirmed": 0, "not_compilable": 0}
         # forwarded attributes the engine reads (GM:2071-2074)
@@ -195,18 +196,39 @@ class GpuBatchValidator:
         import torch
         return self.device if dist.get_backend(grp) == "nccl" else torch.device("cpu")
 
-    RANK0_SHARE = 0.55          # rank 0's shard relative to an equal share: it also turns everybody's strings into bytes
+    PACK_RATIO = 0.07           # rank 0's cost of turning one string into bytes and sending it / a rank's cost of filtering it
 
     @classmethod
     def _shard_bounds(cls, n: int, world: int) -> List[int]:
-        """String boundaries of the shards, 32-aligned (survivor words never straddle two shards), reference order."""
-        eq = n / world
-        w0 = cls.RANK0_SHARE * eq if world > 1 else n
-        rest = (n - w0) / max(world - 1, 1)
-        b, acc = [0], w0
-        for _ in range(1, world):
+        """String boundaries of the shards, 32-aligned (survivor words never straddle two shards), reference order.
+        Rank 0 packs and sends the shards one after the other (ranks 1, 2, ... first, its own last), so rank r starts
+        later the larger r is and rank 0 last of all: the shards shrink accordingly so that all ranks FINISH together.
+        With x_r strings for rank r and rho = PACK_RATIO: rho * (x_1 + ... + x_r) + x_r = F for r >= 1 and
+        rho * (x_1 + ... + x_{world-1}) + x_0 = F; F follows from sum x = n (bisection)."""
+        if world <= 1:
+            return [0, n]
+        rho = cls.PACK_RATIO
+
+        def sizes(F):
+            xs, S = [], 0.0
+            for _ in range(1, world):
+                x = max(0.0, (F - rho * S) / (1.0 + rho))
+                xs.append(x)
+                S += x
+            return [max(0.0, F - rho * S)] + xs
+
+        lo, hi = 0.0, float(n) * (1.0 + rho) + 1.0
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if sum(sizes(mid)) < n:
+                lo = mid
+            else:
+                hi = mid
+        xs = sizes(hi)
+        b, acc = [0], 0.0
+        for r in range(world - 1):
+            acc += xs[r]
             b.append(max(b[-1], min(n, int(acc) // 32 * 32)))
-            acc += rest
         b.append(n)
         return b
 
@@ -274,7 +296,8 @@ class GpuBatchValidator:
             buf[pos:pos + count * k * dt.itemsize] = col.reshape(-1).view(np.uint8)
             pos += nmax * k * dt.itemsize
         pad = torch.from_numpy(buf).to(cdev)
-        got = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        big = torch.empty((world, pad.numel()), dtype=torch.uint8, device=cdev) if rank == 0 else None
+        got = [big[r] for r in range(world)] if rank == 0 else None
         dist.gather(pad, got, dst=0, group=grp)
         tm.append(time.perf_counter())
         if prof:
@@ -282,7 +305,14 @@ class GpuBatchValidator:
                   f"local filter {1e3 * (tm[3] - tm[2]):.1f}, rows+gather {1e3 * (tm[4] - tm[3]):.1f}", file=sys.stderr, flush=True)
         if rank != 0:
             return None
-        host = [g.cpu().numpy() for g in got]
+        if big.is_cuda:                       # ONE device-to-host copy into pinned memory (8 pageable copies cost 3 ms)
+            if self._pin_gather is None or self._pin_gather.shape != big.shape:
+                self._pin_gather = torch.empty(big.shape, dtype=torch.uint8).pin_memory()
+            self._pin_gather.copy_(big, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            host = [self._pin_gather[r].numpy() for r in range(world)]
+        else:
+            host = [g.numpy() for g in got]
         out, pos = {}, 0
         for name, dt, k in fields:
             parts = [h[pos:pos + c * k * dt.itemsize].view(dt) for h, c in zip(host, sizes)]
