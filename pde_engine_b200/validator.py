@@ -52,6 +52,9 @@ class BatchVerdict:
         self.confirm = out.get("confirm")          # [n, 2] (n_finite, n_votes) of the confirmation pass, -1 = not re-examined
         bits = out["survivor_bits"].view(np.uint32)
         n = len(self.strs) if self.strs is not None else int(n)
+        if "survivor" in out:                      # already unpacked (the gathered rows of the sharded path)
+            self.survivor = np.asarray(out["survivor"], bool)
+            return
         self.survivor = ((bits[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
 
     @property
@@ -320,8 +323,9 @@ class GpuBatchValidator:
             pos += nmax * k * dt.itemsize
         out["ref_rs"] = out["ref_rs"].reshape(n, 3, 2)
         out["confirm"] = out["confirm"].reshape(n, 2)
+        out["survivor"] = out["survivor"].astype(bool)
         surv = np.zeros((n + 31) // 32 * 32, bool)
-        surv[:n] = out.pop("survivor").astype(bool)
+        surv[:n] = out["survivor"]
         out["survivor_bits"] = np.packbits(surv, bitorder="little").view(np.int32)
         return BatchVerdict(strs, out.pop("flags"), out)
 
