@@ -295,10 +295,14 @@ struct SmallVec {
     T* end() { return begin() + n; }
 };
 
+// Bytes go through a raw write pointer into a buffer the worker sized up front (a postfix program is never longer
+// than its source text: every byte stands for at least one source character) -- push_back per byte was half the emit.
 struct Emitter {
-    std::vector<uint8_t>& out;
+    uint8_t* base;          // start of the worker's pool
+    uint8_t*& wp;           // write position
     std::vector<Fix>& fixes;
     Arena& ar;
+    void put(uint8_t b) { *wp++ = b; }
 
     struct Term { int sign; Node* body; };
     typedef SmallVec<Term, 24> Terms;
@@ -337,35 +341,35 @@ struct Emitter {
             int sign = 1;
             Node* body = (ir->kind == K_NEG || ir->kind == K_BIN) ? extract_sign(ir, sign) : ir;
             emit_term(body);
-            if (sign < 0) out.push_back(PDE_OP_NEG);
+            if (sign < 0) put(PDE_OP_NEG);
             return;
         }
         Terms terms;
         split_terms(ir, terms);
         for (size_t k = 0; k < terms.size(); ++k) {
             emit_term(terms[k].body);
-            if (k == 0) { if (terms[k].sign < 0) out.push_back(PDE_OP_NEG); }
-            else out.push_back(terms[k].sign > 0 ? PDE_OP_ADD : PDE_OP_SUB);
+            if (k == 0) { if (terms[k].sign < 0) put(PDE_OP_NEG); }
+            else put(terms[k].sign > 0 ? PDE_OP_ADD : PDE_OP_SUB);
         }
     }
 
     void placeholder(bool is_pow, bool named, i64 num, i64 den) {
-        fixes.push_back({(uint32_t)out.size(), (uint8_t)is_pow, (uint8_t)named, num, den});
-        out.push_back(is_pow ? PDE_OP_POW0 : PDE_OP_CONST0);
+        fixes.push_back({(uint32_t)(wp - base), (uint8_t)is_pow, (uint8_t)named, num, den});
+        put(is_pow ? PDE_OP_POW0 : PDE_OP_CONST0);
     }
 
     void emit_term(Node* t) {
         switch (t->kind) {
             case K_CONST: placeholder(false, false, t->rat.n, t->rat.d); break;
             case K_NCONST: placeholder(false, true, t->idx, 0); break;
-            case K_VAR: out.push_back((uint8_t)(PDE_OP_VAR0 + t->idx)); break;
-            case K_NEG: emit(t->a); out.push_back(PDE_OP_NEG); break;
+            case K_VAR: put((uint8_t)(PDE_OP_VAR0 + t->idx)); break;
+            case K_NEG: emit(t->a); put(PDE_OP_NEG); break;
             case K_BIN:
                 if (t->op == '+' || t->op == '-') emit(t);
-                else { emit(t->a); emit(t->b); out.push_back(t->op == '*' ? PDE_OP_MUL : PDE_OP_DIV); }
+                else { emit(t->a); emit(t->b); put(t->op == '*' ? PDE_OP_MUL : PDE_OP_DIV); }
                 break;
             case K_POW: emit(t->a); placeholder(true, false, t->rat.n, t->rat.d); break;
-            case K_CALL: emit(t->a); out.push_back((uint8_t)t->idx); break;
+            case K_CALL: emit(t->a); put((uint8_t)t->idx); break;
         }
     }
 };
@@ -389,34 +393,39 @@ struct Worker {
         Arena ar;
         const int n = hi - lo;
         n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0); attrs.assign(n, 0);
-        pool.reserve((size_t)n * 24);
+        // a program is never longer than its source: size the pool for the worker's whole range once
+        pool.resize((size_t)(off[hi] - off[lo]) + 64);
+        uint8_t* const base = pool.data();
+        uint8_t* wp = base;
+        term_sign.reserve((size_t)n * 2); term_off.reserve((size_t)n * 2);
         Emitter::Terms terms;
         for (int k = 0; k < n; ++k) {
             const char* str = blob + off[lo + k];
-            const size_t pool0 = pool.size(), nt0 = term_sign.size(), nf0 = fixes.size();
+            uint8_t* const wp0 = wp;
+            const size_t nt0 = term_sign.size(), nf0 = fixes.size();
             try {
                 ar.reset();
                 Parser ps(str, (size_t)(off[lo + k + 1] - off[lo + k] - 1), sess, ar);
                 Node* ir = ps.parse_expr();
                 ps.ws();
                 if (ps.pos != ps.n) throw Unsupported();
-                Emitter em{pool, fixes, ar};
+                Emitter em{base, wp, fixes, ar};
                 terms.clear();
                 em.split_terms(ir, terms);
                 for (auto& t : terms) {
                     em.emit_term(t.body);
                     term_sign.push_back((int8_t)t.sign);
-                    term_off.push_back((uint32_t)pool.size());
+                    term_off.push_back((uint32_t)(wp - base));
                 }
                 // whole program length: bodies + (NEG for a leading minus) + (nterms-1) ADD/SUB
-                const size_t whole = pool.size() - pool0 + (terms[0].sign < 0 ? 1 : 0) + (terms.size() - 1);
+                const size_t whole = (size_t)(wp - wp0) + (terms[0].sign < 0 ? 1 : 0) + (terms.size() - 1);
                 if (whole > 255) flags[k] = PDE_FLAG_TOO_LONG;
             } catch (const Unsupported&) {
                 flags[k] = PDE_FLAG_UNSUPPORTED;
             }
-            if (flags[k]) { pool.resize(pool0); term_sign.resize(nt0); term_off.resize(nt0); fixes.resize(nf0); }
+            if (flags[k]) { wp = wp0; term_sign.resize(nt0); term_off.resize(nt0); fixes.resize(nf0); }
             n_terms[k] = (uint32_t)(term_sign.size() - nt0);
-            pool_end[k] = (uint32_t)pool.size();
+            pool_end[k] = (uint32_t)(wp - base);
             fix_end[k] = (uint32_t)fixes.size();
             uint8_t attr = 0;                                  // string attributes of the prune predicates (LBF:134-152)
             if (has_vars(str)) attr |= PDE_ATTR_HAS_VARS;
@@ -424,6 +433,7 @@ struct Worker {
             if (strncmp(str, "inv(", 4) == 0) attr |= PDE_ATTR_STARTS_INV;
             attrs[k] = attr;
         }
+        pool.resize((size_t)(wp - base));
     }
 };
 
