@@ -393,6 +393,7 @@ struct Worker {
         Arena ar;
         const int n = hi - lo;
         n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0); attrs.assign(n, 0);
+        if (n == 0) return;                        // an empty batch has no offsets to read
         // a program is never longer than its source: size the pool for the worker's whole range once
         pool.resize((size_t)(off[hi] - off[lo]) + 64);
         uint8_t* const base = pool.data();
