@@ -429,9 +429,12 @@ def run_ours(args):
             kpts = collocation_grid("kerr_magnetosphere", P)
             kpts_t = torch.from_numpy(kpts).to(dev)
             ktab_t = torch.from_numpy(kprog.point_table(kpts)).to(dev)
-            ew = ksess.compile(uk[:256])
+            # untimed warm-up of the exact code path at full size (first use of a kernel configuration loads its module:
+            # a one-off cost of the process -- a 256-string warm-up once left 50 ms of it inside the timed call)
+            ew = ksess.compile(uk)
             cw, lw = ew.programs(128)
-            pb.validate(ksess, kprog, torch.from_numpy(cw).to(dev), torch.from_numpy(lw).to(dev), kpts_t, ktab_t, None, spill_slots=2)
+            pb.validate(ksess, kprog, torch.from_numpy(cw).to(dev), torch.from_numpy(lw).to(dev), kpts_t, ktab_t, None,
+                        tau=1e-10, min_finite=8, vote_frac=0.5, n_ref=3, spill_slots=2)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             ek = ksess.compile(uk)

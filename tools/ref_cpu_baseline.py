@@ -84,12 +84,22 @@ def run_reference_validators(problem: str = "force_free", max_depth: int = 3, va
         log.close()
         text = open(os.path.join(tmp, "run.log")).read()
         started = text.count("Validator process started")
-        log_tail = text[-1500:] if stats["completed"] == 0 else ""
+        # the reference's own monitor line: "Status (running): generated G, validated V/G (val r/s, gen r/s)" (GM:826-900).
+        # The run database is in WAL mode and is being written when the window closes: a second connection sometimes
+        # sees none of the UPDATEs yet, so the reference's own counter is taken when it is ahead of the database read.
+        import re
+        mon = [int(m.group(1)) for m in re.finditer(r"validated (\d+)/\d+", text)]
+        monitor_validated = max(mon) if mon else 0
+        db_completed = stats["completed"]
+        if monitor_validated > stats["completed"]:
+            stats["completed"] = monitor_validated
+        log_tail = text[-600:] if stats["completed"] == 0 else ""
     pts = POINTS_PER_ROW[problem]
     rps = stats["completed"] / wall if wall > 0 else 0.0
     return dict(kind="reference", command=f"python {GM} --problem {problem} --max-depth {max_depth} --validators {validators}",
                 validators=validators, validator_processes_started=started, cores=os.cpu_count(), wall_s=round(wall, 2),
                 run_finished=finished, rows_inserted=stats["rows"], rows_validated=stats["completed"], rows_valid=stats["valid"],
+                rows_validated_db=db_completed, rows_validated_monitor=monitor_validated,
                 by_depth=stats["by_depth"], rows_per_s=rps, points_per_row=pts, value=rps * pts, unit="evals/s",
                 patch=diff, log_tail=log_tail, note="bounded window: the process group is killed after wall_s; rows the pool completed are read from the run database")
 
