@@ -86,6 +86,10 @@ def main():
             "valid_max_vote_fraction": float(vf[val].max()) if len(val) else None,
             "valid_max_median_ratio": float(np.nanmax(med[val])) if len(val) else None,
             "valid_vote_fraction_on_plain_scale_S_max": float(d["frac_sharp"][val].max()) if len(val) else None,
+            # what the round-1 rule (votes on the plain scale S, no round-off majorant) would have done to them
+            "valid_rejected_by_round1_rule": [strs[i] for i in val if d["n_finite_sharp"][i] >= 8 and d["frac_sharp"][i] >= 0.5],
+            "timeouts_of_the_reference": sum(1 for r in recs if r.get("timeout")),
+            "timeouts_rejected_by_kernel": int((~surv[[idx[r["s"]] for r in recs if r.get("timeout") and r["s"] in idx]]).sum()) if any(r.get("timeout") for r in recs) else 0,
             "invalid_rejected_by_kernel": int((~surv[inv]).sum()) if len(inv) else 0,
             "invalid_median_ratio": hist_decades(med[inv]) if len(inv) else None}
     out = os.path.join(REPO, "profiles", f"filter_margin_{problem}_d{depth}.json")
