@@ -71,120 +71,236 @@ static Rat make_rat(__int128 n, __int128 d) {
     return r;
 }
 
-enum Kind { K_CONST, K_NCONST, K_VAR, K_NEG, K_BIN, K_POW, K_CALL };
-
-struct Node {
-    Kind kind;
-    Rat rat;            // K_CONST value, K_POW exponent
-    int idx = 0;        // K_VAR index, K_NCONST named index, K_CALL opcode
-    char op = 0;        // K_BIN: + - * /
-    Node* a = nullptr;
-    Node* b = nullptr;
+// A CONST / POW byte whose table slot is assigned later, in expression order (the tables are
+// append-only per session and their numbering is part of the bytecode, so the parallel parse
+// must not decide it).
+struct Fix {
+    uint32_t pos;        // byte position in the worker's pool
+    uint8_t is_pow;
+    uint8_t named;       // named constant (M, a, E): num = index into session->named
+    i64 num, den;
 };
 
-// bump allocator, reset per expression (a node per malloc was 20 % of the compile time)
-struct Arena {
-    std::vector<std::unique_ptr<Node[]>> chunks;
-    size_t used = 0;                      // nodes handed out since the last reset
-    static constexpr size_t kChunk = 256;
-    Node* make(Kind k) {
-        const size_t c = used / kChunk, o = used % kChunk;
-        if (c == chunks.size()) chunks.emplace_back(new Node[kChunk]);
-        ++used;
-        Node* x = &chunks[c][o];
-        *x = Node();
-        x->kind = k;
-        return x;
-    }
-    void reset() { used = 0; }
+static std::string rat_key(const Rat& r) {
+    return r.d == 1 ? std::to_string(r.n) : std::to_string(r.n) + "/" + std::to_string(r.d);
+}
+
+// ONE-PASS parser + emitter (round 2; the first version built an IR tree per string and walked it twice: 0.9 us per
+// string and thread, the bound of the depth-4 wall time at every GPU count).  The recursive descent appends postfix
+// bytes to the worker's pool as it goes; what the tree version expressed with nodes lives in the value it returns:
+//   sign    a leading unary minus of the sub-expression, NOT yet emitted -- it travels up the left spine of * / chains
+//           (-a*b*c -> a b MUL c MUL NEG) and is written as a trailing NEG only where the sub-expression is used as an
+//           operand; in an additive chain it merges into the ADD / SUB that joins the term
+//   konst   the sub-expression is one exact rational (one placeholder byte at the tail of the pool + the last Fix):
+//           constant (op) constant folds in place, -constant negates in place, base ** constant takes the exponent
+//   start   where its bytes begin (they always end at the current write position)
+// The output is byte-for-byte what the tree version produced (tests/test_compiler.py: 200 k strings against
+// oracle/parser.py, which parses with Python's own `ast`).
+struct Val {
+    int sign = 1;
+    bool konst = false;
+    Rat rat;
+    uint32_t start = 0;
 };
 
-struct Parser {
+struct TermRec { int sign; uint32_t end; };
+
+struct OnePass {
     const char* s;
     size_t pos = 0, n;
     const pde_session* sess;
-    Arena& ar;
+    uint8_t* base;
+    uint8_t*& wp;
+    std::vector<Fix>& fixes;
     int depth = 0;
-    Parser(const char* str, size_t len, const pde_session* se, Arena& a) : s(str), n(len), sess(se), ar(a) {}
+
+    OnePass(const char* str, size_t len, const pde_session* se, uint8_t* b, uint8_t*& w, std::vector<Fix>& f)
+        : s(str), n(len), sess(se), base(b), wp(w), fixes(f) {}
 
     void ws() { while (pos < n && (s[pos] == ' ' || s[pos] == '\t')) ++pos; }
     bool peek(char c) { ws(); return pos < n && s[pos] == c; }
     bool peek2(const char* t) { ws(); return pos + 1 < n && s[pos] == t[0] && s[pos + 1] == t[1]; }
+    void put(uint8_t b) { *wp++ = b; }
+    uint32_t here() const { return (uint32_t)(wp - base); }
 
-    Node* constant(Rat r) { Node* x = ar.make(K_CONST); x->rat = r; return x; }
+    Val push_const(const Rat& r) {
+        Val v; v.konst = true; v.rat = r; v.start = here();
+        fixes.push_back({here(), 0, 0, r.n, r.d});
+        put(PDE_OP_CONST0);
+        return v;
+    }
+    void pop_const() { --wp; fixes.pop_back(); }                     // the constant at the tail (byte + Fix)
+    void use(const Val& v) { if (v.sign < 0) put(PDE_OP_NEG); }      // v becomes an operand: its pending minus is written now
 
-    Node* parse_expr() {
+    static Rat fold(char op, const Rat& l, const Rat& r) {
+        const __int128 an = l.n, ad = l.d, bn = r.n, bd = r.d;
+        switch (op) {
+            case '+': return make_rat(an * bd + bn * ad, ad * bd);
+            case '-': return make_rat(an * bd - bn * ad, ad * bd);
+            case '*': return make_rat(an * bn, ad * bd);
+            default:
+                if (bn == 0) throw Unsupported();
+                return make_rat(an * bd, ad * bn);
+        }
+    }
+
+    // expr := term (('+'|'-') term)*.  top != null: the top level of the string -- the additive terms are RECORDED (sign,
+    // end of body) instead of joined, because the enumerator splices operands term-wise (LBF:170-195).
+    // The terms are those of the left spine of the PARSED tree, and parentheses leave no trace in it: `(a + b) + c` has
+    // the three terms a, b, c.  So when the first term of a top-level chain is a complete parenthesised expression
+    // (`leading_paren_is_a_term`), its inner chain is continued instead of being closed (`parse_first`).
+    bool leading_paren_is_a_term(size_t& open_at) {
+        size_t q = pos;
+        while (q < n && (s[q] == ' ' || s[q] == '\t' || s[q] == '+')) ++q;        // unary plus is transparent
+        if (!(q < n && s[q] == '(')) return false;
+        open_at = q;
+        int level = 0;
+        for (; q < n; ++q) {
+            if (s[q] == '(') ++level;
+            else if (s[q] == ')' && --level == 0) break;
+        }
+        if (q >= n) return false;
+        ++q;
+        while (q < n && (s[q] == ' ' || s[q] == '\t')) ++q;
+        return q >= n || s[q] == '+' || s[q] == '-' || s[q] == ')';
+    }
+
+    Val parse_first(std::vector<TermRec>* top, bool& chain) {
+        size_t open_at = 0;
+        if (top && leading_paren_is_a_term(open_at)) {
+            if (++depth > 200) throw Unsupported();
+            pos = open_at + 1;
+            Val acc = parse_first(top, chain);
+            additive_loop(acc, chain, top);
+            if (!peek(')')) throw Unsupported();
+            ++pos;
+            --depth;
+            return acc;
+        }
+        return parse_term();
+    }
+
+    void additive_loop(Val& acc, bool& chain, std::vector<TermRec>* top) {
+        for (;;) {
+            ws();
+            if (!(pos < n && (s[pos] == '+' || s[pos] == '-'))) break;
+            const char op = s[pos++];
+            if (!chain && !acc.konst) {               // a non-constant first term: the chain starts here
+                if (top) top->push_back({acc.sign, here()});
+                else use(acc);
+                acc.sign = 1;
+                chain = true;
+            }
+            const Val t = parse_term();
+            if (!chain) {                             // acc is a constant so far
+                if (t.konst) {                        // constant (+|-) constant: folded in place
+                    const Rat r = fold(op, acc.rat, t.rat);
+                    pop_const(); pop_const();
+                    const uint32_t st = acc.start;
+                    acc = push_const(r);
+                    acc.start = st;
+                    continue;
+                }
+                if (top) top->push_back({1, t.start});   // the constant is term 1 (it ends where t begins)
+                chain = true;
+                acc.konst = false;
+            }
+            const int sg = (op == '+' ? 1 : -1) * t.sign;
+            if (top) top->push_back({sg, here()});
+            else put(sg > 0 ? PDE_OP_ADD : PDE_OP_SUB);
+        }
+    }
+
+    Val parse_expr(std::vector<TermRec>* top) {
         if (++depth > 200) throw Unsupported();
-        Node* l = parse_term();
-        for (;;) {
-            ws();
-            if (pos < n && (s[pos] == '+' || s[pos] == '-')) {
-                char op = s[pos++];
-                Node* r = parse_term();
-                l = binop(op, l, r);
-            } else break;
-        }
+        bool chain = false;
+        Val acc = parse_first(top, chain);
+        additive_loop(acc, chain, top);
+        if (top && !chain) top->push_back({acc.sign, here()});
         --depth;
-        return l;
+        return acc;
     }
-    Node* parse_term() {
-        Node* l = parse_factor();
+
+    // term := factor (('*'|'/') factor)*
+    Val parse_term() {
+        Val l = parse_factor();
         for (;;) {
             ws();
-            if (pos < n && (s[pos] == '*' || s[pos] == '/') && !(pos + 1 < n && s[pos] == '*' && s[pos + 1] == '*')) {
-                if (s[pos] == '/' && pos + 1 < n && s[pos + 1] == '/') throw Unsupported();
-                char op = s[pos++];
-                Node* r = parse_factor();
-                l = binop(op, l, r);
-            } else break;
+            if (!(pos < n && (s[pos] == '*' || s[pos] == '/') && !(pos + 1 < n && s[pos] == '*' && s[pos + 1] == '*'))) break;
+            if (s[pos] == '/' && pos + 1 < n && s[pos + 1] == '/') throw Unsupported();
+            const char op = s[pos++];
+            const Val r = parse_factor();
+            if (l.konst && r.konst) {
+                const Rat q = fold(op, l.rat, r.rat);
+                pop_const(); pop_const();
+                const uint32_t st = l.start;
+                l = push_const(q);
+                l.start = st;
+                continue;
+            }
+            use(r);
+            put(op == '*' ? PDE_OP_MUL : PDE_OP_DIV);
+            l.konst = false;                          // the sign of the left spine stays pending
         }
         return l;
     }
-    Node* parse_factor() {
+
+    // factor := ('+'|'-') factor | power
+    Val parse_factor() {
         ws();
         if (++depth > 200) throw Unsupported();
-        Node* res;
-        if (pos < n && s[pos] == '+') { ++pos; res = parse_factor(); }
+        Val v;
+        if (pos < n && s[pos] == '+') { ++pos; v = parse_factor(); }
         else if (pos < n && s[pos] == '-') {
             ++pos;
-            Node* x = parse_factor();
-            if (x->kind == K_CONST) { Rat r = x->rat; r.n = -r.n; res = constant(r); }
-            else { res = ar.make(K_NEG); res->a = x; }
-        } else res = parse_power();
+            v = parse_factor();
+            if (v.konst) { v.rat.n = -v.rat.n; fixes.back().num = v.rat.n; }
+            else v.sign = -v.sign;
+        } else v = parse_power();
         --depth;
-        return res;
+        return v;
     }
-    Node* parse_power() {
-        Node* base = parse_atom();
-        if (peek2("**")) {
-            pos += 2;
-            Node* e = parse_factor();
-            if (e->kind != K_CONST) throw Unsupported();
-            Rat k = e->rat;
-            if (base->kind == K_CONST && k.d == 1) {
-                if (k.n > 64 || k.n < -64) throw Unsupported();
-                if (base->rat.n == 0 && k.n < 0) throw Unsupported();
-                __int128 nn = 1, dd = 1;
-                i64 e2 = k.n < 0 ? -k.n : k.n;
-                for (i64 i = 0; i < e2; ++i) {
-                    nn *= base->rat.n; dd *= base->rat.d;
-                    if (nn > ((__int128)1 << 100) || nn < -((__int128)1 << 100) || dd > ((__int128)1 << 100)) throw Unsupported();
-                }
-                return constant(k.n < 0 ? make_rat(dd, nn) : make_rat(nn, dd));
+
+    // power := atom ('**' factor)?
+    Val parse_power() {
+        Val b = parse_atom();
+        if (!peek2("**")) return b;
+        pos += 2;
+        const Val e = parse_factor();
+        if (!e.konst) throw Unsupported();
+        const Rat k = e.rat;
+        pop_const();                                  // the exponent is not an operand: it becomes part of the POW byte
+        if (b.konst && k.d == 1) {
+            if (k.n > 64 || k.n < -64) throw Unsupported();
+            if (b.rat.n == 0 && k.n < 0) throw Unsupported();
+            __int128 nn = 1, dd = 1;
+            const i64 e2 = k.n < 0 ? -k.n : k.n;
+            for (i64 i = 0; i < e2; ++i) {
+                nn *= b.rat.n; dd *= b.rat.d;
+                if (nn > ((__int128)1 << 100) || nn < -((__int128)1 << 100) || dd > ((__int128)1 << 100)) throw Unsupported();
             }
-            Node* p = ar.make(K_POW);
-            p->a = base; p->rat = k;
-            return p;
+            const Rat r = k.n < 0 ? make_rat(dd, nn) : make_rat(nn, dd);
+            pop_const();
+            const uint32_t st = b.start;
+            Val v = push_const(r);
+            v.start = st;
+            return v;
         }
-        return base;
+        use(b);
+        fixes.push_back({here(), 1, 0, k.n, k.d});
+        put(PDE_OP_POW0);
+        Val v; v.start = b.start;
+        return v;
     }
-    Node* parse_atom() {
+
+    // atom := INT | NAME | NAME '(' expr ')' | '(' expr ')'
+    Val parse_atom() {
         ws();
         if (pos >= n) throw Unsupported();
-        char c = s[pos];
+        const char c = s[pos];
         if (c == '(') {
             ++pos;
-            Node* e = parse_expr();
+            const Val e = parse_expr(nullptr);
             if (!peek(')')) throw Unsupported();
             ++pos;
             return e;
@@ -201,35 +317,42 @@ struct Parser {
                 ++pos;
             }
             if (pos < n && (s[pos] == '.' || s[pos] == 'e' || s[pos] == 'E' || s[pos] == '_' || s[pos] == 'j')) throw Unsupported();
-            if (nd < 16) { Rat r; r.n = (i64)v64; r.d = 1; return constant(r); }       // < 2^53: no reduction needed
-            return constant(make_rat(v, 1));
+            if (nd < 16) { Rat r; r.n = (i64)v64; r.d = 1; return push_const(r); }       // < 2^53: no reduction needed
+            return push_const(make_rat(v, 1));
         }
         if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') {
-            size_t st = pos;
+            const size_t st = pos;
             while (pos < n && ((s[pos] >= 'a' && s[pos] <= 'z') || (s[pos] >= 'A' && s[pos] <= 'Z') || (s[pos] >= '0' && s[pos] <= '9') || s[pos] == '_')) ++pos;
             const char* nm = s + st;
             const size_t nl = pos - st;
             auto is = [&](const std::string& t) { return t.size() == nl && memcmp(t.data(), nm, nl) == 0; };
             if (peek('(')) {
                 ++pos;
-                int opc = func_opcode(nm, nl);
-                Node* arg = parse_expr();
+                const int opc = func_opcode(nm, nl);
+                const Val arg = parse_expr(nullptr);
                 if (peek(',')) throw Unsupported();
                 if (!peek(')')) throw Unsupported();
                 ++pos;
                 if (opc < 0) throw Unsupported();
-                Node* x = ar.make(K_CALL);
-                x->idx = opc; x->a = arg;
-                return x;
+                use(arg);
+                put((uint8_t)opc);
+                Val v; v.start = arg.start;
+                return v;
             }
-            if (is(sess->var[0])) { Node* x = ar.make(K_VAR); x->idx = 0; return x; }
-            if (is(sess->var[1])) { Node* x = ar.make(K_VAR); x->idx = 1; return x; }
+            Val v; v.start = here();
+            if (is(sess->var[0])) { put(PDE_OP_VAR0); return v; }
+            if (is(sess->var[1])) { put((uint8_t)(PDE_OP_VAR0 + 1)); return v; }
             for (size_t i = 0; i < sess->named.size(); ++i)
-                if (is(sess->named[i])) { Node* x = ar.make(K_NCONST); x->idx = (int)i; return x; }
+                if (is(sess->named[i])) {
+                    fixes.push_back({here(), 0, 1, (i64)i, 0});
+                    put(PDE_OP_CONST0);
+                    return v;
+                }
             throw Unsupported();
         }
         throw Unsupported();
     }
+
     static int func_opcode(const char* f, size_t n) {
         auto eq = [&](const char* t, size_t tn) { return n == tn && memcmp(f, t, tn) == 0; };
         switch (n) {
@@ -247,129 +370,6 @@ struct Parser {
                 return -1;
             case 11: return eq("pow_neg_3_2", 11) ? PDE_OP_FN_POWN32 : -1;
             default: return -1;
-        }
-    }
-    Node* binop(char op, Node* l, Node* r) {
-        if (l->kind == K_CONST && r->kind == K_CONST) {
-            __int128 an = l->rat.n, ad = l->rat.d, bn = r->rat.n, bd = r->rat.d;
-            switch (op) {
-                case '+': return constant(make_rat(an * bd + bn * ad, ad * bd));
-                case '-': return constant(make_rat(an * bd - bn * ad, ad * bd));
-                case '*': return constant(make_rat(an * bn, ad * bd));
-                default:
-                    if (bn == 0) throw Unsupported();
-                    return constant(make_rat(an * bd, ad * bn));
-            }
-        }
-        Node* x = ar.make(K_BIN);
-        x->op = op; x->a = l; x->b = r;
-        return x;
-    }
-};
-
-static std::string rat_key(const Rat& r) {
-    return r.d == 1 ? std::to_string(r.n) : std::to_string(r.n) + "/" + std::to_string(r.d);
-}
-
-// A CONST / POW byte whose table slot is assigned later, in expression order (the tables are
-// append-only per session and their numbering is part of the bytecode, so the parallel parse
-// must not decide it).
-struct Fix {
-    uint32_t pos;        // byte position in the worker's pool
-    uint8_t is_pow;
-    uint8_t named;       // named constant (M, a, E): num = index into session->named
-    i64 num, den;
-};
-
-// Term lists live on the stack up to 24 entries (a heap allocation per additive group was a visible share of the parse)
-template <class T, int N>
-struct SmallVec {
-    T inl[N];
-    std::vector<T> big;
-    int n = 0;
-    void push_back(const T& v) { if (n < N) inl[n] = v; else { if (n == N) big.assign(inl, inl + N); big.push_back(v); } ++n; }
-    T& operator[](size_t i) { return n <= N ? inl[i] : big[i]; }
-    size_t size() const { return (size_t)n; }
-    void clear() { n = 0; big.clear(); }
-    T* begin() { return n <= N ? inl : big.data(); }
-    T* end() { return begin() + n; }
-};
-
-// Bytes go through a raw write pointer into a buffer the worker sized up front (a postfix program is never longer
-// than its source text: every byte stands for at least one source character) -- push_back per byte was half the emit.
-struct Emitter {
-    uint8_t* base;          // start of the worker's pool
-    uint8_t*& wp;           // write position
-    std::vector<Fix>& fixes;
-    Arena& ar;
-    void put(uint8_t b) { *wp++ = b; }
-
-    struct Term { int sign; Node* body; };
-    typedef SmallVec<Term, 24> Terms;
-
-    // leading unary minus: leftmost leaf of the * / chain
-    Node* extract_sign(Node* t, int& sign) {
-        if (t->kind == K_NEG) { sign = -sign; return extract_sign(t->a, sign); }
-        if (t->kind == K_BIN && (t->op == '*' || t->op == '/')) {
-            Node* l2 = extract_sign(t->a, sign);
-            if (l2 != t->a) {
-                Node* x = ar.make(K_BIN);
-                x->op = t->op; x->a = l2; x->b = t->b;
-                return x;
-            }
-        }
-        return t;
-    }
-
-    void split_terms(Node* ir, Terms& terms) {
-        Terms chain;
-        while (ir->kind == K_BIN && (ir->op == '+' || ir->op == '-')) {
-            chain.push_back({ir->op == '+' ? 1 : -1, ir->b});
-            ir = ir->a;
-        }
-        chain.push_back({1, ir});
-        for (size_t i = chain.size(); i-- > 0;) {
-            int sign = chain[i].sign;
-            Node* body = extract_sign(chain[i].body, sign);
-            terms.push_back({sign, body});
-        }
-    }
-
-    void emit(Node* ir) {
-        if (!(ir->kind == K_BIN && (ir->op == '+' || ir->op == '-'))) {
-            // one term (by far the common case: every operand of * / ** and of a call comes through here)
-            int sign = 1;
-            Node* body = (ir->kind == K_NEG || ir->kind == K_BIN) ? extract_sign(ir, sign) : ir;
-            emit_term(body);
-            if (sign < 0) put(PDE_OP_NEG);
-            return;
-        }
-        Terms terms;
-        split_terms(ir, terms);
-        for (size_t k = 0; k < terms.size(); ++k) {
-            emit_term(terms[k].body);
-            if (k == 0) { if (terms[k].sign < 0) put(PDE_OP_NEG); }
-            else put(terms[k].sign > 0 ? PDE_OP_ADD : PDE_OP_SUB);
-        }
-    }
-
-    void placeholder(bool is_pow, bool named, i64 num, i64 den) {
-        fixes.push_back({(uint32_t)(wp - base), (uint8_t)is_pow, (uint8_t)named, num, den});
-        put(is_pow ? PDE_OP_POW0 : PDE_OP_CONST0);
-    }
-
-    void emit_term(Node* t) {
-        switch (t->kind) {
-            case K_CONST: placeholder(false, false, t->rat.n, t->rat.d); break;
-            case K_NCONST: placeholder(false, true, t->idx, 0); break;
-            case K_VAR: put((uint8_t)(PDE_OP_VAR0 + t->idx)); break;
-            case K_NEG: emit(t->a); put(PDE_OP_NEG); break;
-            case K_BIN:
-                if (t->op == '+' || t->op == '-') emit(t);
-                else { emit(t->a); emit(t->b); put(t->op == '*' ? PDE_OP_MUL : PDE_OP_DIV); }
-                break;
-            case K_POW: emit(t->a); placeholder(true, false, t->rat.n, t->rat.d); break;
-            case K_CALL: emit(t->a); put((uint8_t)t->idx); break;
         }
     }
 };
@@ -390,7 +390,6 @@ struct Worker {
     std::vector<uint8_t> flags, attrs;
 
     void run(const char* blob, const uint32_t* off, const pde_session* sess) {
-        Arena ar;
         const int n = hi - lo;
         n_terms.assign(n, 0); pool_end.assign(n, 0); fix_end.assign(n, 0); flags.assign(n, 0); attrs.assign(n, 0);
         if (n == 0) return;                        // an empty batch has no offsets to read
@@ -399,24 +398,20 @@ struct Worker {
         uint8_t* const base = pool.data();
         uint8_t* wp = base;
         term_sign.reserve((size_t)n * 2); term_off.reserve((size_t)n * 2);
-        Emitter::Terms terms;
+        std::vector<TermRec> terms;
         for (int k = 0; k < n; ++k) {
             const char* str = blob + off[lo + k];
             uint8_t* const wp0 = wp;
             const size_t nt0 = term_sign.size(), nf0 = fixes.size();
             try {
-                ar.reset();
-                Parser ps(str, (size_t)(off[lo + k + 1] - off[lo + k] - 1), sess, ar);
-                Node* ir = ps.parse_expr();
+                OnePass ps(str, (size_t)(off[lo + k + 1] - off[lo + k] - 1), sess, base, wp, fixes);
+                terms.clear();
+                ps.parse_expr(&terms);
                 ps.ws();
                 if (ps.pos != ps.n) throw Unsupported();
-                Emitter em{base, wp, fixes, ar};
-                terms.clear();
-                em.split_terms(ir, terms);
-                for (auto& t : terms) {
-                    em.emit_term(t.body);
+                for (const TermRec& t : terms) {
                     term_sign.push_back((int8_t)t.sign);
-                    term_off.push_back((uint32_t)(wp - base));
+                    term_off.push_back(t.end);
                 }
                 // whole program length: bodies + (NEG for a leading minus) + (nterms-1) ADD/SUB
                 const size_t whole = (size_t)(wp - wp0) + (terms[0].sign < 0 ? 1 : 0) + (terms.size() - 1);
