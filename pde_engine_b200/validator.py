@@ -98,11 +98,12 @@ def _cut_blob(blob: bytes, n: int, bounds: Sequence[int]):
     return cuts
 
 
-# Shares of a large batch per pipeline part (part k + 1 is compiled while the device validates part k).  The host work
-# per part exceeds the kernel's (143 461 depth-4 uniques: compile 19-25 ms in total, kernel 21.8), so the wall is
-# roughly the sum of the compiles + the last part's kernel: few parts (each has a fixed cost; five parts measured
-# 43.2 ms against 41.6 for three; a small last part, 44/44/12 %, 40.7-45.0 ms against 38.4-47.5 for thirds: no gain).
-PART_SHARES = (0.34, 0.34, 0.32)
+# Shares of a large batch per pipeline part (part k + 1 is compiled while the device validates part k).  With the
+# one-pass host compiler a part compiles about as fast as the device validates it (143 461 depth-4 uniques: compile
+# ~20 ms in total, kernel 22 ms), so the wall is ~ first compile + kernel + result copies: a small first part gets the
+# device going early.  Medians on a B200 host: thirds 38.9 ms, quarters 40.7, halves 39.3, (8, 30, 31, 31 %) 37.0,
+# (6, 20, 37, 37 %) 36.2.
+PART_SHARES = (0.06, 0.20, 0.37, 0.37)
 
 
 class GpuBatchValidator:
