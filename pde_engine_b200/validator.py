@@ -241,7 +241,8 @@ class GpuBatchValidator:
         [cmd, n, shard boundaries]; then rank 0 packs shard after shard into a byte blob (NUL-terminated strings, the
         compiler's own input format -- pickling the 143 461 depth-4 strings cost 44 + 25 ms, more than compiling and
         validating them) and SENDS each one as soon as it is packed, so the workers compile while rank 0 is still packing;
-        rank 0 takes a smaller shard (RANK0_SHARE) and does it last.  The verdict columns come back in one gather.
+        rank 0 does its own shard last; the shard sizes make all ranks finish together (`_shard_bounds`).  The verdict
+        columns come back in one gather.
         Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
         import time
         import torch
