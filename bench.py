@@ -31,8 +31,8 @@ METRIC = "candidate_x_point_fp64_jet_evals_per_sec"
 UNIT = "evals/s"
 NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 # validate_kernel's DRAM traffic from the committed ncu --set full capture (read + written bytes / trees of that launch)
-TRAFFIC_BYTES_PER_TREE = 55.2
-TRAFFIC_SOURCE = "profiles/r1b_validate_full_metrics.csv (ncu --set full, 200 000 trees: dram__bytes_read.sum 11.03 MB, dram__bytes_write.sum 0)"
+TRAFFIC_BYTES_PER_TREE = 55.0
+TRAFFIC_SOURCE = "profiles/r2_validate_full_metrics.csv (ncu --set full of pass 1, 200 000 trees: dram__bytes_read.sum 10.99 MB, dram__bytes_write.sum 0; pass 2 adds 8.5 + 2.6 MB)"
 
 
 def parse_args():

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.h"
 #include "validate.cuh"
 
@@ -89,8 +90,11 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
     // the dynamic chunk counter: 8 bytes from the library's stream-ordered pool, zeroed and released on the stream
     ValidateParams v = vp;
     unsigned long long* ctr = nullptr;
-    if (int rc = scratch_alloc(reinterpret_cast<void**>(&ctr), sizeof(unsigned long long), st)) return rc;
-    PDE_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+    static const bool static_deal = getenv("PDE_B200_STATIC_DEAL") != nullptr;      // A/B switch: round-robin chunks
+    if (!static_deal) {
+        if (int rc = scratch_alloc(reinterpret_cast<void**>(&ctr), sizeof(unsigned long long), st)) return rc;
+        PDE_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+    }
     v.chunk_counter = ctr;
     kern<<<grid, W * 32, smem, st>>>(v);
     count_launch();
