@@ -253,7 +253,7 @@ int  pde_compile_residual_program(int jet_order, int n_cols, const double *const
  * oracle/majorant.py).  For an exact solution |R| <= tau S~ under
  * ANY float64 evaluation order, so a point can only vote when its residual is
  * non-zero beyond the propagated rounding error of u's own jet; t0 (0 < t0 <= 1,
- * default 1/8) is the radius the majorant series are evaluated at: points
+ * the Python layer uses 1/16) is the radius the majorant series are evaluated at: points
  * closer than t0 to a pole of a sub-expression do not vote.
  *
  * Two passes (confirm_points > 0, a multiple of 128; default 128): carrying the
