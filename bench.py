@@ -417,6 +417,45 @@ def run_ours(args):
     except Exception as e:   # the fixture is optional for the headline metric
         depth4 = {"error": repr(e)[:200]}
 
+    # ---- the same depth WITHOUT strings: stage 1 -> stage 2 on the device (the generator's last-depth path) ----
+    # Rank 0 passes the 3 786 operand strings (depth <= 3 uniques) to GpuBatchValidator.filter_enumerated; every rank
+    # enumerates its window of the 258 285 raw depth-4 candidates into CSR rows and validates them where they were
+    # written; the survivor words are gathered on rank 0.  No candidate ever exists as a string.
+    depth4_dev = None
+    try:
+        with gzip.open(os.path.join(REPO, "tests", "golden", "enum_force_free_d4.json.gz"), "rt") as f:
+            gd4 = json.load(f)["depths"]
+        flat4, db4 = [], [0]
+        for d_ in ("1", "2", "3"):
+            flat4 += gd4[d_]["uniques"]
+            db4.append(len(flat4))
+        gv5 = GpuBatchValidator(None, "force_free", P=P, device=dev)
+        walls = []
+        if rank == 0:
+            try:
+                for _ in range(2):
+                    gv5.filter_enumerated(flat4, db4, 4, True, 128)
+                for _ in range(5):
+                    tq = time.perf_counter()
+                    surv5 = gv5.filter_enumerated(flat4, db4, 4, True, 128)
+                    walls.append((time.perf_counter() - tq) * 1e3)
+            finally:
+                gv5.shutdown()             # (always: the other ranks sit in serve())
+            es5 = gv5.session.compile(flat4)
+            c5 = pb.enumerate_candidates_csr(es5, db4, 4, True, 0, len(surv5), 128, device=dev)
+            f5, nu5 = pb.dedup_csr(c5["pool"], c5["off"], c5["len"], c5["hash"])
+            f5 = f5.cpu().numpy().astype(bool)
+            depth4_dev = {"input": f"{len(flat4)} force-free uniques of depth <= 3 (operands); the {len(surv5)} raw depth-4 candidates are enumerated on the device",
+                          "n_candidates": int(len(surv5)), "distinct_programs": int(nu5), "points": P,
+                          "wall_ms_operand_strings_to_survivor_flags": float(np.median(walls)), "wall_ms_runs": [round(x, 3) for x in walls],
+                          "survivors_for_the_normaliser": int((surv5 & f5).sum()), "rejected_on_device": int((~surv5).sum()),
+                          "note": "GpuBatchValidator.filter_enumerated from rank 0 (ranks > 0 in serve()): operand strings broadcast (0.1 MB), every rank compiles them, enumerates its shard_range window in CSR form (pde_enumerate_csr), drops exact duplicates inside the window (pde_dedup_csr) and validates the rest (pde_validate_csr); one gather of survivor words.  Host wall clock on rank 0 around the call, median of 5"}
+        else:
+            gv5.serve()
+        barrier()
+    except Exception as e:
+        depth4_dev = {"error": repr(e)[:200]}
+
     # ---- BASELINE configs[3]: kerr_magnetosphere depth 3 (order-2 jets, 16 174 uniques), same span A ----
     kerr3 = None
     if rank == 0:
@@ -603,6 +642,7 @@ def run_ours(args):
                              "the kernel has no early exit, every tree is evaluated at every point (evaluated_fraction)",
             "strong_scaling": strong,
             "depth4_validation": depth4,
+            "depth4_device_resident": depth4_dev,
             "kerr_depth3_validation": kerr3,
             "function_fingerprints_depth4": fp_info,
             "enumerator": enum_info,

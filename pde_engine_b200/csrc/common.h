@@ -16,6 +16,7 @@ bool have_device();
 // cudaFree around every call (8-70 ms for the 400 MB dedup table).
 int scratch_alloc(void** ptr, size_t bytes, void* stream);
 void scratch_free(void* ptr, void* stream);
+void exprset_mark_use(const pde_exprset* e, void* stream);     // pde_b200.cu: the handle's mirrors are in use on `stream` up to here
 
 #define PDE_CUDA(call)                                                     \
     do {                                                                   \
@@ -56,8 +57,10 @@ struct pde_exprset {
     std::vector<char> str_blob;         // the source strings (NUL separated): lazy lexicographic rank
     std::vector<uint32_t> str_off;      // [n+1]
     bool rank_ready = false;
-    // device mirrors (cudaMalloc'd by the library on first use by the enumerator)
+    // device mirrors (from the library's stream-ordered pool, on first use by the enumerator; cudaMalloc / cudaFree
+    // per handle cost 1-20 ms and, now and then, several hundred -- more than a whole depth-4 validation)
     int device = -1;
+    void* used_event = nullptr;         // cudaEvent_t: recorded after the last kernel that reads the mirrors; the free waits for it
     uint8_t* d_flags = nullptr;
     uint8_t* d_attrs = nullptr;
     uint32_t* d_rank = nullptr;

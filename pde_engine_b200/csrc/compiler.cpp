@@ -570,8 +570,8 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
 template <typename T>
 static int upload(T** dptr, const std::vector<T>& v) {
     size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
-    cudaError_t e = cudaMalloc((void**)dptr, bytes);
-    if (e != cudaSuccess) return pde::cuda_fail((int)e, "cudaMalloc(exprset)");
+    if (int rc = pde::scratch_alloc((void**)dptr, bytes, nullptr)) return rc;     // legacy stream: ordered before the copy below
+    cudaError_t e;
     if (!v.empty()) {
         e = cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return pde::cuda_fail((int)e, "cudaMemcpy(exprset)");
@@ -701,11 +701,14 @@ int pde_compile_exprs_packed(pde_session* s, const char* blob, const uint32_t* o
 void pde_exprset_free(pde_exprset* e) {
     if (!e) return;
     if (e->device >= 0) {
-        cudaFree(e->d_flags); cudaFree(e->d_attrs); cudaFree(e->d_rank); cudaFree(e->d_term_begin);
-        cudaFree(e->d_term_sign); cudaFree(e->d_term_off); cudaFree(e->d_pool); cudaFree(e->d_desc); cudaFree(e->d_wpool);
-        cudaFree(e->d_count_sums); cudaFree(e->d_count_in_tile); cudaFree(e->d_count_tile);
-        cudaFree(e->d_bytes_sums); cudaFree(e->d_bytes_in_tile); cudaFree(e->d_bytes_tile);
+        // stream-ordered: the legacy stream waits for the last kernel that read the mirrors, then the buffers go back to
+        // the library's pool (no device-wide synchronisation, unlike cudaFree)
+        if (e->used_event) cudaStreamWaitEvent(nullptr, (cudaEvent_t)e->used_event, 0);
+        void* bufs[] = {e->d_flags, e->d_attrs, e->d_rank, e->d_term_begin, e->d_term_sign, e->d_term_off, e->d_pool, e->d_desc, e->d_wpool,
+                        e->d_count_sums, e->d_count_in_tile, e->d_count_tile, e->d_bytes_sums, e->d_bytes_in_tile, e->d_bytes_tile};
+        for (void* b : bufs) pde::scratch_free(b, nullptr);
     }
+    if (e->used_event) cudaEventDestroy((cudaEvent_t)e->used_event);
     delete e;
 }
 

@@ -704,15 +704,16 @@ static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long 
     const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0) { if (total_host) *total_host = 0; return PDE_OK; }
     if (count_cached(e, p)) { if (total_host) *total_host = e->count_total; return PDE_OK; }
-    cudaFree(e->d_count_sums); cudaFree(e->d_count_in_tile); cudaFree(e->d_count_tile);
+    scratch_free(e->d_count_sums, st); scratch_free(e->d_count_in_tile, st); scratch_free(e->d_count_tile, st);
     e->d_count_sums = nullptr; e->d_count_in_tile = nullptr; e->d_count_tile = nullptr;
     e->count_bytes_L = 0;                  // the CSR byte counts belong to the same (depth, prune, depth_begin)
     const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
-    PDE_CUDA(cudaMalloc(&e->d_count_sums, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&e->d_count_in_tile, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&e->d_count_tile, sizeof(unsigned long long) * (ntiles + 1)));
+    int rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_count_sums), sizeof(unsigned) * nblocks, st))) return rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_count_in_tile), sizeof(unsigned) * nblocks, st))) return rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_count_tile), sizeof(unsigned long long) * (ntiles + 1), st))) return rc;
     long long* d_total = nullptr;
-    int rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
+    rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
     if (rc) return rc;
     enum_count_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, e->d_count_sums);
     scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(e->d_count_sums, e->d_count_in_tile, e->d_count_tile, (int)nblocks);
@@ -736,14 +737,15 @@ static int run_count(pde_exprset* e, const EnumParams& p, cudaStream_t st, long 
 static int run_count_bytes(pde_exprset* e, const EnumParams& p, int L, cudaStream_t st) {
     const long long nblocks = p.seg_block[p.depth];
     if (nblocks == 0 || (e->count_bytes_L == L && e->d_bytes_sums)) return PDE_OK;
-    cudaFree(e->d_bytes_sums); cudaFree(e->d_bytes_in_tile); cudaFree(e->d_bytes_tile);
+    scratch_free(e->d_bytes_sums, st); scratch_free(e->d_bytes_in_tile, st); scratch_free(e->d_bytes_tile, st);
     e->d_bytes_sums = nullptr; e->d_bytes_in_tile = nullptr; e->d_bytes_tile = nullptr;
     const int ntiles = (int)((nblocks + kScanTile - 1) / kScanTile);
-    PDE_CUDA(cudaMalloc(&e->d_bytes_sums, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&e->d_bytes_in_tile, sizeof(unsigned) * nblocks));
-    PDE_CUDA(cudaMalloc(&e->d_bytes_tile, sizeof(unsigned long long) * (ntiles + 1)));
+    int rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_bytes_sums), sizeof(unsigned) * nblocks, st))) return rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_bytes_in_tile), sizeof(unsigned) * nblocks, st))) return rc;
+    if ((rc = scratch_alloc(reinterpret_cast<void**>(&e->d_bytes_tile), sizeof(unsigned long long) * (ntiles + 1), st))) return rc;
     long long* d_total = nullptr;
-    int rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
+    rc = scratch_alloc(reinterpret_cast<void**>(&d_total), sizeof(long long), st);
     if (rc) return rc;
     enum_count_bytes_kernel<<<(unsigned)nblocks, kEnumThreads, 0, st>>>(p, L, e->d_bytes_sums);
     scan_tiles_kernel<<<ntiles, kScanTile, 0, st>>>(e->d_bytes_sums, e->d_bytes_in_tile, e->d_bytes_tile, (int)nblocks);
@@ -823,6 +825,7 @@ int pde_enumerate(const pde_exprset* e, const int32_t* depth_begin, int depth, i
                                                                     reinterpret_cast<unsigned long long*>(hash));
     count_launch();
     PDE_CUDA(cudaGetLastError());
+    exprset_mark_use(e, st);
     return PDE_OK;
 }
 
@@ -879,6 +882,7 @@ int pde_enumerate_csr(const pde_exprset* e, const int32_t* depth_begin, int dept
     enum_emit_csr_kernel<<<(unsigned)(b1 - b0), kEnumThreads, smem, st>>>(p, c);
     count_launch();
     PDE_CUDA(cudaGetLastError());
+    exprset_mark_use(e, st);
     return PDE_OK;
 }
 

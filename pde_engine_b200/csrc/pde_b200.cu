@@ -63,6 +63,16 @@ void scratch_free(void* ptr, void* stream) {
     if (ptr) cudaFreeAsync(ptr, (cudaStream_t)stream);
 }
 
+void exprset_mark_use(const pde_exprset* e, void* stream) {
+    pde_exprset* em = const_cast<pde_exprset*>(e);
+    if (!em->used_event) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+        em->used_event = ev;
+    }
+    cudaEventRecord((cudaEvent_t)em->used_event, (cudaStream_t)stream);
+}
+
 bool have_device() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return false; }

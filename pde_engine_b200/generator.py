@@ -99,7 +99,7 @@ class GpuExpressionGenerator:
         dev = core.enumerate_candidates_csr(exprs, depth_begin, depth, prune, 0, n, self.L)
         first, n_unique = core.dedup_csr(dev["pool"], dev["off"], dev["len"], dev["hash"])
         out = {
-            "n": n, "n_unique_programs": n_unique, "strings": all_strs,
+            "n": n, "n_unique_programs": n_unique, "strings": all_strs, "depth_begin": depth_begin,
             "triple": dev["triple"].cpu().numpy(), "first": first.cpu().numpy().astype(bool),
             "n_uncompiled": int((dev["len"] == 0).sum().item()),
         }
@@ -124,18 +124,14 @@ class GpuExpressionGenerator:
             n, triple, first, strs = enum["n"], enum["triple"], enum["first"], enum["strings"]
             n_filtered = 0
             if filt is not None and n > 0:
-                # stage 1 -> stage 2 on the device: the spliced programs are validated where they were written
+                # stage 1 -> stage 2 on the device: the spliced programs are validated where they were written; under
+                # torch.distributed every rank takes a window of the index space (GpuBatchValidator.filter_enumerated)
                 dev = enum.pop("device")
-                enum.pop("device_first", None)
-                out = core.validate(self.session, filt.program, dev["pool"], dev["len"], filt.pts, filt.table, None,
-                                    tau=filt.tau, min_finite=filt.min_finite, vote_frac=filt.vote_frac, t0=filt.t0, confirm_points=filt.confirm_points, n_ref=0,
-                                    spill_slots=filt.spill_slots, row_off=dev["off"], L=self.L)
-                bits = out["survivor_bits"].cpu().numpy().view(np.uint32)
-                k = np.arange(n)
-                surv = ((bits[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool)
+                surv = filt.filter_enumerated(strs, enum["depth_begin"], depth, prune, self.L, cand=dev,
+                                              first_flags=enum.pop("device_first"), session=self.session)
                 n_filtered = int((first & ~surv).sum())
                 first = first & surv
-                del dev, out
+                del dev
             print(f"Depth {depth}: {n} candidates to normalize")
             unique_expressions: List[str] = []
             n_normalized = 0

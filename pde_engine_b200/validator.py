@@ -183,9 +183,15 @@ class GpuBatchValidator:
         if d is None or d[2] == 0:
             return 0
         served = 0
-        while self._sharded_prefilter(None, d) is not False:
+        while True:
+            h = self._recv_header(d)
+            if h[0] == 0:
+                return served
+            if h[0] == 2:
+                self._sharded_filter_enumerated(None, None, None, None, None, None, d, h)
+            else:
+                self._sharded_prefilter(None, d, h)
             served += 1
-        return served
 
     def shutdown(self) -> None:
         """Rank 0: release the workers from `serve()`."""
@@ -195,6 +201,14 @@ class GpuBatchValidator:
             dist, grp, rank, world = d
             hdr = torch.zeros(world + 3, dtype=torch.int64, device=self._comm_device(dist, grp))
             dist.broadcast(hdr, src=0, group=grp)
+
+    def _recv_header(self, d) -> List[int]:
+        """Worker side of the header broadcast: [cmd, ...] (cmd 0 stop, 1 prefilter shards, 2 filter enumerated windows)."""
+        import torch
+        dist, grp, rank, world = d
+        hdr = torch.zeros(world + 3, dtype=torch.int64, device=self._comm_device(dist, grp))
+        dist.broadcast(hdr, src=0, group=grp)
+        return [int(x) for x in hdr.cpu().tolist()]
 
     def _comm_device(self, dist, grp):
         import torch
@@ -236,28 +250,24 @@ class GpuBatchValidator:
         b.append(n)
         return b
 
-    def _sharded_prefilter(self, strs: Optional[List[str]], d):
+    def _sharded_prefilter(self, strs: Optional[List[str]], d, h: Optional[List[int]] = None):
         """One sharded batch.  Rank 0 passes the strings; workers pass None.  Protocol: a broadcast header
         [cmd, n, shard boundaries]; then rank 0 packs shard after shard into a byte blob (NUL-terminated strings, the
         compiler's own input format -- pickling the 143 461 depth-4 strings cost 44 + 25 ms, more than compiling and
         validating them) and SENDS each one as soon as it is packed, so the workers compile while rank 0 is still packing;
         rank 0 does its own shard last; the shard sizes make all ranks finish together (`_shard_bounds`).  The verdict
         columns come back in one gather.
-        Returns the BatchVerdict (rank 0), None (worker), False (worker: stop)."""
+        Returns the BatchVerdict (rank 0) or None (worker; `h` is the header `serve()` already received)."""
         import time
         import torch
         dist, grp, rank, world = d
         prof = os.environ.get("PDE_B200_PROFILE") is not None
         tm = [time.perf_counter()]
         cdev = self._comm_device(dist, grp)
-        hdr = torch.zeros(world + 3, dtype=torch.int64, device=cdev)
         if rank == 0:
             n = len(strs)
-            hdr = torch.tensor([1, n] + self._shard_bounds(n, world), dtype=torch.int64).to(cdev)
-        dist.broadcast(hdr, src=0, group=grp)
-        h = hdr.cpu().tolist()
-        if h[0] == 0:
-            return False
+            h = [1, n] + self._shard_bounds(n, world)
+            dist.broadcast(torch.tensor(h, dtype=torch.int64).to(cdev), src=0, group=grp)
         n, bounds = int(h[1]), [int(x) for x in h[2:]]
         first, count = bounds[rank], bounds[rank + 1] - bounds[rank]
         threads = max(1, (os.cpu_count() or 1) // world)
@@ -446,6 +456,162 @@ class GpuBatchValidator:
         self.stats["gpu_rejected"] += int(bv.rejected.sum())
         self.stats["not_compilable"] += n_uncompiled
         return bv
+
+    # ---- stage 1 -> stage 2 on the device: the raw candidates of a depth never leave the GPU --------------------
+    def filter_enumerated(self, strs: Sequence[str], depth_begin: Sequence[int], depth: int, prune: bool = True,
+                          L: int = 128, cand: Optional[dict] = None, first_flags=None, session=None) -> np.ndarray:
+        """Survivor flags (bool [n]) of ALL raw depth-`depth` candidates built from `strs` (E[1] .. E[depth-1] back to
+        back, `depth_begin` their boundaries; LBF:128-200 order).  Nothing but the operand strings crosses the host:
+        the candidates are enumerated into CSR rows on the device and validated where they were written.
+
+        Under torch.distributed every rank enumerates the candidates itself (stage 1 is a pure function of the index
+        and costs a fraction of a millisecond; no candidate travels), finds the exact duplicates, and validates its own
+        window of the index space -- windows of equal COST (first occurrences weighted by program length), computed
+        identically on every rank; the ONLY exchange is the gather of the survivor words.  Ranks > 0 sit in `serve()`.  `cand` / `first_flags`: rank 0's full
+        enumeration and its first-occurrence flags when the caller already has them (the generator needs them for the
+        triples) together with the `session` they were compiled in (constants are interned per session); exact
+        duplicates are not evaluated (their rows get length 0 = "survives", and the caller drops them by `first_flags`
+        anyway)."""
+        strs = list(strs)
+        if cand is not None and session is None:
+            raise ValueError("filter_enumerated: `cand` needs the session its operands were compiled in")
+        d = self._dist()
+        if d is not None and d[2] != 0:
+            raise RuntimeError("GpuBatchValidator.filter_enumerated is driven from rank 0; ranks > 0 call serve()")
+        if d is None:
+            if cand is None:
+                exprs = self.session.compile(strs)
+                n = core.enumerate_count(exprs, depth_begin, depth, prune)
+            else:
+                exprs, n = None, int(cand["len"].shape[0])
+            bits = self._enum_filter_local(exprs, depth_begin, depth, prune, L, 0, n, cand, first_flags, session)
+            words = bits.cpu().numpy().view(np.uint32)
+        else:
+            words = self._sharded_filter_enumerated(strs, depth_begin, depth, prune, L, (cand, first_flags, session), d, None)
+            n = self._last_enum_n
+        return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n].astype(bool)
+
+    def _enum_filter_local(self, exprs, depth_begin, depth: int, prune: bool, L: int, first: int, count: int,
+                           cand: Optional[dict] = None, first_flags=None, session=None):
+        """This device's window [first, first + count): survivor words (int32 tensor, (count + 31) // 32)."""
+        import torch
+        if count == 0:
+            return torch.zeros(0, dtype=torch.int32, device=self.device)
+        prof = os.environ.get("PDE_B200_PROFILE") is not None
+        if prof:
+            import time
+            torch.cuda.synchronize()
+            t_a = time.perf_counter()
+        if cand is None:
+            cand = core.enumerate_candidates_csr(exprs, depth_begin, depth, prune, first, count, L, device=self.device)
+            off, ln, hs = cand["off"], cand["len"], cand["hash"]
+            if first_flags is None:
+                first_flags, _ = core.dedup_csr(cand["pool"], off, ln, hs)
+        else:                   # rows [first, first + count) of a full enumeration (offsets are absolute into the pool)
+            off, ln = cand["off"][first:first + count + 1], cand["len"][first:first + count]
+            if first_flags is None:
+                first_flags, _ = core.dedup_csr(cand["pool"], cand["off"], cand["len"], cand["hash"])
+            first_flags = first_flags[first:first + count]
+        ln = torch.where(first_flags.bool(), ln, torch.zeros_like(ln))
+        if prof:
+            torch.cuda.synchronize()
+            t_b = time.perf_counter()
+        out = core.validate(session or self.session, self.program, cand["pool"], ln, self.pts, self.table, None,
+                            tau=self.tau, min_finite=self.min_finite, vote_frac=self.vote_frac, t0=self.t0,
+                            confirm_points=self.confirm_points, n_ref=0, spill_slots=self.spill_slots, row_off=off, L=L)
+        self.stats["gpu_evaluated"] += int(count)
+        if prof:
+            torch.cuda.synchronize()
+            print(f"[enum_filter_local] window [{first}, {first + count}): enumerate+dedup {1e3 * (t_b - t_a):.2f} ms, "
+                  f"validate {1e3 * (time.perf_counter() - t_b):.2f} ms", file=sys.stderr, flush=True)
+        return out["survivor_bits"]
+
+    def _enumerate_all(self, exprs, depth_begin, depth: int, prune: bool, L: int):
+        """All candidates of the depth as CSR rows on this device + their first-occurrence flags."""
+        cand = core.enumerate_candidates_csr(exprs, depth_begin, depth, prune, 0, None, L, device=self.device)
+        first_flags, _ = core.dedup_csr(cand["pool"], cand["off"], cand["len"], cand["hash"])
+        return cand, first_flags
+
+    @staticmethod
+    def _cost_bounds(ln, first_flags, world: int) -> List[int]:
+        """Window boundaries [0, ..., n] of `world` windows of equal cost, 32-aligned (survivor words never straddle two
+        windows), candidate order preserved.  Cost of a candidate: its program length + 8 if it is a first occurrence,
+        else 1 (duplicates are not evaluated).  Integer arithmetic on identical inputs: every rank gets the same bounds."""
+        import torch
+        n = int(ln.shape[0])
+        if world <= 1 or n == 0:
+            return [0, n]
+        cost = torch.where(first_flags.bool(), ln.to(torch.int64) + 8, torch.ones((), dtype=torch.int64, device=ln.device))
+        cs = torch.cumsum(cost, 0)
+        targets = (cs[-1] * torch.arange(1, world, dtype=torch.int64, device=ln.device)) // world
+        idx = torch.searchsorted(cs, targets).cpu().tolist()
+        b = [0]
+        for i in idx:
+            b.append(max(b[-1], min(n, (int(i) + 16) // 32 * 32)))
+        b.append(n)
+        return b
+
+    def _sharded_filter_enumerated(self, strs, depth_begin, depth, prune, L, mine, d, h: Optional[List[int]]):
+        """One sharded last-depth filter.  Protocol: header [2, payload bytes, strings, depth | prune << 8 | L << 16],
+        then ONE broadcast payload (depth_begin as int64, then the NUL-terminated operand strings: 3 786 strings =
+        0.1 MB at depth 4); every rank compiles the operands itself (a millisecond), enumerates + dedups (another one),
+        takes its `_cost_bounds` window and answers with its survivor words in one gather.  Rank 0 returns the
+        concatenated words."""
+        import torch
+        import time
+        dist, grp, rank, world = d
+        cdev = self._comm_device(dist, grp)
+        prof = os.environ.get("PDE_B200_PROFILE") is not None
+        tm = [time.perf_counter()]
+        if rank == 0:
+            blob, n_str = core.pack_strings(strs)
+            head = np.asarray(list(depth_begin), dtype=np.int64).view(np.uint8)
+            assert len(depth_begin) == depth
+            payload = torch.from_numpy(np.concatenate([head, np.frombuffer(blob, dtype=np.uint8)])).to(cdev)
+            h = [2, payload.numel(), n_str, int(depth) | (int(bool(prune)) << 8) | (int(L) << 16)] + [0] * (world - 1)
+            dist.broadcast(torch.tensor(h, dtype=torch.int64).to(cdev), src=0, group=grp)
+        else:
+            payload = torch.empty(h[1], dtype=torch.uint8, device=cdev)
+        dist.broadcast(payload, src=0, group=grp)
+        tm.append(time.perf_counter())
+        n_str, depth, prune, L = h[2], h[3] & 0xff, bool((h[3] >> 8) & 1), h[3] >> 16
+        cand, first_flags, session = (None, None, None)
+        if rank == 0:
+            cand, first_flags, session = mine
+        else:
+            raw = payload.cpu().numpy()
+            depth_begin = [int(x) for x in raw[:8 * depth].view(np.int64)]
+            blob = raw[8 * depth:].tobytes()
+        os.environ["PDE_B200_COMPILE_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        if cand is None:
+            session = self.session
+            cand, first_flags = self._enumerate_all(session.compile_blob(blob, n_str), depth_begin, depth, prune, L)
+        elif first_flags is None:
+            first_flags, _ = core.dedup_csr(cand["pool"], cand["off"], cand["len"], cand["hash"])
+        n = int(cand["len"].shape[0])
+        bounds = self._cost_bounds(cand["len"], first_flags, world)
+        first, count = bounds[rank], bounds[rank + 1] - bounds[rank]
+        tm.append(time.perf_counter())
+        bits = self._enum_filter_local(None, depth_begin, depth, prune, L, first, count, cand, first_flags, session)
+        if prof:
+            torch.cuda.synchronize()
+        tm.append(time.perf_counter())
+        wmax = max((b1 - b0 + 31) // 32 for b0, b1 in zip(bounds[:-1], bounds[1:]))
+        pad = torch.zeros(wmax, dtype=torch.int32, device=cdev)
+        pad[:bits.numel()] = bits.to(cdev)
+        big = torch.empty((world, wmax), dtype=torch.int32, device=cdev) if rank == 0 else None
+        dist.gather(pad, [big[r] for r in range(world)] if rank == 0 else None, dst=0, group=grp)
+        if prof:
+            if rank == 0:
+                big.cpu()
+            tm.append(time.perf_counter())
+            print(f"[sharded_filter_enumerated rank {rank}] header+payload {1e3 * (tm[1] - tm[0]):.2f} ms, compile+enumerate+dedup+bounds {1e3 * (tm[2] - tm[1]):.2f}, "
+                  f"validate [{first}, {first + count}) {1e3 * (tm[3] - tm[2]):.2f}, gather {1e3 * (tm[4] - tm[3]):.2f}", file=sys.stderr, flush=True)
+        if rank != 0:
+            return None
+        host = big.cpu().numpy().view(np.uint32)
+        self._last_enum_n = n
+        return np.concatenate([host[r, :(bounds[r + 1] - bounds[r] + 31) // 32] for r in range(world)])
 
     def prefetch(self, depth: int, expr_strs: Sequence[str]) -> None:
         """pre_batch_hook for GpuExpressionGenerator: filter a whole on_batch chunk at

@@ -156,3 +156,71 @@ def test_sharded_prefilter_protocol_gloo_world2():
         p.join(60)
         assert p.exitcode == 0
     assert ok == (True, True, True)
+
+
+def _enum_worker(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pde_engine_b200 import core
+    from pde_engine_b200.validator import GpuBatchValidator
+    strs = [f"rho**{k} + z" for k in range(1, 41)]
+    depth_begin = [0, 5, 40]
+    n_total = 70001
+
+    rng = np.random.default_rng(7)
+    len_all = torch.from_numpy(rng.integers(1, 60, size=n_total).astype(np.uint8))
+    first_all = torch.from_numpy((rng.random(n_total) < 0.8).astype(np.uint8))
+    first_all[n_total // 2:] &= torch.from_numpy((rng.random(n_total - n_total // 2) < 0.5).astype(np.uint8))   # a cheaper second half
+
+    def fake_all(self, exprs, db, depth, prune, L):
+        assert list(db) == depth_begin and depth == 3 and prune is True and L == 96
+        assert exprs.n == len(strs)                  # the worker compiled the broadcast operand strings itself
+        return {"len": len_all, "pool": None, "off": None, "hash": None}, first_all
+
+    windows = []
+
+    def fake_local(self, exprs, db, depth, prune, L, first, count, cand=None, first_flags=None, session=None):
+        assert L == 96 and first % 32 == 0 and cand is not None
+        windows.append((first, count))
+        k = np.arange(first, first + count, dtype=np.int64)
+        surv = ((k * 2654435761) >> 7) & 1
+        pad = np.zeros((count + 31) // 32 * 32, np.uint8)
+        pad[:count] = surv
+        return torch.from_numpy(np.packbits(pad, bitorder="little").view(np.int32).copy())
+
+    GpuBatchValidator._enumerate_all = fake_all
+    GpuBatchValidator._enum_filter_local = fake_local
+    gv = object.__new__(GpuBatchValidator)          # the protocol only: no device behind it
+    gv.group, gv.device = "auto", torch.device("cpu")
+    gv.session = core.Session.for_problem("force_free")
+    if rank == 0:
+        got = gv.filter_enumerated(strs, depth_begin, 3, True, 96)
+        gv.shutdown()
+        k = np.arange(n_total, dtype=np.int64)
+        # the cost-balanced cut lies before the middle (the second half is cheaper: rank 1 takes more candidates), 32-aligned
+        (lo, cnt), = windows
+        q.put(bool(np.array_equal(got, (((k * 2654435761) >> 7) & 1).astype(bool))) and lo == 0 and cnt % 32 == 0 and cnt < n_total // 2 - 1000)
+    else:
+        assert gv.serve() == 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_filter_enumerated_protocol_gloo_world2():
+    """GpuBatchValidator.filter_enumerated under torch.distributed: the operand strings and depth boundaries are
+    broadcast, each rank answers for its own window of the candidate index space, rank 0 gets the flags of all n."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_enum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok is True

@@ -80,6 +80,42 @@ def test_validate_on_csr_rows(cuda_device, enum_ff):
         np.testing.assert_array_equal(a[k].cpu().numpy().view(np.int64), b[k].cpu().numpy().view(np.int64))
 
 
+def test_filter_enumerated_equals_string_prefilter(cuda_device, enum_ff):
+    """GpuBatchValidator.filter_enumerated (stage 1 -> stage 2 without leaving the device) gives every first-occurrence
+    candidate the verdict `prefilter` gives the same candidate as a string; windows of the index space (what a rank of
+    a sharded run evaluates) concatenate to the whole."""
+    import torch
+    import pde_engine_b200 as pb
+    from pde_engine_b200.generator import candidate_string
+    from pde_engine_b200.validator import GpuBatchValidator
+    flat, db = _sets(enum_ff, 3)
+    gv = GpuBatchValidator(None, problem="force_free", P=512, L=128, spill_slots=3, group=None)
+    surv = gv.filter_enumerated(flat, db, 3, True, 128)
+    es = gv.session.compile(flat)
+    n = pb.enumerate_count(es, db, 3, True)
+    assert surv.shape == (n,)
+    csr = pb.enumerate_candidates_csr(es, db, 3, True, 0, n, 128)
+    first, _ = pb.dedup_csr(csr["pool"], csr["off"], csr["len"], csr["hash"])
+    first = first.cpu().numpy().astype(bool)
+    tri = csr["triple"].cpu().numpy()
+    strs = [candidate_string(int(o), flat[a], flat[b] if b >= 0 else None) for o, a, b in tri]
+    bv = gv.prefilter(strs)
+    done = first & (csr["len"].cpu().numpy() != 0)   # (rows the device could not splice survive for the CPU path)
+    np.testing.assert_array_equal(surv[done], bv.survivor[done])
+    assert surv[~first].all()                        # exact duplicates are not evaluated: length 0 = "survives"
+    assert 0 < int((~surv).sum()) < n
+    # the caller's own enumeration + flags (the generator's case) and windows of it
+    again = gv.filter_enumerated(flat, db, 3, True, 128, cand=csr, first_flags=torch.from_numpy(first.astype(np.uint8)).to(cuda_device),
+                                 session=gv.session)
+    np.testing.assert_array_equal(again, surv)
+    words = []
+    for lo, cnt in ((0, 2048), (2048, 1024), (3072, n - 3072)):
+        words.append(gv._enum_filter_local(es, db, 3, True, 128, lo, cnt).cpu().numpy().view(np.uint32))
+    w = np.concatenate(words)
+    k = np.arange(n)
+    np.testing.assert_array_equal(((w[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool) | ~first, surv | ~first)
+
+
 def test_csr_depth5_full_size(cuda_device, enum_ff):
     """BASELINE depth-5 enumeration (11 778 899 candidates) in CSR form: same hashes and lengths as the padded pass,
     pool = sum of the padded lengths, and the window of one rank of eight equals its slice."""

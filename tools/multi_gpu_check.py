@@ -69,4 +69,34 @@ if rank == 0:
     print(f"multi-GPU parity ok: {world} ranks, {n} depth-4 candidates, {int(surv.sum())} survivors, "
           f"{len(idx)} distinct surviving programs; sharded == single-GPU bit for bit", flush=True)
 dist.barrier()
+
+# the same through the public API: GpuBatchValidator.filter_enumerated driven from rank 0, ranks > 0 in serve()
+import time
+from pde_engine_b200.validator import GpuBatchValidator
+gv = GpuBatchValidator(None, "force_free", P=4096, device=dev)
+if rank == 0:
+    try:
+        for _ in range(2):
+            got = gv.filter_enumerated(flat, db, 4, True, 128)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            got = gv.filter_enumerated(flat, db, 4, True, 128)
+            ts.append(1e3 * (time.perf_counter() - t0))
+    finally:
+        gv.shutdown()
+    alone = GpuBatchValidator(None, "force_free", P=4096, device=dev, group=None)
+    want = alone.filter_enumerated(flat, db, 4, True, 128)
+    t0 = time.perf_counter()
+    want = alone.filter_enumerated(flat, db, 4, True, 128)
+    t1 = 1e3 * (time.perf_counter() - t0)
+    es2 = alone.session.compile(flat)
+    c2 = pb.enumerate_candidates_csr(es2, db, 4, True, 0, n, 128, device=dev)
+    f2 = pb.dedup_csr(c2["pool"], c2["off"], c2["len"], c2["hash"])[0].cpu().numpy().astype(bool)
+    assert np.array_equal(got, want), int((got != want).sum())      # (every rank dedups the whole depth: same rows evaluated)
+    print(f"filter_enumerated: {world} ranks == 1 rank on all {n} candidates ({int(f2.sum())} first occurrences evaluated); "
+          f"wall {sorted(ts)[len(ts) // 2]:.2f} ms on {world} GPUs (runs {[round(x, 2) for x in ts]}) vs {t1:.2f} ms on one", flush=True)
+else:
+    gv.serve()
+dist.barrier()
 dist.destroy_process_group()
