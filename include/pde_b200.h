@@ -124,6 +124,9 @@ int  pde_compile_exprs(pde_session *s, const char *const *strs, int n, pde_exprs
  * thread count.  offsets may be NULL: the blob is then n NUL-terminated strings back to back and
  * the library finds the terminators itself. */
 int  pde_compile_exprs_packed(pde_session *s, const char *blob, const uint32_t *offsets, int n, pde_exprset **out);
+/* Frees the handle.  Its device mirrors (made by the first pde_enumerate* call, from the library's stream-ordered
+ * pool) go back to the pool after the last enumerate kernel that read them has finished: no device-wide
+ * synchronisation, safe to call while that work is still queued. */
 void pde_exprset_free(pde_exprset *e);
 int  pde_exprset_size(const pde_exprset *e, int *n_expr, int *n_terms, int *n_pool_bytes);
 /* host copies of the compiled form:

@@ -703,10 +703,14 @@ void pde_exprset_free(pde_exprset* e) {
     if (e->device >= 0) {
         // stream-ordered: the legacy stream waits for the last kernel that read the mirrors, then the buffers go back to
         // the library's pool (no device-wide synchronisation, unlike cudaFree)
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != e->device) cudaSetDevice(e->device);          // the pool and the legacy stream of the mirrors' device
         if (e->used_event) cudaStreamWaitEvent(nullptr, (cudaEvent_t)e->used_event, 0);
         void* bufs[] = {e->d_flags, e->d_attrs, e->d_rank, e->d_term_begin, e->d_term_sign, e->d_term_off, e->d_pool, e->d_desc, e->d_wpool,
                         e->d_count_sums, e->d_count_in_tile, e->d_count_tile, e->d_bytes_sums, e->d_bytes_in_tile, e->d_bytes_tile};
         for (void* b : bufs) pde::scratch_free(b, nullptr);
+        if (cur >= 0 && cur != e->device) cudaSetDevice(cur);
     }
     if (e->used_event) cudaEventDestroy((cudaEvent_t)e->used_event);
     delete e;

@@ -582,7 +582,8 @@ class GpuBatchValidator:
             raw = payload.cpu().numpy()
             depth_begin = [int(x) for x in raw[:8 * depth].view(np.int64)]
             blob = raw[8 * depth:].tobytes()
-        os.environ["PDE_B200_COMPILE_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        # (a few thousand operand strings: a sub-millisecond burst, so not less than 4 threads even when the ranks share the cores)
+        os.environ["PDE_B200_COMPILE_THREADS"] = str(max(min(4, os.cpu_count() or 1), (os.cpu_count() or 1) // world))
         if cand is None:
             session = self.session
             cand, first_flags = self._enumerate_all(session.compile_blob(blob, n_str), depth_begin, depth, prune, L)
