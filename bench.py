@@ -452,9 +452,9 @@ def run_ours(args):
                           "note": "GpuBatchValidator.filter_enumerated from rank 0 (ranks > 0 in serve()): operand strings broadcast (0.1 MB), every rank compiles them, enumerates its shard_range window in CSR form (pde_enumerate_csr), drops exact duplicates inside the window (pde_dedup_csr) and validates the rest (pde_validate_csr); one gather of survivor words.  Host wall clock on rank 0 around the call, median of 5"}
         else:
             gv5.serve()
-        barrier()
     except Exception as e:
         depth4_dev = {"error": repr(e)[:200]}
+    barrier()
 
     # ---- BASELINE configs[3]: kerr_magnetosphere depth 3 (order-2 jets, 16 174 uniques), same span A ----
     kerr3 = None
