@@ -590,16 +590,32 @@ void exprset_ensure_rank(pde_exprset* e) {
     const int n = e->n;
     e->rank.assign(n, 0);
     const char* blob = e->str_blob.data();
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        int c = strcmp(blob + e->str_off[a], blob + e->str_off[b]);
-        return c < 0 || (c == 0 && a < b);
+    // sort by the first 8 bytes as one big-endian integer; strcmp only on ties, from byte 8 on (a key with a NUL byte in
+    // it is a whole string): 3-4x faster than strcmp for every comparison, and this sort is on the critical path of the
+    // first enumerate call of every handle
+    struct Key { uint64_t k; int i; };
+    std::vector<Key> order(n);
+    for (int i = 0; i < n; ++i) {
+        const unsigned char* s = reinterpret_cast<const unsigned char*>(blob + e->str_off[i]);
+        uint64_t k = 0;
+        int j = 0;
+        for (; j < 8 && s[j]; ++j) k = (k << 8) | s[j];
+        k <<= 8 * (8 - j);
+        order[i] = Key{k, i};
+    }
+    auto tail_cmp = [&](const Key& a, const Key& b) {
+        if ((a.k & 0xffULL) == 0) return 0;                       // shorter than 8 bytes: the key is the string
+        return strcmp(blob + e->str_off[a.i] + 8, blob + e->str_off[b.i] + 8);
+    };
+    std::sort(order.begin(), order.end(), [&](const Key& a, const Key& b) {
+        if (a.k != b.k) return a.k < b.k;
+        const int c = tail_cmp(a, b);
+        return c < 0 || (c == 0 && a.i < b.i);
     });
     uint32_t r = 0;
     for (int k = 0; k < n; ++k) {
-        if (k > 0 && strcmp(blob + e->str_off[order[k]], blob + e->str_off[order[k - 1]]) != 0) ++r;
-        e->rank[order[k]] = r;
+        if (k > 0 && (order[k].k != order[k - 1].k || tail_cmp(order[k], order[k - 1]) != 0)) ++r;
+        e->rank[order[k].i] = r;
     }
     e->rank_ready = true;
 }
@@ -609,7 +625,11 @@ void exprset_ensure_rank(pde_exprset* e) {
 int exprset_ensure_device(pde_exprset* e) {
     if (e->device >= 0) return PDE_OK;
     if (!have_device()) { set_error("exprset has no device mirror: no CUDA device"); return PDE_E_NODEVICE; }
+    const bool prof = getenv("PDE_B200_PROFILE") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_a = tnow();
     exprset_ensure_rank(e);
+    auto t_b = tnow();
     // splice descriptors + whole programs (enumerate.cu): whole(i) = t1 [NEG] (tk ADD|SUB)*
     {
         e->desc.assign((size_t)e->n * 2, 0);
@@ -638,6 +658,7 @@ int exprset_ensure_device(pde_exprset* e) {
         }
         e->wpool.resize(e->wpool.size() + 8, 0);                 // the word-wise reader looks one word ahead
     }
+    auto t_c = tnow();
     int dev = 0;
     cudaGetDevice(&dev);
     int rc;
@@ -650,6 +671,10 @@ int exprset_ensure_device(pde_exprset* e) {
     if ((rc = upload(&e->d_term_sign, e->term_sign))) return rc;
     if ((rc = upload(&e->d_term_off, e->term_off))) return rc;
     if ((rc = upload(&e->d_pool, e->pool))) return rc;
+    if (prof) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[exprset_ensure_device] n=%d rank %.2f ms, descriptors %.2f ms, uploads %.2f ms\n", e->n, ms(t_a, t_b), ms(t_b, t_c), ms(t_c, tnow()));
+    }
     e->device = dev;
     return PDE_OK;
 }

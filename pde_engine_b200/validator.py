@@ -586,7 +586,13 @@ class GpuBatchValidator:
         os.environ["PDE_B200_COMPILE_THREADS"] = str(max(min(4, os.cpu_count() or 1), (os.cpu_count() or 1) // world))
         if cand is None:
             session = self.session
-            cand, first_flags = self._enumerate_all(session.compile_blob(blob, n_str), depth_begin, depth, prune, L)
+            exprs = session.compile_blob(blob, n_str)
+            if prof:
+                t_c = time.perf_counter()
+            cand, first_flags = self._enumerate_all(exprs, depth_begin, depth, prune, L)
+            if prof:
+                torch.cuda.synchronize()
+                print(f"[sharded_filter_enumerated rank {rank}] compile {1e3 * (t_c - tm[-1]):.2f} ms, enumerate+dedup {1e3 * (time.perf_counter() - t_c):.2f}", file=sys.stderr, flush=True)
         elif first_flags is None:
             first_flags, _ = core.dedup_csr(cand["pool"], cand["off"], cand["len"], cand["hash"])
         n = int(cand["len"].shape[0])

@@ -80,7 +80,8 @@ def test_validate_on_csr_rows(cuda_device, enum_ff):
         np.testing.assert_array_equal(a[k].cpu().numpy().view(np.int64), b[k].cpu().numpy().view(np.int64))
 
 
-def test_filter_enumerated_equals_string_prefilter(cuda_device, enum_ff):
+@pytest.mark.parametrize("problem", ["force_free", "kerr_magnetosphere"])
+def test_filter_enumerated_equals_string_prefilter(problem, cuda_device, enum_ff, enum_kerr):
     """GpuBatchValidator.filter_enumerated (stage 1 -> stage 2 without leaving the device) gives every first-occurrence
     candidate the verdict `prefilter` gives the same candidate as a string; windows of the index space (what a rank of
     a sharded run evaluates) concatenate to the whole."""
@@ -88,8 +89,8 @@ def test_filter_enumerated_equals_string_prefilter(cuda_device, enum_ff):
     import pde_engine_b200 as pb
     from pde_engine_b200.generator import candidate_string
     from pde_engine_b200.validator import GpuBatchValidator
-    flat, db = _sets(enum_ff, 3)
-    gv = GpuBatchValidator(None, problem="force_free", P=512, L=128, spill_slots=3, group=None)
+    flat, db = _sets(enum_ff if problem == "force_free" else enum_kerr, 3)
+    gv = GpuBatchValidator(None, problem=problem, P=512, L=128, spill_slots=3, group=None)
     surv = gv.filter_enumerated(flat, db, 3, True, 128)
     es = gv.session.compile(flat)
     n = pb.enumerate_count(es, db, 3, True)
