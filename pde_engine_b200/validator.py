@@ -539,7 +539,9 @@ class GpuBatchValidator:
         else 1 (duplicates are not evaluated).  Integer arithmetic on identical inputs: every rank gets the same bounds."""
         import torch
         n = int(ln.shape[0])
-        if world <= 1 or n == 0:
+        if n == 0:
+            return [0] * (max(world, 1) + 1)
+        if world <= 1:
             return [0, n]
         cost = torch.where(first_flags.bool(), ln.to(torch.int64) + 8, torch.ones((), dtype=torch.int64, device=ln.device))
         cs = torch.cumsum(cost, 0)
@@ -603,7 +605,7 @@ class GpuBatchValidator:
         if prof:
             torch.cuda.synchronize()
         tm.append(time.perf_counter())
-        wmax = max((b1 - b0 + 31) // 32 for b0, b1 in zip(bounds[:-1], bounds[1:]))
+        wmax = max(1, max((b1 - b0 + 31) // 32 for b0, b1 in zip(bounds[:-1], bounds[1:])))     # (never an empty collective)
         pad = torch.zeros(wmax, dtype=torch.int32, device=cdev)
         pad[:bits.numel()] = bits.to(cdev)
         big = torch.empty((world, wmax), dtype=torch.int32, device=cdev) if rank == 0 else None

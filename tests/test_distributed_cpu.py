@@ -224,3 +224,26 @@ def test_sharded_filter_enumerated_protocol_gloo_world2():
         p.join(60)
         assert p.exitcode == 0
     assert ok is True
+
+
+def test_cost_bounds_tile_the_index_space():
+    """Windows of the string-free last-depth filter: 32-aligned, monotone, [0 .. n], balanced by cost."""
+    from pde_engine_b200.validator import GpuBatchValidator as G
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 10, 31, 32, 33, 1000, 258285):
+        ln = torch.from_numpy(rng.integers(1, 60, size=n).astype(np.uint8))
+        first = torch.from_numpy((rng.random(n) < 0.7).astype(np.uint8))
+        for world in (1, 2, 3, 8):
+            b = G._cost_bounds(ln, first, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n
+            assert all(x <= y for x, y in zip(b[:-1], b[1:]))
+            assert all(x % 32 == 0 or x == n for x in b)
+    # balanced: the windows' costs differ by less than 2 % on a large, skewed batch
+    n = 258285
+    ln = torch.from_numpy(rng.integers(1, 60, size=n).astype(np.uint8))
+    first = torch.from_numpy((rng.random(n) < np.linspace(1.0, 0.3, n)).astype(np.uint8))
+    b = G._cost_bounds(ln, first, 8)
+    cost = np.where(first.numpy().astype(bool), ln.numpy().astype(np.int64) + 8, 1)
+    per = [int(cost[x:y].sum()) for x, y in zip(b[:-1], b[1:])]
+    assert max(per) < 1.02 * min(per), per
+    assert b[1] - b[0] < b[-1] - b[-2]           # cheaper candidates at the end: the last window is longer
