@@ -10,6 +10,7 @@ $NVCC $FLAGS --jump-table-density=${PDE_JTD:-25} ${PDE_PTXAS_V:+-Xptxas -v} -c p
 $NVCC $FLAGS --jump-table-density=${PDE_JTD:-25} ${PDE_PTXAS_V:+-Xptxas -v} -c program.cu -o program.o &
 $NVCC $FLAGS ${PDE_PTXAS_V:+-Xptxas -v} -c enumerate.cu -o enumerate.o &
 $NVCC $FLAGS -x cu -c compiler.cpp -o compiler.o &
+$NVCC $FLAGS -c order.cu -o order.o &
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT pde_b200.o program.o enumerate.o compiler.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT pde_b200.o program.o enumerate.o compiler.o order.o -lcudart
 echo "built $(realpath $OUT)"

@@ -16,6 +16,10 @@ bool have_device();
 // cudaFree around every call (8-70 ms for the 400 MB dedup table).
 int scratch_alloc(void** ptr, size_t bytes, void* stream);
 void scratch_free(void* ptr, void* stream);
+// order.cu: evaluation order of a batch for the stage-2 kernel -- candidate indices sorted by the leading program
+// bytes, so that the warp groups resident on an SM run near-identical micro-op streams (instruction-cache locality).
+// *order comes from scratch_alloc (release with scratch_free on the same stream); null when the batch is too small.
+int candidate_order(const uint8_t* code, const unsigned* row_off, const uint8_t* len, long long n, int L, int** order, void* stream);
 void exprset_mark_use(const pde_exprset* e, void* stream);     // pde_b200.cu: the handle's mirrors are in use on `stream` up to here
 
 #define PDE_CUDA(call)                                                     \

@@ -11,11 +11,14 @@
 namespace pde {
 
 // Proposed rejections of the first pass (cleared survivor bits) -> index list for the confirmation pass.
-// Order is whatever the atomics give: every output of the confirmation pass is addressed by candidate.
+// Order is whatever the atomics give (roughly the evaluation order of the first pass): every output of the confirmation
+// pass is addressed by candidate.
 static __global__ void __launch_bounds__(256)
-compact_rejects_kernel(const unsigned* __restrict__ bits, long long n, int* __restrict__ index, unsigned long long* __restrict__ count) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool rej = i < n && !((bits[i >> 5] >> (i & 31)) & 1u);
+compact_rejects_kernel(const unsigned* __restrict__ bits, long long n, const int* __restrict__ order, int* __restrict__ index,
+                       unsigned long long* __restrict__ count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (t < n && order) ? (long long)order[t] : t;          // walk the batch in its evaluation order
+    const bool rej = t < n && !((bits[i >> 5] >> (i & 31)) & 1u);
     const unsigned b = __ballot_sync(0xffffffffu, rej);
     if (!b) return;
     const int lane = threadIdx.x & 31;
@@ -109,23 +112,31 @@ static int launch_validate_cfg(const ValidateParams& vp, cudaStream_t st, bool* 
 // kernel of one residual with / without the round-off majorants.
 template <class LAUNCHER>
 static int run_two_pass(ValidateParams vp, const pde_validate_out* out, int confirm_points, cudaStream_t st) {
+    // evaluation order of the batch (common.h: candidate_order; null for small batches)
+    int* order = nullptr;
+    int rc = candidate_order(vp.code, vp.row_off, vp.len, vp.n, vp.L, &order, st);
+    if (rc) return rc;
+    vp.index = order; vp.n_index = nullptr; vp.is_confirm = 0;
     if (confirm_points == 0) {
         // one pass over the whole grid with the majorants carried
-        return LAUNCHER::template launch<true>(vp, st);
+        rc = LAUNCHER::template launch<true>(vp, st);
+        scratch_free(order, st);
+        return rc;
     }
     // pass 1: all P points, no majorants -- proposes rejections
-    int rc = LAUNCHER::template launch<false>(vp, st);
-    if (rc) return rc;
+    rc = LAUNCHER::template launch<false>(vp, st);
+    if (rc) { scratch_free(order, st); return rc; }
     // pass 2: the proposed rejections again on the first confirm_points points WITH the majorants; a rejection
     // stands only if this pass votes it too (include/pde_b200.h)
     unsigned long long* cnt = reinterpret_cast<unsigned long long*>(out->scratch);
     int* index = out->scratch + 2;
     PDE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
     if (out->confirm) PDE_CUDA(cudaMemsetAsync(out->confirm, 0xff, sizeof(int32_t) * 2 * (size_t)vp.n, st));   // -1: not re-examined
-    compact_rejects_kernel<<<(unsigned)((vp.n + 255) / 256), 256, 0, st>>>(out->survivor_bits, vp.n, index, cnt);
+    compact_rejects_kernel<<<(unsigned)((vp.n + 255) / 256), 256, 0, st>>>(out->survivor_bits, vp.n, order, index, cnt);
     count_launch();
+    scratch_free(order, st);
     PDE_CUDA(cudaGetLastError());
-    vp.index = index; vp.n_index = cnt; vp.confirm = out->confirm; vp.P_eval = confirm_points;
+    vp.index = index; vp.n_index = cnt; vp.is_confirm = 1; vp.confirm = out->confirm; vp.P_eval = confirm_points;
     return LAUNCHER::template launch<true>(vp, st);
 }
 

@@ -100,9 +100,11 @@ struct ValidateParams {
     int n_prim;           // PRIM(p) with p >= n_prim is malformed input
     int P;
     int P_eval;           // points evaluated (the first P_eval of the grid; a multiple of 128 * NP or == P)
-    // confirmation pass: candidate i of this launch is index[i], i < *n_index (both on the device)
+    // item i of this launch is candidate index[i] (null: i), i < *n_index (null: n) -- both on the device.  First pass:
+    // the evaluation order (candidate_order, common.h); confirmation pass (is_confirm): the proposed rejections
     const int* index;
     const unsigned long long* n_index;
+    int is_confirm;
     int* confirm;         // [n, 2] (n_finite, n_votes) of the confirmation pass, or null
     unsigned long long* chunk_counter;   // zeroed by the launcher: chunks are dealt dynamically (null: round-robin)
     int ns;               // spill slots per lane
@@ -1086,8 +1088,9 @@ validate_kernel(const ValidateParams p) {
     double* s_spill = reinterpret_cast<double*>(smem + per_cand * W + (size_t)W * 4 * sizeof(WarpPartial) + 16 * W) + threadIdx.x;
 
     const unsigned spill_addr = keep_in_register(smem_addr(s_spill));
-    const bool indexed = MAJ && p.index != nullptr;
-    const long long n_items = indexed ? (long long)*p.n_index : p.n;
+    const bool indexed = MAJ && p.is_confirm;              // confirmation pass: only the verdict is written
+    const bool mapped = p.index != nullptr;
+    const long long n_items = p.n_index ? (long long)*p.n_index : p.n;
     const long long n_chunks = (n_items + 3) / 4;
     // Chunks are dealt DYNAMICALLY (one atomicAdd per chunk by the group's first lane): candidates differ in cost by an
     // order of magnitude (2 to 60 micro-ops), and with a static round-robin the last groups of a small batch -- one
@@ -1105,7 +1108,7 @@ validate_kernel(const ValidateParams p) {
         // ---- phase 1: every warp of the group stages + translates its own candidate ----
         {
             const long long item = cand0 + wg;
-            const long long cand = (indexed && item < n_items) ? (long long)p.index[item] : item;
+            const long long cand = (mapped && item < n_items) ? (long long)p.index[item] : item;
             int status = -1;
             if (item < n_items) {
                 int len = p.len[cand];
@@ -1127,7 +1130,7 @@ validate_kernel(const ValidateParams p) {
         for (int c = 0; c < 4; ++c) {
             const int status = s_status[c];
             if (status != 0) continue;
-            const long long cand = indexed ? (long long)p.index[cand0 + c] : cand0 + c;
+            const long long cand = mapped ? (long long)p.index[cand0 + c] : cand0 + c;
             const unsigned uc = keep_in_register(smem_addr(smem + per_cand * (grp * 4 + c) + 5 * Lp));
             int n_fin = 0, n_vote = 0;
             double best_ratio = 0.0, best_S = 0.0, max_R = 0.0;
@@ -1219,7 +1222,7 @@ validate_kernel(const ValidateParams p) {
             const long long item = cand0 + c;
             const int status = s_status[c];
             if (item < n_items) {
-                const long long cand = indexed ? (long long)p.index[item] : item;
+                const long long cand = mapped ? (long long)p.index[item] : item;
                 WarpPartial t = s_part[c * 4];
                 if (status == 0) {
                     for (int w = 1; w < 4; ++w) {

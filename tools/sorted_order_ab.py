@@ -46,8 +46,26 @@ def be64(lo, hi):
     for j in range(hi - lo):
         k = (k << 8) | w[:, j]
     return k
+# the op SIGNATURE: leaves collapsed (coordinates -> 1, PRIM -> 8, constants -> 0x80): what decides the micro-op kinds
+raw = code
+sig = code.clone()
+sig[(code == 2)] = 1
+sig[(code >= 0x08) & (code < 0x10)] = 8
+sig[(code >= 0x80)] = 0x80
+
+
+def be64sig(lo, hi):
+    w = sig[:, lo:hi].to(torch.int64)
+    k = torch.zeros(n, dtype=torch.int64, device=dev)
+    for j in range(hi - lo):
+        k = (k << 8) | w[:, j]
+    return k
+
+
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for name, keys in (("sorted by leading 7 bytes", [be64(0, 7)]),
+for name, keys in (("sorted by op signature, bytes 0-27", [be64sig(21, 28), be64sig(14, 21), be64sig(7, 14), be64sig(0, 7)]),
+                   ("sorted by length only", [ln.to(torch.int64)]),
+                   ("sorted by op signature 0-41, then length", [ln.to(torch.int64), be64sig(35, 42), be64sig(28, 35), be64sig(21, 28), be64sig(14, 21), be64sig(7, 14), be64sig(0, 7)][::-1][::-1]),("sorted by leading 7 bytes", [be64(0, 7)]),
                    ("sorted by bytes 0-13", [be64(7, 14), be64(0, 7)]),
                    ("sorted by length, then bytes 0-13", [be64(7, 14), be64(0, 7), ln.to(torch.int64)]),
                    ("sorted by bytes 0-27", [be64(21, 28), be64(14, 21), be64(7, 14), be64(0, 7)])):
