@@ -289,6 +289,15 @@ int  pde_compile_residual_program(int jet_order, int n_cols, const double *const
  *   survivor_bits[(n+31)/32]  bit c = 1 iff candidate c is NOT rejected
  *   n_finite < 0: not evaluated (-1 empty program, -2 malformed, -3 needs more
  *   than `spill_slots` (1..8) spilled jets) -> survivor
+ *
+ * Every output is addressed by candidate and does not depend on which warp group
+ * evaluates a candidate or when: the library deals chunks of candidates to the
+ * groups dynamically and walks batches of 2^18 candidates or more in the order
+ * of their op signature (instruction-cache locality; work space from the
+ * library's stream-ordered pool, 24 B per candidate).  Environment switches
+ * for A/B measurements, read once per process: PDE_B200_NO_ORDER (keep the
+ * caller's order), PDE_B200_STATIC_DEAL (round-robin chunks); PDE_B200_PROFILE
+ * prints host-side phase timings to stderr.
  * ---------------------------------------------------------------------- */
 typedef struct pde_validate_out {
     double   *ratio_max;     /* [n] */
