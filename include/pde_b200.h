@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 5
+#define PDE_B200_ABI_VERSION 6
 
 /* ---- error codes ------------------------------------------------------- */
 #define PDE_OK            0
@@ -124,6 +124,11 @@ int  pde_compile_exprs(pde_session *s, const char *const *strs, int n, pde_exprs
  * thread count.  offsets may be NULL: the blob is then n NUL-terminated strings back to back and
  * the library finds the terminators itself. */
 int  pde_compile_exprs_packed(pde_session *s, const char *blob, const uint32_t *offsets, int n, pde_exprset **out);
+/* same, for a blob of KNOWN size that must hold exactly n NUL-terminated strings back to back (what
+ * travels between the ranks of a sharded batch): the library finds the terminators inside blob_bytes
+ * and fails with PDE_E_INVALID if there are fewer or more than n strings -- the caller need not scan
+ * the blob itself. */
+int  pde_compile_exprs_blob(pde_session *s, const char *blob, size_t blob_bytes, int n, pde_exprset **out);
 /* Frees the handle.  Its device mirrors (made by the first pde_enumerate* call, from the library's stream-ordered
  * pool) go back to the pool after the last enumerate kernel that read them has finished: no device-wide
  * synchronisation, safe to call while that work is still queued. */

@@ -59,6 +59,7 @@ _sig("pde_session_const_key", c_char_p, c_void_p, c_int)
 _sig("pde_session_pow_key", c_char_p, c_void_p, c_int)
 _sig("pde_compile_exprs", c_int, c_void_p, P(c_char_p), c_int, P(c_void_p))
 _sig("pde_compile_exprs_packed", c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p))
+_sig("pde_compile_exprs_blob", c_int, c_void_p, c_void_p, C.c_size_t, c_int, P(c_void_p))
 _sig("pde_exprset_free", None, c_void_p)
 _sig("pde_exprset_size", c_int, c_void_p, P(c_int), P(c_int), P(c_int))
 _sig("pde_exprset_export", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
@@ -91,7 +92,7 @@ _sig("pde_fp64_peak_3op", c_int, c_int, P(c_double), c_void_p)
 EXPORTED = [
     "pde_abi_version", "pde_last_error", "pde_device_count", "pde_launch_count",
     "pde_session_create", "pde_session_free", "pde_session_tables", "pde_session_const_key", "pde_session_pow_key",
-    "pde_compile_exprs", "pde_compile_exprs_packed", "pde_exprset_free", "pde_exprset_size", "pde_exprset_export", "pde_exprset_programs",
+    "pde_compile_exprs", "pde_compile_exprs_packed", "pde_compile_exprs_blob", "pde_exprset_free", "pde_exprset_size", "pde_exprset_export", "pde_exprset_programs",
     "pde_enumerate_count", "pde_enumerate", "pde_dedup", "pde_enumerate_csr_size", "pde_enumerate_csr", "pde_dedup_csr", "pde_synth_trees",
     "pde_compile_residual", "pde_compile_residual_program", "pde_program_free", "pde_program_info", "pde_program_point_table",
     "pde_validate", "pde_validate_csr", "pde_eval_points", "pde_fingerprint", "pde_fp64_peak", "pde_fp64_peak_3op",

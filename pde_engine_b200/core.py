@@ -116,12 +116,17 @@ class ExprSet:
         if blob is None:
             blob, n = pack_strings(strs)
         self.n = int(n)
-        # one blob of NUL-terminated strings; the library finds the terminators (offsets = NULL): building a ctypes
-        # array of 10^5 char pointers, or the offsets with numpy, costs more than compiling the strings
-        if blob.count(b"\0") != self.n or (self.n and not blob.endswith(b"\0")):
-            raise ValueError("expression strings must not contain NUL")
+        # one blob of NUL-terminated strings; the library finds the terminators inside len(blob) and checks that there
+        # are exactly n strings (pde_compile_exprs_blob): building a ctypes array of 10^5 char pointers, the offsets
+        # with numpy, or even bytes.count(b"\0") costs as much as compiling a good part of the strings
+        blob = bytes(blob) if not isinstance(blob, bytes) else blob
         h = C.c_void_p()
-        check(lib.pde_compile_exprs_packed(session._h, bytes(blob) if not isinstance(blob, bytes) else blob, None, self.n, C.byref(h)))
+        rc = lib.pde_compile_exprs_blob(session._h, blob, len(blob), self.n, C.byref(h))
+        if rc == -1:        # PDE_E_INVALID: not exactly n NUL-terminated strings
+            msg = (lib.pde_last_error() or b"").decode(errors="replace")
+            if "strings expected" in msg:
+                raise ValueError("expression strings must not contain NUL (" + msg + ")")
+        check(rc)
         if self.n:
             got = C.c_int()
             check(lib.pde_exprset_size(h, C.byref(got), None, None))

@@ -696,6 +696,26 @@ int pde_compile_exprs(pde_session* s, const char* const* strs, int n, pde_exprse
     return compile_impl(s, blob.data(), off.data(), n, out);
 }
 
+int pde_compile_exprs_blob(pde_session* s, const char* blob, size_t blob_bytes, int n, pde_exprset** out) {
+    if (!s || !out || n < 0 || (n > 0 && !blob)) { pde::set_error("pde_compile_exprs_blob: bad argument"); return PDE_E_INVALID; }
+    if (blob_bytes >= 0xffffffffULL) { pde::set_error("pde_compile_exprs_blob: input too large"); return PDE_E_OVERFLOW; }
+    // exactly n NUL-terminated strings in blob_bytes bytes: the terminators are found here, inside the size the caller
+    // states (memchr at memory speed; counting them in Python -- bytes.count -- cost 3-8 ms for the 4.7 MB of the depth-4
+    // uniques, as much as parsing a quarter of them)
+    std::vector<uint32_t> found((size_t)n + 1);
+    const char* p = blob;
+    const char* end = blob + blob_bytes;
+    for (int i = 0; i < n; ++i) {
+        found[i] = (uint32_t)(p - blob);
+        const char* q = p < end ? (const char*)memchr(p, 0, (size_t)(end - p)) : nullptr;
+        if (!q) { pde::set_error("pde_compile_exprs_blob: %d strings expected, the blob holds %d", n, i); return PDE_E_INVALID; }
+        p = q + 1;
+    }
+    found[n] = (uint32_t)(p - blob);
+    if (p != end) { pde::set_error("pde_compile_exprs_blob: the blob holds more than the %d strings expected (a string with a NUL inside?)", n); return PDE_E_INVALID; }
+    return pde_compile_exprs_packed(s, blob, found.data(), n, out);
+}
+
 int pde_compile_exprs_packed(pde_session* s, const char* blob, const uint32_t* offsets, int n, pde_exprset** out) {
     if (!s || !out || n < 0 || (n > 0 && !blob)) { pde::set_error("pde_compile_exprs_packed: bad argument"); return PDE_E_INVALID; }
     std::vector<uint32_t> found;

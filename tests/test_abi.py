@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib.pde_abi_version() == 5
+    assert _lib.lib.pde_abi_version() == 6
 
 
 def test_opcode_tables_agree():
