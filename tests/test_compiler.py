@@ -102,3 +102,22 @@ def test_empty_batch_compiles():
     assert es.sizes() == (0, 0, 0)
     code, ln = es.programs(16)
     assert code.shape == (0, 16) and ln.shape == (0,)
+
+
+def test_blob_entry_counts_the_strings_itself():
+    """pde_compile_exprs_blob: a blob of known size must hold exactly n NUL-terminated strings -- fewer, more (a NUL
+    inside a string), or a missing last terminator are errors, never an over-read; the bytecode equals the list entry's."""
+    import pde_engine_b200 as pb
+    from pde_engine_b200 import core
+    sess = pb.Session.for_problem("force_free")
+    strs = ["rho**2*z", "", "rho/z + 3", "sqrt(rho**2 + z**2) - z"]
+    blob, n = core.pack_strings(strs)
+    a, b = sess.compile(strs).export(), sess.compile_blob(blob, n).export()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    for bad_blob, bad_n in ((blob, n + 1), (blob, n - 1), (blob[:-1], n), (b"rho\0\0z\0", 2), (b"", 1)):
+        with pytest.raises(ValueError):
+            sess.compile_blob(bad_blob, bad_n)
+    assert sess.compile_blob(b"", 0).n == 0
+    with pytest.raises(ValueError):
+        sess.compile(["rho\0z"])
