@@ -512,6 +512,7 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
             f0 = f1;
         }
     }
+    auto t_b1 = tnow();
     // B2: sizes per worker (expressions flagged in B1 contribute nothing), exclusive offsets
     std::vector<size_t> pool_base(nthreads + 1, 0), term_base(nthreads + 1, 0);
     for (int t = 0; t < nthreads; ++t) {
@@ -529,6 +530,7 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     e->term_sign.resize(term_base[nthreads]);
     e->term_off.resize(term_base[nthreads] + 1);
     e->term_off[0] = 0;
+    auto t_b2 = tnow();
     // B3: copy (parallel)
     auto assemble = [&](int t) {
         Worker& w = workers[t];
@@ -560,8 +562,9 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     e->term_begin[n] = (uint32_t)term_base[nthreads];
     if (prof) {
         auto t_c = tnow();
-        fprintf(stderr, "[pde_compile] n=%d threads=%d parse %.2f ms, slots+assembly %.2f ms\n", n, nthreads,
-                std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count());
+        fprintf(stderr, "[pde_compile] n=%d threads=%d parse %.2f ms, slots+assembly %.2f ms (B1 %.2f B2 %.2f B3 %.2f)\n", n, nthreads,
+                std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count(),
+                std::chrono::duration<double, std::milli>(t_b1 - t_b).count(), std::chrono::duration<double, std::milli>(t_b2 - t_b1).count(), std::chrono::duration<double, std::milli>(t_c - t_b2).count());
     }
     *out = e.release();
     return PDE_OK;
