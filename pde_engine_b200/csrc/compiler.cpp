@@ -380,8 +380,12 @@ static bool has_vars(const char* s) {
 }
 
 // ---- parallel front end: one worker per contiguous range of strings ----
+static int table_find(const pde_session* s, const Fix& f);
+constexpr uint32_t kFixResolved = 0xffffffffu;     // Fix::pos of a placeholder whose slot phase A already wrote
+
 struct Worker {
     int lo = 0, hi = 0;
+    std::vector<int> pending;           // expressions with a constant / exponent that is not in the tables yet (phase B1)
     std::vector<uint8_t> pool;
     std::vector<int8_t> term_sign;
     std::vector<uint32_t> term_off;     // end offset (in `pool`) of every term
@@ -420,6 +424,18 @@ struct Worker {
                 flags[k] = PDE_FLAG_UNSUPPORTED;
             }
             if (flags[k]) { wp = wp0; term_sign.resize(nt0); term_off.resize(nt0); fixes.resize(nf0); }
+            else {
+                // constants / exponents the session tables already hold get their slot here, in parallel (the tables are
+                // read-only during phase A); only NEW keys wait for the sequential numbering of phase B1
+                bool wait = false;
+                for (size_t f = nf0; f < fixes.size(); ++f) {
+                    const int slot = table_find(sess, fixes[f]);
+                    if (slot < 0) { wait = true; continue; }
+                    base[fixes[f].pos] = (uint8_t)((fixes[f].is_pow ? PDE_OP_POW0 : PDE_OP_CONST0) + slot);
+                    fixes[f].pos = kFixResolved;
+                }
+                if (wait) pending.push_back(k);
+            }
             n_terms[k] = (uint32_t)(term_sign.size() - nt0);
             pool_end[k] = (uint32_t)(wp - base);
             fix_end[k] = (uint32_t)fixes.size();
@@ -433,26 +449,45 @@ struct Worker {
     }
 };
 
+// numeric mirror of a key table (numerator, denominator; denominator 0 = named constant index), rebuilt when its size
+// differs from the key table's
+static void ensure_mirror(pde_session* s, bool is_pow) {
+    std::vector<std::string>& keys = is_pow ? s->pow_keys : s->const_keys;
+    std::vector<long long>& num = is_pow ? s->pow_num : s->const_num;
+    std::vector<long long>& den = is_pow ? s->pow_den : s->const_den;
+    if (num.size() == keys.size() && den.size() == keys.size()) return;
+    num.assign(keys.size(), 0); den.assign(keys.size(), -1);
+    for (size_t i = 0; i < keys.size(); ++i) {
+        const std::string& k = keys[i];
+        bool named = false;
+        for (size_t j = 0; j < s->named.size() && !is_pow; ++j) if (s->named[j] == k) { num[i] = (long long)j; den[i] = 0; named = true; }
+        if (named) continue;
+        const size_t sl = k.find('/');
+        num[i] = atoll(k.c_str());
+        den[i] = sl == std::string::npos ? 1 : atoll(k.c_str() + sl + 1);
+    }
+}
+
+// slot of a constant / exponent that is ALREADY in the session tables, or -1 (read-only: phase A calls it from every
+// worker while nobody appends)
+static int table_find(const pde_session* s, const Fix& f) {
+    const std::vector<long long>& num = f.is_pow ? s->pow_num : s->const_num;
+    const std::vector<long long>& den = f.is_pow ? s->pow_den : s->const_den;
+    const long long fn = f.num, fd = f.named ? 0 : f.den;
+    for (size_t i = 0; i < num.size(); ++i) if (num[i] == fn && den[i] == fd) return (int)i;
+    return -1;
+}
+
 // slot of a constant / exponent in the session tables; appends; -1 = table full
 static int table_slot(pde_session* s, const Fix& f) {
     std::vector<std::string>& keys = f.is_pow ? s->pow_keys : s->const_keys;
     std::vector<double>& vals = f.is_pow ? s->pow_vals : s->const_vals;
     std::vector<long long>& num = f.is_pow ? s->pow_num : s->const_num;
     std::vector<long long>& den = f.is_pow ? s->pow_den : s->const_den;
-    if (num.size() != keys.size()) {        // (re)build the numeric mirror of the keys
-        num.assign(keys.size(), 0); den.assign(keys.size(), -1);
-        for (size_t i = 0; i < keys.size(); ++i) {
-            const std::string& k = keys[i];
-            bool named = false;
-            for (size_t j = 0; j < s->named.size() && !f.is_pow; ++j) if (s->named[j] == k) { num[i] = (long long)j; den[i] = 0; named = true; }
-            if (named) continue;
-            const size_t sl = k.find('/');
-            num[i] = atoll(k.c_str());
-            den[i] = sl == std::string::npos ? 1 : atoll(k.c_str() + sl + 1);
-        }
-    }
+    ensure_mirror(s, f.is_pow);
+    const int hit = table_find(s, f);
+    if (hit >= 0) return hit;
     const long long fn = f.num, fd = f.named ? 0 : f.den;
-    for (size_t i = 0; i < num.size(); ++i) if (num[i] == fn && den[i] == fd) return (int)i;
     const int cap = f.is_pow ? PDE_N_POW : PDE_N_CONST;
     if ((int)keys.size() >= cap) return -1;
     if (f.named) { keys.push_back(s->named[f.num]); vals.push_back(s->named_vals[f.num]); }
@@ -472,7 +507,9 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     const bool prof = getenv("PDE_B200_PROFILE") != nullptr;
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto t_a = tnow();
-    // ---- phase A (parallel): parse + emit with deferred table slots ----
+    // ---- phase A (parallel): parse + emit; slots of keys the tables already hold, deferred slots for new keys ----
+    ensure_mirror(s, false);
+    ensure_mirror(s, true);
     int nthreads = 1;
     if (const char* ev = getenv("PDE_B200_COMPILE_THREADS")) nthreads = atoi(ev);
     else nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
@@ -491,25 +528,23 @@ static int compile_impl(pde_session* s, const char* blob, const uint32_t* off, i
     auto t_b = tnow();
     // ---- phase B: table slots (sequential, in expression order -- the numbering is part of the bytecode), then the
     //      assembly of the pools at precomputed offsets (parallel again) ----
-    // B1: slots.  Only the CONST / POW placeholders are visited; an expression whose constants do not fit the
-    //     tables any more is flagged and its slots are rolled back (tables stay append-only for successful compiles).
+    // B1: slots of NEW keys.  Only the expressions phase A left pending are visited (none once a session has seen its
+    //     constants); an expression whose constants do not fit the tables any more is flagged and its slots are rolled
+    //     back (tables stay append-only for successful compiles).
     for (auto& w : workers) {
-        uint32_t f0 = 0;
-        for (int k = 0; k < w.hi - w.lo; ++k) {
-            const uint32_t f1 = w.fix_end[k];
-            if (!w.flags[k] && f1 > f0) {
-                const size_t nc0 = s->const_keys.size(), np0 = s->pow_keys.size();
-                for (uint32_t f = f0; f < f1; ++f) {
-                    const int slot = table_slot(s, w.fixes[f]);
-                    if (slot < 0) { w.flags[k] = PDE_FLAG_TABLE_FULL; break; }
-                    w.pool[w.fixes[f].pos] = (uint8_t)((w.fixes[f].is_pow ? PDE_OP_POW0 : PDE_OP_CONST0) + slot);
-                }
-                if (w.flags[k]) {
-                    s->const_keys.resize(nc0); s->const_vals.resize(nc0); s->const_num.resize(nc0); s->const_den.resize(nc0);
-                    s->pow_keys.resize(np0); s->pow_vals.resize(np0); s->pow_num.resize(np0); s->pow_den.resize(np0);
-                }
+        for (const int k : w.pending) {
+            const uint32_t f0 = k > 0 ? w.fix_end[k - 1] : 0u, f1 = w.fix_end[k];
+            const size_t nc0 = s->const_keys.size(), np0 = s->pow_keys.size();
+            for (uint32_t f = f0; f < f1; ++f) {
+                if (w.fixes[f].pos == kFixResolved) continue;
+                const int slot = table_slot(s, w.fixes[f]);
+                if (slot < 0) { w.flags[k] = PDE_FLAG_TABLE_FULL; break; }
+                w.pool[w.fixes[f].pos] = (uint8_t)((w.fixes[f].is_pow ? PDE_OP_POW0 : PDE_OP_CONST0) + slot);
             }
-            f0 = f1;
+            if (w.flags[k]) {
+                s->const_keys.resize(nc0); s->const_vals.resize(nc0); s->const_num.resize(nc0); s->const_den.resize(nc0);
+                s->pow_keys.resize(np0); s->pow_vals.resize(np0); s->pow_num.resize(np0); s->pow_den.resize(np0);
+            }
         }
     }
     auto t_b1 = tnow();

@@ -121,3 +121,31 @@ def test_blob_entry_counts_the_strings_itself():
     assert sess.compile_blob(b"", 0).n == 0
     with pytest.raises(ValueError):
         sess.compile(["rho\0z"])
+
+
+def test_warm_session_gives_the_same_bytecode(enum_ff, monkeypatch):
+    """Keys the session tables already hold get their slots in the parallel parse phase, only new keys wait for the
+    sequential numbering: a batch compiled in pieces (the later pieces into a warm session), in one piece, or again into
+    the warm session gives the same programs and the same tables -- also when the table fills up on the way."""
+    import pde_engine_b200 as pb
+    E = uniques_by_depth(enum_ff)
+    a = E[4][:20000] + [f"{k}*rho + z/{k + 1}" for k in range(2, 60)]
+    b = E[4][20000:40000] + [f"{k}*rho + z/{k + 1}" for k in range(40, 140)] + E[3][:500]
+    for threads in ("1", "5"):
+        monkeypatch.setenv("PDE_B200_COMPILE_THREADS", threads)
+        one = pb.Session.for_problem("force_free")
+        whole = one.compile(a + b)
+        cw, lw = whole.programs(128)
+        fw = whole.flags()
+        two = pb.Session.for_problem("force_free")
+        ea, eb = two.compile(a), two.compile(b)
+        ca, la = ea.programs(128)
+        cb, lb = eb.programs(128)
+        assert np.array_equal(np.concatenate([ca, cb]), cw) and np.array_equal(np.concatenate([la, lb]), lw)
+        assert np.array_equal(np.concatenate([ea.flags(), eb.flags()]), fw)
+        assert (fw == 2).sum() > 10                                     # the constant table did fill in `b`
+        assert two.const_keys() == one.const_keys() and two.pow_keys() == one.pow_keys()
+        again = two.compile(a + b)                                      # everything known (or known not to fit)
+        c2, l2 = again.programs(128)
+        assert np.array_equal(c2, cw) and np.array_equal(l2, lw) and np.array_equal(again.flags(), fw)
+        assert two.const_keys() == one.const_keys()
